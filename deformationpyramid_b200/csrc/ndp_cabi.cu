@@ -1,0 +1,500 @@
+// C ABI of libndp_b200.so (include/ndp_b200.h): argument checking, workspace carving and the
+// host-side orchestration of the kernels.  No torch types, no CPU fallback.
+#include "../../include/ndp_b200.h"
+#include "ndp_kernels.h"
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (cudaError_t)(call);                                             \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(NDP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));  \
+    } while (0)
+
+extern "C" const char* ndp_last_error(void) { return g_err.c_str(); }
+extern "C" int32_t ndp_version(void) { return 100; }
+
+static int init_once() {
+    static std::once_flag once;
+    static int rc = 0;
+    std::call_once(once, [] {
+        int e = ndp_fwd_init();
+        if (e == 0) e = ndp_bwd_init();
+        rc = e;
+    });
+    if (rc != 0) return fail(NDP_E_CUDA, std::string("kernel init: ") + cudaGetErrorString((cudaError_t)rc));
+    return NDP_OK;
+}
+
+static int check_cfg(const ndp_layer_cfg* c) {
+    if (!c) return fail(NDP_E_INVALID, "cfg is NULL");
+    if (c->width != NDP_W) return fail(NDP_E_INVALID, "this build supports width 128 only");
+    if (c->depth < 1 || c->depth > NDP_MAX_HIDDEN + 1) return fail(NDP_E_INVALID, "depth must be in [1, 9]");
+    if (c->motion < 0 || c->motion > 2) return fail(NDP_E_INVALID, "motion must be SE3, Sim3 or sflow");
+    if (c->rot_format < 0 || c->rot_format > 3) return fail(NDP_E_INVALID, "unknown rotation format");
+    return NDP_OK;
+}
+static NdpLayout layout_of(const ndp_layer_cfg* c) {
+    return ndp_make_layout(c->depth, c->motion, c->rot_format, c->nonrigidity, c->freq, c->mlp_scale);
+}
+static bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+static long long pad4(long long v) { return (v + 3) / 4 * 4; }
+static long long pad256(long long v) { return (v + 255) / 256 * 256; }
+
+extern "C" int64_t ndp_param_count(const ndp_layer_cfg* c) { return check_cfg(c) ? -1 : layout_of(c).param_count; }
+extern "C" int64_t ndp_pack_count(const ndp_layer_cfg* c) { return check_cfg(c) ? -1 : layout_of(c).pack_count; }
+extern "C" int64_t ndp_saved_floats_per_point(const ndp_layer_cfg* c) {
+    return check_cfg(c) ? -1 : (int64_t)c->depth * NDP_W + NDP_ZPITCH;
+}
+extern "C" int64_t ndp_backward_workspace_bytes(const ndp_layer_cfg* c, int64_t n) {
+    if (check_cfg(c)) return -1;
+    const long long tiles = n > 0 ? (n + NDP_TP - 1) / NDP_TP : 1;
+    return tiles * pad4(layout_of(c).param_count) * (long long)sizeof(float);
+}
+
+// ---- nearest-neighbour launch plan -------------------------------------------------------------
+struct NnPlan { int chunk_targets, chunks, qpitch, blocks; };
+static NnPlan nn_plan(long long n, long long m) {
+    NnPlan p;
+    const long long big = n > m ? n : m;
+    long long k = (big + 16LL * NDP_NN_TS - 1) / (16LL * NDP_NN_TS);
+    if (k < 1) k = 1;
+    p.chunk_targets = (int)(k * NDP_NN_TS);
+    p.chunks = (int)((big + p.chunk_targets - 1) / p.chunk_targets);
+    if (p.chunks < 1) p.chunks = 1;
+    p.qpitch = (int)pad4(big);
+    p.blocks = (int)((big + 255) / 256);
+    if (p.blocks < 1) p.blocks = 1;
+    return p;
+}
+struct ChamferWs { long long part, gacc, sums, counter, total; };
+static ChamferWs chamfer_ws(long long n, long long m) {
+    NnPlan p = nn_plan(n, m);
+    ChamferWs w;
+    long long o = 0;
+    w.part = o; o += pad256(2LL * p.chunks * p.qpitch * (long long)sizeof(float2));
+    w.gacc = o; o += pad256(n * 3 * 8);
+    w.sums = o; o += pad256((long long)p.blocks * 2 * 8);
+    w.counter = o; o += 256;
+    w.total = o;
+    return w;
+}
+extern "C" int64_t ndp_chamfer_workspace_bytes(int64_t n, int64_t m) {
+    if (n < 0 || m < 0) return -1;
+    return chamfer_ws(n, m).total;
+}
+
+extern "C" int ndp_pack_params(const ndp_layer_cfg* c, const float* params, float* pack, void* stream) {
+    if (int e = check_cfg(c)) return e;
+    if (!params || !pack) return fail(NDP_E_INVALID, "NULL buffer");
+    NdpPackArgs a; a.lay = layout_of(c); a.params = params; a.params_stride = 0; a.pack = pack; a.pack_stride = 0; a.npairs = 1;
+    ndp_launch_pack(a, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return NDP_OK;
+}
+
+extern "C" int ndp_layer_forward(const ndp_layer_cfg* c, const float* params, const float* pack, const float* x,
+                                 int64_t n, float* y, float* nu, float* saved, void* stream) {
+    if (int e = check_cfg(c)) return e;
+    if (int e = init_once()) return e;
+    if (n < 0 || n > 0x7fffffff / 4) return fail(NDP_E_INVALID, "bad point count");
+    if (n == 0) return NDP_OK;
+    if (!params || !pack || !x || !y) return fail(NDP_E_INVALID, "NULL buffer");
+    if (!aligned16(params) || !aligned16(pack) || (saved && !aligned16(saved)))
+        return fail(NDP_E_INVALID, "params, pack and saved must be 16-byte aligned");
+    NdpFwdArgs a;
+    a.lay = layout_of(c);
+    a.params = params; a.params_stride = 0; a.pack = pack; a.pack_stride = 0;
+    a.x = x; a.x_stride = 0; a.y = y; a.y_stride = 0; a.nu = nu; a.nu_stride = 0;
+    a.act = saved; a.act_stride = 0; a.act_layer_stride = n * NDP_W;
+    a.zsave = saved ? saved + (long long)c->depth * n * NDP_W : nullptr; a.z_stride = 0;
+    a.y_add = nullptr; a.y_add_stride = 0; a.n = (int)n; a.counts = nullptr; a.state = nullptr; a.npairs = 1;
+    ndp_launch_fwd(a, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return NDP_OK;
+}
+
+extern "C" int ndp_layer_backward(const ndp_layer_cfg* c, const float* params, const float* x, int64_t n,
+                                  const float* saved, const float* grad_y, const float* grad_nu,
+                                  float* grad_params, float* grad_x, void* workspace, void* stream) {
+    if (int e = check_cfg(c)) return e;
+    if (int e = init_once()) return e;
+    if (n <= 0 || n > 0x7fffffff / 4) return fail(NDP_E_INVALID, "bad point count");
+    if (!params || !x || !saved || !grad_y || !grad_params || !workspace) return fail(NDP_E_INVALID, "NULL buffer");
+    if (!aligned16(params) || !aligned16(saved) || !aligned16(workspace))
+        return fail(NDP_E_INVALID, "params, saved and workspace must be 16-byte aligned");
+    NdpLayout L = layout_of(c);
+    NdpBwdArgs b;
+    b.lay = L; b.params = params; b.params_stride = 0; b.x = x; b.x_stride = 0;
+    b.act = saved; b.act_stride = 0; b.act_layer_stride = n * NDP_W;
+    b.zsave = saved + (long long)c->depth * n * NDP_W; b.z_stride = 0;
+    b.gy = grad_y; b.gy_stride = 0; b.gacc = nullptr; b.gacc_stride = 0; b.m = 1; b.mcounts = nullptr;
+    b.gnu = grad_nu; b.gnu_stride = 0;
+    b.partials = (float*)workspace; b.partials_stride = 0; b.partial_pitch = (int)pad4(L.param_count);
+    b.gx = grad_x; b.gx_stride = 0; b.n = (int)n; b.counts = nullptr; b.state = nullptr; b.npairs = 1;
+    ndp_launch_bwd(b, (cudaStream_t)stream);
+    NdpAdamArgs r;
+    r.lay = L; r.params = nullptr; r.params_stride = 0; r.pack = nullptr; r.pack_stride = 0;
+    r.m = nullptr; r.v = nullptr; r.mv_stride = 0;
+    r.partials = (const float*)workspace; r.partials_stride = 0; r.partial_pitch = b.partial_pitch;
+    r.n = (int)n; r.counts = nullptr; r.grads_out = grad_params; r.grads_stride = 0; r.state = nullptr;
+    r.fixed_step = 0; r.lr = r.beta1 = r.beta2 = r.eps = 0.0; r.do_adam = 0; r.npairs = 1;
+    ndp_launch_adam(r, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return NDP_OK;
+}
+
+extern "C" int ndp_chamfer(const float* x, int64_t n, const float* y, int64_t m, float trunc, float grad_scale,
+                           float* loss, float* grad_x, float* d2_x, int64_t* idx_x, float* d2_y, int64_t* idx_y,
+                           void* workspace, void* stream) {
+    if (n < 1 || m < 1 || n > (1 << 27) || m > (1 << 27)) return fail(NDP_E_INVALID, "clouds must hold 1..2^27 points");
+    if (!x || !y || !loss || !grad_x || !workspace) return fail(NDP_E_INVALID, "NULL buffer");
+    if ((d2_x == nullptr) != (idx_x == nullptr) || (d2_y == nullptr) != (idx_y == nullptr))
+        return fail(NDP_E_INVALID, "d2/idx outputs must be given in pairs");
+    if (!aligned16(workspace)) return fail(NDP_E_INVALID, "workspace must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    NnPlan p = nn_plan(n, m);
+    ChamferWs w = chamfer_ws(n, m);
+    char* ws = (char*)workspace;
+    CK(cudaMemsetAsync(ws + w.gacc, 0, (size_t)(w.total - w.gacc), st));   // accumulators, sums, counter
+    NdpChamferArgs a;
+    a.nn.x = x; a.nn.x_stride = 0; a.nn.n = (int)n; a.nn.ncounts = nullptr;
+    a.nn.y = y; a.nn.y_stride = 0; a.nn.m = (int)m; a.nn.mcounts = nullptr;
+    a.nn.part = (float2*)(ws + w.part); a.nn.part_pair_stride = 0;
+    a.nn.qpitch = p.qpitch; a.nn.chunks = p.chunks; a.nn.chunk_targets = p.chunk_targets;
+    a.nn.state = nullptr; a.nn.npairs = 1;
+    a.trunc = trunc; a.gx = grad_x; a.gx_stride = 0;
+    a.gacc = (unsigned long long*)(ws + w.gacc); a.gacc_stride = 0;
+    a.d2x = d2_x; a.idxx = (long long*)idx_x; a.nx_stride = 0;
+    a.d2y = d2_y; a.idxy = (long long*)idx_y; a.ny_stride = 0;
+    a.blocksums = (double*)(ws + w.sums); a.blocks_pitch = p.blocks;
+    a.counters = (int*)(ws + w.counter); a.loss_out = loss; a.state = nullptr;
+    a.loss_hist = nullptr; a.hist_stride = 0; a.hist_cap = 0; a.max_break_count = 0; a.break_ratio = 0.0;
+    ndp_launch_nn(a.nn, st);
+    ndp_launch_chamfer_reduce(a, st);
+    NdpGradFinalizeArgs f;
+    f.gx = grad_x; f.gx_stride = 0; f.gacc = a.gacc; f.gacc_stride = 0;
+    f.n = (int)n; f.ncounts = nullptr; f.m = (int)m; f.mcounts = nullptr; f.scale = grad_scale; f.npairs = 1;
+    ndp_launch_grad_finalize(f, st);
+    CK(cudaGetLastError());
+    return NDP_OK;
+}
+
+extern "C" int ndp_adam_step(const ndp_layer_cfg* c, float* params, const float* grads, float* exp_avg,
+                             float* exp_avg_sq, int64_t count, int32_t step, double lr, double beta1, double beta2,
+                             double eps, float* pack, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq) return fail(NDP_E_INVALID, "NULL buffer");
+    if (step < 1) return fail(NDP_E_INVALID, "step is 1-based");
+    NdpAdamArgs r;
+    if (pack) {
+        if (int e = check_cfg(c)) return e;
+        r.lay = layout_of(c);
+        if (count != r.lay.param_count) return fail(NDP_E_INVALID, "count does not match cfg");
+    } else {
+        r.lay = ndp_make_layout(1, NDP_MOTION_SFLOW, 0, 0, 1.0f, 1.0f);
+        r.lay.hidden = 0; r.lay.off_b_in = 0;
+        if (count < 0 || count > 0x7fffffff) return fail(NDP_E_INVALID, "bad count");
+        r.lay.param_count = (int)count;
+    }
+    r.params = params; r.params_stride = 0; r.pack = pack; r.pack_stride = 0;
+    r.m = exp_avg; r.v = exp_avg_sq; r.mv_stride = 0;
+    r.partials = grads; r.partials_stride = 0; r.partial_pitch = 0; r.n = 0; r.counts = nullptr;
+    r.grads_out = nullptr; r.grads_stride = 0; r.state = nullptr; r.fixed_step = step;
+    r.lr = lr; r.beta1 = beta1; r.beta2 = beta2; r.eps = eps; r.do_adam = 1; r.npairs = 1;
+    ndp_launch_adam(r, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return NDP_OK;
+}
+
+// =================================================================================================
+// Fused per-pair driver
+// =================================================================================================
+struct ndp_solver {
+    ndp_solver_cfg cfg;
+    std::vector<NdpLayout> lay;
+    int P, Ppad, packn, tiles, B, S, NS, NT;
+    NnPlan plan;
+    // device
+    float *src_raw = nullptr, *tgt_raw = nullptr, *src_c = nullptr, *wbuf[2] = {nullptr, nullptr};
+    float *means = nullptr, *smp[2] = {nullptr, nullptr}, *tsmp = nullptr;
+    int *perm_s = nullptr, *perm_t = nullptr, *ncount = nullptr, *mcount = nullptr, *nscount = nullptr, *ntcount = nullptr;
+    float *params = nullptr, *pack = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+    float *act = nullptr, *zsave = nullptr, *gx = nullptr, *partials = nullptr, *loss = nullptr, *loss_hist = nullptr;
+    unsigned long long* gacc = nullptr;
+    float2* nnpart = nullptr;
+    double* blocksums = nullptr;
+    int* counters = nullptr;
+    NdpPairState* state = nullptr;
+    // host (pinned)
+    NdpPairState* h_state = nullptr;
+    int* h_counts = nullptr;
+    long long launches = 0;
+    std::vector<void*> allocs;
+};
+
+template <class T> static int dalloc(ndp_solver* s, T** p, long long count) {
+    void* q = nullptr;
+    if (cudaMalloc(&q, (size_t)(count > 0 ? count : 1) * sizeof(T)) != cudaSuccess) return fail(NDP_E_NOMEM, "cudaMalloc failed");
+    s->allocs.push_back(q);
+    *p = (T*)q;
+    return NDP_OK;
+}
+
+extern "C" void ndp_solver_destroy(ndp_solver* s) {
+    if (!s) return;
+    for (void* p : s->allocs) cudaFree(p);
+    if (s->h_state) cudaFreeHost(s->h_state);
+    if (s->h_counts) cudaFreeHost(s->h_counts);
+    delete s;
+}
+
+extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
+    if (!c || !out) return fail(NDP_E_INVALID, "NULL argument");
+    if (int e = init_once()) return e;
+    ndp_layer_cfg lc{c->width, c->depth, c->motion, c->rot_format, 0, 1.0f, 0.001f};
+    if (int e = check_cfg(&lc)) return e;
+    if (c->max_pairs < 1 || c->samples < 1 || c->levels < 1 || c->iters < 0 || c->max_src_points < 1 || c->max_tgt_points < 1)
+        return fail(NDP_E_INVALID, "bad solver sizes");
+    ndp_solver* s = new ndp_solver();
+    s->cfg = *c;
+    for (int l = 0; l < c->levels; ++l)   // Deformation_Pyramid.__init__, nets.py:20-30: level i has m = i+1
+        s->lay.push_back(ndp_make_layout(c->depth, c->motion, c->rot_format, 0, ldexpf(1.0f, l + 1 + c->k0), 0.001f));
+    s->P = s->lay[0].param_count; s->Ppad = (int)pad4(s->P); s->packn = s->lay[0].pack_count;
+    s->B = c->max_pairs; s->S = c->samples; s->NS = c->max_src_points; s->NT = c->max_tgt_points;
+    s->tiles = (s->S + NDP_TP - 1) / NDP_TP;
+    s->plan = nn_plan(s->S, s->S);
+    const long long B = s->B, S = s->S;
+    int e = NDP_OK;
+#define DA(ptr, count) if (!e) e = dalloc(s, &s->ptr, (count))
+    DA(src_raw, B * s->NS * 3); DA(tgt_raw, B * s->NT * 3); DA(src_c, B * s->NS * 3);
+    DA(wbuf[0], B * s->NS * 3); DA(wbuf[1], B * s->NS * 3);
+    DA(means, B * 6); DA(smp[0], B * S * 3); DA(smp[1], B * S * 3); DA(tsmp, B * S * 3);
+    DA(perm_s, B * S); DA(perm_t, B * S); DA(ncount, B); DA(mcount, B); DA(nscount, B); DA(ntcount, B);
+    DA(params, B * c->levels * s->Ppad); DA(pack, B * s->packn); DA(adam_m, B * s->Ppad); DA(adam_v, B * s->Ppad);
+    DA(act, B * c->depth * S * NDP_W); DA(zsave, B * S * NDP_ZPITCH); DA(gx, B * S * 3); DA(gacc, B * S * 3);
+    DA(partials, B * s->tiles * s->Ppad); DA(loss, B);
+    DA(nnpart, B * 2 * s->plan.chunks * s->plan.qpitch); DA(blocksums, B * s->plan.blocks * 2); DA(counters, B);
+    DA(state, B);
+    if (c->record_loss) DA(loss_hist, B * c->levels * (long long)c->iters);
+#undef DA
+    if (!e && cudaMallocHost((void**)&s->h_state, sizeof(NdpPairState) * B) != cudaSuccess) e = fail(NDP_E_NOMEM, "cudaMallocHost failed");
+    if (!e && cudaMallocHost((void**)&s->h_counts, sizeof(int) * B * 4) != cudaSuccess) e = fail(NDP_E_NOMEM, "cudaMallocHost failed");
+    if (!e && cudaMemset(s->counters, 0, sizeof(int) * B) != cudaSuccess) e = fail(NDP_E_CUDA, "cudaMemset failed");
+    if (!e && cudaMemset(s->gacc, 0, 8 * B * S * 3) != cudaSuccess) e = fail(NDP_E_CUDA, "cudaMemset failed");
+    if (e) { ndp_solver_destroy(s); return e; }
+    *out = s;
+    return NDP_OK;
+}
+
+extern "C" int64_t ndp_solver_params_per_pair(const ndp_solver* s) { return s ? (int64_t)s->cfg.levels * s->P : -1; }
+extern "C" int64_t ndp_solver_launch_count(const ndp_solver* s) { return s ? s->launches : -1; }
+
+// Optimise all levels for the npairs pairs whose raw clouds / perms / params are already in the
+// solver's device buffers; leaves the warped full clouds in s->wbuf[final] and returns which.
+static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_perm_t, int32_t* iters_out,
+                      float* loss_out, cudaStream_t st, int* final_buf) {
+    const ndp_solver_cfg& c = s->cfg;
+    const long long S = s->S;
+    // centring (registration.py:150-153) and sub-sampling (:156-159)
+    NdpCenterArgs ce;
+    ce.src = s->src_raw; ce.src_stride = (long long)s->NS * 3; ce.ns = s->NS; ce.nscounts = s->nscount;
+    ce.tgt = s->tgt_raw; ce.tgt_stride = (long long)s->NT * 3; ce.nt = s->NT; ce.ntcounts = s->ntcount;
+    ce.means = s->means; ce.npairs = npairs;
+    ndp_launch_means(ce, st);
+    NdpGatherArgs g;
+    g.means = s->means; g.npairs = npairs;
+    g.in = s->src_raw; g.in_stride = (long long)s->NS * 3; g.idx = nullptr; g.idx_stride = 0; g.which = 0;
+    g.out = s->src_c; g.out_stride = (long long)s->NS * 3; g.n = s->NS; g.counts = s->nscount;
+    ndp_launch_gather_center(g, st);
+    g.idx = have_perm_s ? s->perm_s : nullptr; g.idx_stride = S;
+    g.out = s->smp[0]; g.out_stride = S * 3; g.n = s->S; g.counts = s->ncount;
+    ndp_launch_gather_center(g, st);
+    g.in = s->tgt_raw; g.in_stride = (long long)s->NT * 3; g.idx = have_perm_t ? s->perm_t : nullptr; g.which = 1;
+    g.out = s->tsmp; g.counts = s->mcount;
+    ndp_launch_gather_center(g, st);
+    s->launches += 4;
+
+    int cur = 0;
+    const int poll = (c.max_break_count > c.iters) ? 64 : 8;
+    for (int level = 0; level < c.levels; ++level) {
+        const NdpLayout& L = s->lay[level];
+        float* lvl_params = s->params + (long long)level * s->Ppad;
+        const long long pstride = (long long)c.levels * s->Ppad;
+        ndp_launch_state_reset(s->state, npairs, st);
+        CK(cudaMemsetAsync(s->adam_m, 0, sizeof(float) * (size_t)npairs * s->Ppad, st));
+        CK(cudaMemsetAsync(s->adam_v, 0, sizeof(float) * (size_t)npairs * s->Ppad, st));
+        NdpPackArgs pk; pk.lay = L; pk.params = lvl_params; pk.params_stride = pstride; pk.pack = s->pack; pk.pack_stride = s->packn; pk.npairs = npairs;
+        ndp_launch_pack(pk, st);
+        s->launches += 2;
+
+        NdpFwdArgs f;
+        f.lay = L; f.params = lvl_params; f.params_stride = pstride; f.pack = s->pack; f.pack_stride = s->packn;
+        f.x = s->smp[cur]; f.x_stride = S * 3; f.y = s->smp[cur ^ 1]; f.y_stride = S * 3; f.nu = nullptr; f.nu_stride = 0;
+        f.act = s->act; f.act_stride = (long long)c.depth * S * NDP_W; f.act_layer_stride = S * NDP_W;
+        f.zsave = s->zsave; f.z_stride = S * NDP_ZPITCH; f.y_add = nullptr; f.y_add_stride = 0;
+        f.n = s->S; f.counts = s->ncount; f.state = s->state; f.npairs = npairs;
+
+        NdpChamferArgs ch;
+        ch.nn.x = s->smp[cur ^ 1]; ch.nn.x_stride = S * 3; ch.nn.n = s->S; ch.nn.ncounts = s->ncount;
+        ch.nn.y = s->tsmp; ch.nn.y_stride = S * 3; ch.nn.m = s->S; ch.nn.mcounts = s->mcount;
+        ch.nn.part = s->nnpart; ch.nn.part_pair_stride = 2LL * s->plan.chunks * s->plan.qpitch;
+        ch.nn.qpitch = s->plan.qpitch; ch.nn.chunks = s->plan.chunks; ch.nn.chunk_targets = s->plan.chunk_targets;
+        ch.nn.state = s->state; ch.nn.npairs = npairs;
+        ch.trunc = c.trunc; ch.gx = s->gx; ch.gx_stride = S * 3; ch.gacc = s->gacc; ch.gacc_stride = S * 3;
+        ch.d2x = nullptr; ch.idxx = nullptr; ch.nx_stride = 0; ch.d2y = nullptr; ch.idxy = nullptr; ch.ny_stride = 0;
+        ch.blocksums = s->blocksums; ch.blocks_pitch = s->plan.blocks; ch.counters = s->counters; ch.loss_out = s->loss;
+        ch.state = s->state;
+        ch.loss_hist = s->loss_hist ? s->loss_hist + (long long)level * c.iters : nullptr;
+        ch.hist_stride = (long long)c.levels * c.iters; ch.hist_cap = c.iters;
+        ch.max_break_count = c.max_break_count; ch.break_ratio = (double)c.break_threshold_ratio;
+
+        NdpBwdArgs b;
+        b.lay = L; b.params = lvl_params; b.params_stride = pstride; b.x = s->smp[cur]; b.x_stride = S * 3;
+        b.act = s->act; b.act_stride = f.act_stride; b.act_layer_stride = f.act_layer_stride;
+        b.zsave = s->zsave; b.z_stride = f.z_stride; b.gy = s->gx; b.gy_stride = S * 3;
+        b.gacc = s->gacc; b.gacc_stride = S * 3; b.m = s->S; b.mcounts = s->mcount; b.gnu = nullptr; b.gnu_stride = 0;
+        b.partials = s->partials; b.partials_stride = (long long)s->tiles * s->Ppad; b.partial_pitch = s->Ppad;
+        b.gx = nullptr; b.gx_stride = 0; b.n = s->S; b.counts = s->ncount; b.state = s->state; b.npairs = npairs;
+
+        NdpAdamArgs ad;
+        ad.lay = L; ad.params = lvl_params; ad.params_stride = pstride; ad.pack = s->pack; ad.pack_stride = s->packn;
+        ad.m = s->adam_m; ad.v = s->adam_v; ad.mv_stride = s->Ppad;
+        ad.partials = s->partials; ad.partials_stride = b.partials_stride; ad.partial_pitch = s->Ppad;
+        ad.n = s->S; ad.counts = s->ncount; ad.grads_out = nullptr; ad.grads_stride = 0; ad.state = s->state;
+        ad.fixed_step = 0; ad.lr = c.lr; ad.beta1 = 0.9; ad.beta2 = 0.999; ad.eps = 1e-8; ad.do_adam = 1; ad.npairs = npairs;
+
+        for (int it = 0; it < c.iters; ++it) {
+            ndp_launch_fwd(f, st);
+            ndp_launch_nn(ch.nn, st);
+            ndp_launch_chamfer_reduce(ch, st);
+            ndp_launch_bwd(b, st);
+            ndp_launch_adam(ad, st);
+            s->launches += 5;
+            if ((it + 1) % poll == 0 && it + 1 < c.iters) {
+                CK(cudaMemcpyAsync(s->h_state, s->state, sizeof(NdpPairState) * npairs, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                bool all = true;
+                for (int p = 0; p < npairs; ++p) all = all && s->h_state[p].stopped;
+                if (all) break;
+            }
+        }
+        CK(cudaMemcpyAsync(s->h_state, s->state, sizeof(NdpPairState) * npairs, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        for (int p = 0; p < npairs; ++p) {
+            if (iters_out) iters_out[(long long)p * c.levels + level] = s->h_state[p].evals - (s->h_state[p].stopped ? 1 : 0);
+            if (loss_out) loss_out[(long long)p * c.levels + level] = s->h_state[p].last_loss;
+        }
+        cur ^= 1;   // the level's output feeds the next level (registration.py:249)
+    }
+
+    // final warp of the full, centred source cloud through every level (registration.py:254-259)
+    const float* xin = s->src_c;
+    int wb = 0;
+    for (int level = 0; level < c.levels; ++level) {
+        NdpPackArgs pk; pk.lay = s->lay[level]; pk.params = s->params + (long long)level * s->Ppad;
+        pk.params_stride = (long long)c.levels * s->Ppad; pk.pack = s->pack; pk.pack_stride = s->packn; pk.npairs = npairs;
+        ndp_launch_pack(pk, st);
+        NdpFwdArgs f;
+        f.lay = s->lay[level]; f.params = pk.params; f.params_stride = pk.params_stride; f.pack = s->pack; f.pack_stride = s->packn;
+        f.x = xin; f.x_stride = (long long)s->NS * 3; f.y = s->wbuf[wb]; f.y_stride = (long long)s->NS * 3;
+        f.nu = nullptr; f.nu_stride = 0; f.act = nullptr; f.act_stride = 0; f.act_layer_stride = 0; f.zsave = nullptr; f.z_stride = 0;
+        const bool last = level == c.levels - 1;
+        f.y_add = last ? s->means + 3 : nullptr; f.y_add_stride = 6;
+        f.n = s->NS; f.counts = s->nscount; f.state = nullptr; f.npairs = npairs;
+        ndp_launch_fwd(f, st);
+        s->launches += 2;
+        xin = s->wbuf[wb];
+        *final_buf = wb;
+        wb ^= 1;
+    }
+    CK(cudaGetLastError());
+    return NDP_OK;
+}
+
+static int solver_counts(ndp_solver* s, int npairs, const int32_t* ns, const int32_t* nt, cudaStream_t st) {
+    if (npairs < 1 || npairs > s->B) return fail(NDP_E_INVALID, "npairs exceeds max_pairs");
+    for (int p = 0; p < npairs; ++p) {
+        if (ns[p] < 1 || ns[p] > s->NS || nt[p] < 1 || nt[p] > s->NT) return fail(NDP_E_INVALID, "cloud size out of range");
+        s->h_counts[p] = ns[p] < s->S ? ns[p] : s->S;                     // src[: samples]
+        s->h_counts[s->B + p] = nt[p] < s->S ? nt[p] : s->S;
+        s->h_counts[2 * s->B + p] = ns[p];
+        s->h_counts[3 * s->B + p] = nt[p];
+    }
+    CK(cudaMemcpyAsync(s->ncount, s->h_counts, sizeof(int) * npairs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->mcount, s->h_counts + s->B, sizeof(int) * npairs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->nscount, s->h_counts + 2 * s->B, sizeof(int) * npairs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->ntcount, s->h_counts + 3 * s->B, sizeof(int) * npairs, cudaMemcpyHostToDevice, st));
+    return NDP_OK;
+}
+
+static int solver_register(ndp_solver* s, int32_t npairs, const float* const* src, const int32_t* ns,
+                           const float* const* tgt, const int32_t* nt, const int32_t* const* src_perm,
+                           const int32_t* const* tgt_perm, float* params_host, float* const* params_dev,
+                           int params_out, float* const* warped, int32_t* iters_out, float* loss_out,
+                           cudaStream_t st, cudaMemcpyKind in_kind, cudaMemcpyKind out_kind) {
+    if (!s || !src || !ns || !tgt || !nt || !warped) return fail(NDP_E_INVALID, "NULL argument");
+    if (!params_host && !params_dev) return fail(NDP_E_INVALID, "initial weights are required");
+    if (int e = solver_counts(s, npairs, ns, nt, st)) return e;
+    const ndp_solver_cfg& c = s->cfg;
+    bool hps = src_perm != nullptr, hpt = tgt_perm != nullptr;
+    for (int p = 0; p < npairs; ++p) {
+        if (hps != (src_perm && src_perm[p]) || hpt != (tgt_perm && tgt_perm[p]))
+            return fail(NDP_E_INVALID, "permutations must be given for all pairs or none");
+    }
+    for (int p = 0; p < npairs; ++p) {
+        CK(cudaMemcpyAsync(s->src_raw + (long long)p * s->NS * 3, src[p], sizeof(float) * 3 * ns[p], in_kind, st));
+        CK(cudaMemcpyAsync(s->tgt_raw + (long long)p * s->NT * 3, tgt[p], sizeof(float) * 3 * nt[p], in_kind, st));
+        if (hps) CK(cudaMemcpyAsync(s->perm_s + (long long)p * s->S, src_perm[p], sizeof(int) * s->h_counts[p], in_kind, st));
+        if (hpt) CK(cudaMemcpyAsync(s->perm_t + (long long)p * s->S, tgt_perm[p], sizeof(int) * s->h_counts[s->B + p], in_kind, st));
+        for (int l = 0; l < c.levels; ++l) {
+            const float* from = params_host ? params_host + ((long long)p * c.levels + l) * s->P
+                                            : params_dev[p] + (long long)l * s->P;
+            CK(cudaMemcpyAsync(s->params + ((long long)p * c.levels + l) * s->Ppad, from, sizeof(float) * s->P, in_kind, st));
+        }
+    }
+    int fb = 0;
+    if (int e = solver_run(s, npairs, hps, hpt, iters_out, loss_out, st, &fb)) return e;
+    for (int p = 0; p < npairs; ++p) {
+        CK(cudaMemcpyAsync(warped[p], s->wbuf[fb] + (long long)p * s->NS * 3, sizeof(float) * 3 * ns[p], out_kind, st));
+        if (params_out || params_dev) {
+            for (int l = 0; l < c.levels; ++l) {
+                float* to = params_host ? params_host + ((long long)p * c.levels + l) * s->P
+                                        : params_dev[p] + (long long)l * s->P;
+                CK(cudaMemcpyAsync(to, s->params + ((long long)p * c.levels + l) * s->Ppad, sizeof(float) * s->P, out_kind, st));
+            }
+        }
+    }
+    CK(cudaStreamSynchronize(st));
+    return NDP_OK;
+}
+
+extern "C" int ndp_solver_register_host(ndp_solver* s, int32_t npairs, const float* const* src, const int32_t* ns,
+                                        const float* const* tgt, const int32_t* nt, const int32_t* const* src_perm,
+                                        const int32_t* const* tgt_perm, float* params, int32_t params_out,
+                                        float* const* warped, int32_t* iters_out, float* loss_out, void* stream) {
+    return solver_register(s, npairs, src, ns, tgt, nt, src_perm, tgt_perm, params, nullptr, params_out, warped,
+                           iters_out, loss_out, (cudaStream_t)stream, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost);
+}
+
+extern "C" int ndp_solver_register_device(ndp_solver* s, int32_t npairs, const float* const* src, const int32_t* ns,
+                                          const float* const* tgt, const int32_t* nt, const int32_t* const* src_perm,
+                                          const int32_t* const* tgt_perm, float* const* params, float* const* warped,
+                                          int32_t* iters_out, float* loss_out, void* stream) {
+    return solver_register(s, npairs, src, ns, tgt, nt, src_perm, tgt_perm, nullptr, params, 1, warped, iters_out,
+                           loss_out, (cudaStream_t)stream, cudaMemcpyDeviceToDevice, cudaMemcpyDeviceToDevice);
+}
+
+extern "C" int ndp_solver_losses(ndp_solver* s, int32_t pair, float* out, void* stream) {
+    if (!s || !out || pair < 0 || pair >= s->B) return fail(NDP_E_INVALID, "bad argument");
+    if (!s->loss_hist) return fail(NDP_E_INVALID, "solver was created with record_loss = 0");
+    const long long n = (long long)s->cfg.levels * s->cfg.iters;
+    CK(cudaMemcpyAsync(out, s->loss_hist + pair * n, sizeof(float) * n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return NDP_OK;
+}

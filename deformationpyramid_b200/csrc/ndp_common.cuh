@@ -1,0 +1,143 @@
+// Shared definitions of the sm_100a kernels: platform shim (CUDA vs the test-only CPU emulation),
+// bulk-copy (TMA) + mbarrier helpers, parameter-block layout, tile constants.
+#pragma once
+#include <stdint.h>
+
+#ifdef NDP_EMU
+#include "cuda_emu.h"
+#define NDP_LAUNCH(kernel, grid, block, smem, stream, ...) ndp_emu::launch(kernel, grid, block, smem, __VA_ARGS__)
+#define NDP_DYN_SMEM(name) unsigned char* name = ndp_emu::dyn_smem()
+#else
+#include <cuda_runtime.h>
+#define NDP_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define NDP_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
+#endif
+
+#include "ndp_math.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// Tile constants.  The MLP kernels are specialised for the reference's hidden width 128
+// (config/NDP.yaml:26, shape_transfer.py:43); other widths are rejected at the C-ABI.
+// ------------------------------------------------------------------------------------------------
+#define NDP_W 128          // hidden width
+#define NDP_PITCH 132      // smem row pitch (floats) of a [points][128] tile: 4-bank skew per row
+#define NDP_TP 128         // points per CTA tile
+#define NDP_THREADS 256    // threads per CTA of the MLP kernels
+#define NDP_MAX_HIDDEN 8   // depth-1 <= 8
+#define NDP_ZPITCH 12      // saved head vector pitch (floats)
+
+// Flat parameter block of one pyramid level, in nn.Module.parameters() order of the reference
+// NDPLayer (model/nets.py:75-103): input.0.{weight[W,6],bias[W]}, mlp.pts_linears.l.{weight[W,W],
+// bias[W]}, rot_brach.{weight[R,W],bias[R]}, s_branch (Sim3), trn_branch.{weight[3,W],bias[3]},
+// nr_branch (nonrigidity).  The "pack" block holds the transposed copies the forward kernel
+// streams through shared memory: WT_in[6][W], WT_l[W][W] (k-major).
+struct NdpLayout {
+    int hidden;                 // L = depth - 1
+    int motion, rot, nonrigid;
+    int head_dim;               // rows of the head matrix = NdpHeadIdx.dim
+    int off_w_in, off_b_in;
+    int off_w[NDP_MAX_HIDDEN], off_b[NDP_MAX_HIDDEN];
+    int head_w[NDP_MAX_HEAD], head_b[NDP_MAX_HEAD];   // per head row: weight row / bias offsets
+    int param_count;
+    int pack_in, pack_w[NDP_MAX_HIDDEN], pack_count;
+    float freq, mu;
+};
+
+static inline NdpLayout ndp_make_layout(int depth, int motion, int rot, int nonrigid, float freq, float mu) {
+    NdpLayout L;
+    L.hidden = depth - 1; L.motion = motion; L.rot = rot; L.nonrigid = nonrigid ? 1 : 0;
+    L.freq = freq; L.mu = mu;
+    int o = 0;
+    L.off_w_in = o; o += NDP_W * 6;
+    L.off_b_in = o; o += NDP_W;
+    for (int l = 0; l < NDP_MAX_HIDDEN; ++l) { L.off_w[l] = 0; L.off_b[l] = 0; L.pack_w[l] = 0; }
+    for (int l = 0; l < L.hidden; ++l) {
+        L.off_w[l] = o; o += NDP_W * NDP_W;
+        L.off_b[l] = o; o += NDP_W;
+    }
+    NdpHeadIdx h = ndp_head_idx(motion, rot, nonrigid);
+    L.head_dim = h.dim;
+    for (int r = 0; r < NDP_MAX_HEAD; ++r) { L.head_w[r] = 0; L.head_b[r] = 0; }
+    int row = 0;
+    int R = ndp_rot_dim(motion, rot);
+    if (R > 0) {
+        for (int r = 0; r < R; ++r) { L.head_w[row + r] = o + r * NDP_W; L.head_b[row + r] = o + R * NDP_W + r; }
+        o += R * NDP_W + R; row += R;
+        if (motion == NDP_MOTION_SIM3) { L.head_w[row] = o; L.head_b[row] = o + NDP_W; o += NDP_W + 1; row += 1; }
+    }
+    for (int r = 0; r < 3; ++r) { L.head_w[row + r] = o + r * NDP_W; L.head_b[row + r] = o + 3 * NDP_W + r; }
+    o += 3 * NDP_W + 3; row += 3;
+    if (nonrigid) { L.head_w[row] = o; L.head_b[row] = o + NDP_W; o += NDP_W + 1; row += 1; }
+    L.param_count = o;
+    int p = 0;
+    L.pack_in = p; p += 6 * NDP_W;
+    for (int l = 0; l < L.hidden; ++l) { L.pack_w[l] = p; p += NDP_W * NDP_W; }
+    L.pack_count = p;
+    return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bulk asynchronous copy global -> shared (TMA, non-tensor form: cp.async.bulk, SASS UBLKCP) with
+// mbarrier transaction-count completion.  Sizes and addresses must be multiples of 16 bytes.
+// ------------------------------------------------------------------------------------------------
+#ifdef NDP_EMU
+struct NdpMbar { volatile long long pending; volatile unsigned phase; unsigned pad; };
+static inline void ndp_mbar_init(NdpMbar* b, int) { b->pending = 0; b->phase = 0; }
+static inline void ndp_mbar_expect_tx(NdpMbar* b, unsigned bytes) { __atomic_fetch_add((long long*)&b->pending, (long long)bytes, __ATOMIC_SEQ_CST); }
+static inline void ndp_bulk_g2s(void* dst, const void* src, unsigned bytes, NdpMbar* b) {
+    memcpy(dst, src, bytes);
+    long long left = __atomic_sub_fetch((long long*)&b->pending, (long long)bytes, __ATOMIC_SEQ_CST);
+    if (left == 0) __atomic_fetch_add((unsigned*)&b->phase, 1u, __ATOMIC_SEQ_CST);
+}
+static inline void ndp_mbar_wait(NdpMbar* b, unsigned parity) {
+    while ((__atomic_load_n((unsigned*)&b->phase, __ATOMIC_SEQ_CST) & 1u) == parity) std::this_thread::yield();
+}
+static inline void ndp_fence_proxy_async() {}
+#else
+struct __align__(8) NdpMbar { unsigned long long v; };
+__device__ __forceinline__ unsigned ndp_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ndp_mbar_init(NdpMbar* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ndp_smem_u32(b)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void ndp_mbar_expect_tx(NdpMbar* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ndp_smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ndp_bulk_g2s(void* dst, const void* src, unsigned bytes, NdpMbar* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(ndp_smem_u32(dst)), "l"(src), "r"(bytes), "r"(ndp_smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void ndp_mbar_wait(NdpMbar* b, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "NDP_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra NDP_DONE;\n\t"
+        "bra NDP_WAIT;\n\t"
+        "NDP_DONE:\n\t}"
+        ::"r"(ndp_smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void ndp_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+
+// Stage `bytes` (multiple of 16) with bulk copies of at most 32 KiB each; one thread calls this.
+__device__ __forceinline__ void ndp_stage_bulk(void* dst, const void* src, unsigned bytes, NdpMbar* bar) {
+    ndp_fence_proxy_async();
+    ndp_mbar_expect_tx(bar, bytes);
+    const unsigned CH = 32768u;
+    for (unsigned o = 0; o < bytes; o += CH) {
+        unsigned n = bytes - o < CH ? bytes - o : CH;
+        ndp_bulk_g2s((char*)dst + o, (const char*)src + o, n, bar);
+    }
+}
+
+// Per-pair optimisation state (device resident; model/registration.py:179-180, 225-232).
+struct NdpPairState {
+    int stopped;         // 1 once the early-stop rule fired for the current level
+    int steps;           // Adam steps taken in the current level
+    int break_counter;   // cumulative per level
+    int evals;           // forward+loss evaluations in the current level
+    double loss_prev;    // initial 1e6
+    float last_loss;
+    float pad;
+};

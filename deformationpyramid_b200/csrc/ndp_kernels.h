@@ -1,0 +1,133 @@
+// Internal launcher interface between the C-ABI (ndp_cabi.cu / ndp_solver.cu) and the kernels.
+// Every kernel is batched over point-cloud PAIRS (blockIdx.y or .z = pair): each pair has its own
+// clouds, parameter block, Adam state and early-stop state, addressed by uniform strides.
+#pragma once
+#include "ndp_common.cuh"
+
+// ---- kernel (1): positional encoding + MLP + heads + SE(3)/Sim(3)/flow warp ---------------------
+struct NdpFwdArgs {
+    NdpLayout lay;
+    const float* params; long long params_stride;   // canonical flat block (heads, biases)
+    const float* pack;   long long pack_stride;     // transposed hidden/input weights (TMA source)
+    const float* x;      long long x_stride;        // [pair][n][3]
+    float* y;            long long y_stride;        // [pair][n][3]
+    float* nu;           long long nu_stride;       // [pair][n] or null
+    float* act;          long long act_stride;      // saved activations [pair][L+1][n_alloc][128] or null
+    long long act_layer_stride;
+    float* zsave;        long long z_stride;        // saved head vectors [pair][n_alloc][12] or null
+    const float* y_add; int y_add_stride;            // [pair][stride] 3 floats added to the output, or null
+    int n; const int* counts;                        // points per pair (counts overrides n when non-null)
+    const NdpPairState* state;                       // pairs with state.stopped are skipped, or null
+    int npairs;
+};
+void ndp_launch_fwd(const NdpFwdArgs& a, cudaStream_t s);
+
+// ---- kernel (3a): backward of kernel (1) -> per-tile parameter-gradient partials -----------------
+struct NdpBwdArgs {
+    NdpLayout lay;
+    const float* params; long long params_stride;
+    const float* x;      long long x_stride;
+    const float* act;    long long act_stride; long long act_layer_stride;
+    const float* zsave;  long long z_stride;
+    const float* gy;     long long gy_stride;        // dL/dy [pair][n][3]
+    unsigned long long* gacc; long long gacc_stride; // optional fixed-point addend [pair][n][3]; consumed+zeroed
+    int m; const int* mcounts;                        // gacc scale = 2^-40 / m
+    const float* gnu;    long long gnu_stride;        // dL/dnu [pair][n] or null
+    float* partials;     long long partials_stride; int partial_pitch;   // [pair][tile][pitch]
+    float* gx;           long long gx_stride;         // dL/dx [pair][n][3] or null
+    int n; const int* counts;
+    const NdpPairState* state;
+    int npairs;
+};
+void ndp_launch_bwd(const NdpBwdArgs& a, cudaStream_t s);
+
+// ---- kernel (3b): fixed-order reduction of the partials + Adam + transposed-copy refresh ---------
+struct NdpAdamArgs {
+    NdpLayout lay;
+    float* params;  long long params_stride;
+    float* pack;    long long pack_stride;           // may be null
+    float* m; float* v; long long mv_stride;         // Adam moments (null when do_adam == 0)
+    const float* partials; long long partials_stride; int partial_pitch;
+    int n; const int* counts;                         // tiles per pair = ceil(n / NDP_TP); n == 0 -> 1 partial row
+    float* grads_out; long long grads_stride;         // reduced gradient, or null
+    const NdpPairState* state;                        // step = state.evals; stopped pairs skipped
+    int fixed_step;                                   // used when state == null
+    double lr, beta1, beta2, eps;                     // Python floats in torch.optim.Adam => double here
+    int do_adam;
+    int npairs;
+};
+void ndp_launch_adam(const NdpAdamArgs& a, cudaStream_t s);
+
+struct NdpPackArgs {
+    NdpLayout lay;
+    const float* params; long long params_stride;
+    float* pack; long long pack_stride;
+    int npairs;
+};
+void ndp_launch_pack(const NdpPackArgs& a, cudaStream_t s);
+
+// ---- kernel (2): brute-force nearest neighbour, both directions, + Chamfer epilogue --------------
+#define NDP_NN_THREADS 128
+#define NDP_NN_Q 4
+#define NDP_NN_QT (NDP_NN_THREADS * NDP_NN_Q)   // queries per CTA
+#define NDP_NN_TS 512                            // targets per shared-memory tile
+struct NdpNnArgs {
+    const float* x; long long x_stride; int n; const int* ncounts;   // warped source [pair][n][3]
+    const float* y; long long y_stride; int m; const int* mcounts;   // target        [pair][m][3]
+    float2* part; long long part_pair_stride;   // [pair][dir][chunk][qpitch] (d2, idx bits)
+    int qpitch; int chunks; int chunk_targets;  // chunk_targets is a multiple of NDP_NN_TS
+    const NdpPairState* state;
+    int npairs;
+};
+void ndp_launch_nn(const NdpNnArgs& a, cudaStream_t s);
+
+struct NdpChamferArgs {
+    NdpNnArgs nn;
+    float trunc;
+    float* gx; long long gx_stride;                   // direct term of dL/dx [pair][n][3]
+    unsigned long long* gacc; long long gacc_stride;  // scattered term, fixed point [pair][n][3]
+    float* d2x; long long* idxx; long long nx_stride; // optional NN outputs (raw squared distances)
+    float* d2y; long long* idxy; long long ny_stride;
+    double* blocksums; int blocks_pitch;              // [pair][blocks_pitch][2]
+    int* counters;                                    // [pair], zero before the first launch
+    float* loss_out;                                  // [pair]
+    NdpPairState* state;                              // early-stop update, or null
+    float* loss_hist; long long hist_stride; int hist_cap;   // optional loss curve: loss_hist[pair*stride + eval], eval < cap
+    int max_break_count; double break_ratio;
+};
+void ndp_launch_chamfer_reduce(const NdpChamferArgs& a, cudaStream_t s);
+
+struct NdpGradFinalizeArgs {                          // gx += fixed-point gacc (standalone Chamfer API)
+    float* gx; long long gx_stride;
+    unsigned long long* gacc; long long gacc_stride;
+    int n; const int* ncounts; int m; const int* mcounts;
+    float scale;                                      // upstream dL/dloss
+    int npairs;
+};
+void ndp_launch_grad_finalize(const NdpGradFinalizeArgs& a, cudaStream_t s);
+
+// ---- small helpers of the per-pair driver -------------------------------------------------------
+struct NdpCenterArgs {                                // registration.py:150-159
+    const float* src; long long src_stride; int ns; const int* nscounts;   // full clouds
+    const float* tgt; long long tgt_stride; int nt; const int* ntcounts;
+    float* means;                                     // [pair][2][3]  (src mean, tgt mean)
+    int npairs;
+};
+void ndp_launch_means(const NdpCenterArgs& a, cudaStream_t s);
+
+struct NdpGatherArgs {                                // out[i] = in[idx[i]] - mean   (idx null: identity)
+    const float* in; long long in_stride;
+    const int* idx; long long idx_stride;
+    const float* means; int which;                    // means[pair][which][3]
+    float* out; long long out_stride;
+    int n; const int* counts;
+    int npairs;
+};
+void ndp_launch_gather_center(const NdpGatherArgs& a, cudaStream_t s);
+
+void ndp_launch_state_reset(NdpPairState* state, int npairs, cudaStream_t s);
+
+size_t ndp_fwd_smem_bytes();
+size_t ndp_bwd_smem_bytes();
+int ndp_fwd_init();   // opt-in dynamic shared memory size; returns cudaError_t
+int ndp_bwd_init();

@@ -1,0 +1,185 @@
+"""Parity checks shared by the GPU tests (real library, CUDA tensors) and the emulation tests (same
+sources on the CPU shim).  The checker is always the oracle / the golden vectors of the reference."""
+import os
+
+import numpy as np
+import torch
+
+from deformationpyramid_b200 import ops
+from deformationpyramid_b200.synthetic import make_pair
+from oracle import ndp_oracle as O
+
+REL_TOL = 1e-4     # BASELINE.json north_star: 1e-4 relative fp32; NN indices bit-exact
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def dev(t, device):
+    return t.to(device).contiguous()
+
+
+def parse_meta(meta):
+    motion, fmt, nr, m, seed, depth = str(meta).split(",")
+    return motion, fmt, bool(int(nr)), int(m), int(seed), int(depth)
+
+
+def check_layers_against_golden(lib, golden_dir, device):
+    G = np.load(os.path.join(golden_dir, "layers.npz"))
+    for vi, meta in enumerate(G["meta"]):
+        motion, fmt, nr, m, seed, depth = parse_meta(meta)
+        cfg = ops.make_layer_cfg(depth, 128, -8, m, fmt, nr, motion)
+        k = f"v{vi}"
+        params = dev(torch.from_numpy(G[f"{k}_params"]), device)
+        x = dev(torch.from_numpy(G[f"{k}_x"]), device)
+        assert ops.param_count(cfg, lib=lib) == params.numel()
+        pack = ops.pack_params(cfg, params, lib=lib)
+        y, nu, saved = ops.layer_forward(cfg, params, pack, x, lib=lib)
+        assert rel(y.cpu().numpy(), G[f"{k}_y"]) < REL_TOL, meta
+        gnu = None
+        if nr:
+            assert rel(nu.cpu().numpy(), G[f"{k}_nu"]) < REL_TOL, meta
+            gnu = dev(torch.from_numpy(G[f"{k}_gnu"]), device)
+        gy = dev(torch.from_numpy(G[f"{k}_gy"]), device)
+        gp, gx = ops.layer_backward(cfg, params, x, saved, gy, gnu, need_grad_x=True, lib=lib)
+        assert rel(gp.cpu().numpy(), G[f"{k}_gparams"]) < REL_TOL, meta
+        assert rel(gx.cpu().numpy(), G[f"{k}_gx"]) < REL_TOL, meta
+        # inference variant (no saved activations) gives the same output
+        y2, _, _ = ops.layer_forward(cfg, params, pack, x, need_saved=False, lib=lib)
+        assert torch.equal(y, y2)
+
+
+def check_chamfer_against_golden(lib, golden_dir, device):
+    G = np.load(os.path.join(golden_dir, "chamfer.npz"))
+    for name in G["meta"]:
+        name = str(name)
+        x = dev(torch.from_numpy(G[f"{name}_x"]), device)
+        y = dev(torch.from_numpy(G[f"{name}_y"]), device)
+        loss, gx, (d2x, ix, d2y, iy) = ops.chamfer(x, y, float(G[f"{name}_trunc"]), want_nn=True, lib=lib)
+        assert np.array_equal(ix.cpu().numpy(), G[f"{name}_ix"]), name            # bit-exact indices
+        assert np.array_equal(iy.cpu().numpy(), G[f"{name}_iy"]), name
+        assert np.array_equal(d2x.cpu().numpy(), G[f"{name}_d2x"]), name          # bit-exact distances
+        assert np.array_equal(d2y.cpu().numpy(), G[f"{name}_d2y"]), name
+        assert abs(float(loss) - float(G[f"{name}_loss"])) <= REL_TOL * abs(float(G[f"{name}_loss"])), name
+        assert rel(gx.cpu().numpy(), G[f"{name}_gx"]) < REL_TOL, name
+        # determinism: a second run is bit-identical (no float atomics)
+        loss2, gx2 = ops.chamfer(x, y, float(G[f"{name}_trunc"]), lib=lib)
+        assert torch.equal(loss, loss2) and torch.equal(gx, gx2)
+        # upstream gradient scaling
+        _, gx3 = ops.chamfer(x, y, float(G[f"{name}_trunc"]), grad_scale=0.5, lib=lib)
+        assert torch.allclose(gx3, 0.5 * gx, rtol=1e-6, atol=0)
+
+
+def check_chamfer_vs_oracle_random(lib, device, sizes, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    for n, m in sizes:
+        x = torch.randn(n, 3, generator=g) * 0.4
+        y = torch.randn(m, 3, generator=g) * 0.4
+        xo = x.clone().requires_grad_(True)
+        lo, nn = O.chamfer_truncated(xo[None], y[None], trunc=1e9, return_nn=True)
+        go, = torch.autograd.grad(lo, xo)
+        loss, gx, (d2x, ix, d2y, iy) = ops.chamfer(dev(x, device), dev(y, device), 1e9, want_nn=True, lib=lib)
+        assert torch.equal(ix.cpu(), nn[0][1]) and torch.equal(iy.cpu(), nn[0][3]), (n, m)
+        assert torch.equal(d2x.cpu(), nn[0][0]) and torch.equal(d2y.cpu(), nn[0][2]), (n, m)
+        assert abs(float(loss) - float(lo)) <= REL_TOL * abs(float(lo))
+        assert rel(gx.cpu().numpy(), go.numpy()) < REL_TOL
+
+
+def check_adam(lib, device):
+    g = torch.Generator().manual_seed(3)
+    p0 = torch.randn(5000, generator=g)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=0.01)
+    p = dev(p0.clone(), device)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    for step in range(1, 6):
+        grad = torch.randn(5000, generator=g) * (10.0 ** (step - 3))
+        ref.grad = grad.clone()
+        opt.step()
+        ops.adam_step(p, dev(grad, device), m, v, step, 0.01, lib=lib)
+        assert rel(p.cpu().numpy(), ref.detach().numpy()) < 1e-6
+    st = opt.state[ref]
+    assert rel(m.cpu().numpy(), st["exp_avg"].numpy()) < 1e-6
+    assert rel(v.cpu().numpy(), st["exp_avg_sq"].numpy()) < 1e-6
+
+
+def check_trajectory_teacher_forced(lib, golden_dir, device):
+    """From each recorded state of the unmodified reference run: ONE iteration of the CUDA path
+    (forward, Chamfer, backward, Adam) reproduces warped points, loss, gradients, new weights."""
+    G = np.load(os.path.join(golden_dir, "trajectory.npz"))
+    src, tgt = torch.from_numpy(G["src"]), torch.from_numpy(G["tgt"])
+    torch.manual_seed(int(G["seed"]))
+    spec = O.LayerSpec(depth=3, width=128, k0=-8, m=1)
+    O.init_params(spec)                                     # consume the RNG as registration.py:133
+    sp, tp = torch.randperm(512), torch.randperm(512)
+    s_sample = dev((src - src.mean(0, keepdim=True))[sp[:512]], device)
+    t_sample = dev((tgt - tgt.mean(0, keepdim=True))[tp[:512]], device)
+    cfg = ops.make_layer_cfg(3, 128, -8, 1, "axis_angle", False, "SE3")
+    for it in G["keep_its"]:
+        k = f"it{int(it)}"
+        params = dev(torch.from_numpy(G[f"{k}_params_before"]), device)
+        pack = ops.pack_params(cfg, params, lib=lib)
+        y, _, saved = ops.layer_forward(cfg, params, pack, s_sample, lib=lib)
+        assert rel(y.cpu().numpy(), G[f"{k}_x_warped"]) < REL_TOL
+        loss, gy, nn = ops.chamfer(y, t_sample, 1e9, want_nn=True, lib=lib)
+        assert abs(float(loss) - float(G["losses"][int(it)])) <= REL_TOL * float(G["losses"][int(it)])
+        # NN indices bit-exact against the oracle run on the REFERENCE's warped points
+        yr = torch.from_numpy(G[f"{k}_x_warped"])
+        if np.array_equal(y.cpu().numpy(), G[f"{k}_x_warped"]):
+            d2, idx = O.knn1(yr, t_sample.cpu())
+            assert torch.equal(idx, nn[1].cpu())
+        gp, _ = ops.layer_backward(cfg, params, s_sample, saved, gy, lib=lib)
+        assert rel(gp.cpu().numpy(), G[f"{k}_grads"]) < 5 * REL_TOL
+        m = dev(torch.from_numpy(G[f"{k}_m_before"]), device)
+        v = dev(torch.from_numpy(G[f"{k}_v_before"]), device)
+        gref = dev(torch.from_numpy(G[f"{k}_grads"]), device)
+        ops.adam_step(params, gref, m, v, int(G[f"{k}_step_before"]) + 1, 0.01, cfg=cfg, pack=pack, lib=lib)
+        assert rel(params.cpu().numpy(), G[f"{k}_params_after"]) < 1e-5
+        assert rel(m.cpu().numpy(), G[f"{k}_m_after"]) < 1e-5
+        assert rel(v.cpu().numpy(), G[f"{k}_v_after"]) < 1e-5
+        # the transposed copies refreshed by the Adam kernel equal a fresh pack
+        assert torch.equal(pack, ops.pack_params(cfg, params, lib=lib))
+
+
+def check_solver_against_oracle(lib, device, host, npairs, n, m, samples, levels, iters, early_stop,
+                                ratio=0.001, max_break=15, motion="SE3", rot="axis_angle", free_tol=2e-4):
+    """Fused driver vs oracle.optimize_pair (= registration.py:126-262) on identical pairs, weights
+    and permutations.  Short free-running horizon (hard part 3)."""
+    cfgo = O.NDPConfig(iters=iters, lr=0.01, max_break_count=max_break if early_stop else 10 ** 9,
+                       break_threshold_ratio=ratio, samples=samples, m=levels, motion_type=motion,
+                       rotation_format=rot)
+    specs = O.make_specs(3, 128, -8, levels, rot, motion=motion)
+    srcs, tgts, inits, sps, tps, refs = [], [], [], [], [], []
+    for p in range(npairs):
+        npts = n - 17 * p
+        src, tgt = make_pair(50 + p, npts, m + 5 * p)
+        torch.manual_seed(p)
+        init = [O.init_params(s) for s in specs]
+        sp, tp = torch.randperm(src.shape[0]), torch.randperm(tgt.shape[0])
+        refs.append(O.optimize_pair(cfgo, src, tgt, init=init, src_perm=sp, tgt_perm=tp))
+        srcs.append(src); tgts.append(tgt); inits.append(init)
+        sps.append(sp[:samples].to(torch.int32).contiguous()); tps.append(tp[:samples].to(torch.int32).contiguous())
+    solver = ops.Solver(max_pairs=npairs, max_src_points=n, max_tgt_points=m + 5 * npairs, samples=samples,
+                        levels=levels, k0=-8, depth=3, width=128, motion=motion, rotation_format=rot, iters=iters,
+                        max_break_count=cfgo.max_break_count, break_threshold_ratio=ratio, lr=0.01, trunc=1e9,
+                        record_loss=True, lib=lib)
+    params = [torch.cat([O.flatten_params(s, P) for s, P in zip(specs, init)]).contiguous() for init in inits]
+    d = "cpu" if host else device
+    mv = lambda ts: [t.to(d).contiguous() for t in ts]
+    warped, its, last = solver.register(mv(srcs), mv(tgts), mv(params) if not host else params, mv(sps), mv(tps), host=host)
+    for p in range(npairs):
+        ref = refs[p]
+        curve = solver.losses(p)
+        for lv in range(levels):
+            rc = np.array(ref.loss_curve[lv], np.float32)
+            mine = curve[lv].numpy()[:len(rc)]
+            assert int(its[p, lv]) == ref.iters_per_level[lv], (p, lv, int(its[p, lv]), ref.iters_per_level[lv])
+            assert np.allclose(mine, rc, rtol=free_tol, atol=1e-7), (p, lv, mine, rc)
+            assert abs(float(last[p, lv]) - ref.loss_per_level[lv]) <= free_tol * abs(ref.loss_per_level[lv])
+        assert rel(warped[p].cpu().numpy(), ref.warped.numpy()) < 5 * free_tol, p
+    assert solver.launch_count > 0
+    solver.close()

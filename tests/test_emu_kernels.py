@@ -1,0 +1,55 @@
+"""CPU-only checks of the kernel SOURCES (tiling, indexing, barriers, host orchestration) by running
+them through the test-only CUDA-on-CPU shim (tests/cpu_emu) against the golden vectors of the
+unmodified reference and against the oracle.  The same comparisons run on the real B200 through
+the nvcc-built library in tests/test_gpu_parity.py; this file exists because the build container
+has no GPU.  Nothing here is a product code path."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from deformationpyramid_b200 import ops
+from deformationpyramid_b200.synthetic import make_pair
+from oracle import ndp_oracle as O
+from emu_util import emu_lib
+
+from parity_cases import (check_layers_against_golden, check_chamfer_against_golden, check_adam,
+                          check_trajectory_teacher_forced, check_solver_against_oracle,
+                          check_chamfer_vs_oracle_random)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return emu_lib()
+
+
+def test_layers_golden(lib, golden_dir):
+    check_layers_against_golden(lib, golden_dir, device="cpu")
+
+
+def test_chamfer_golden(lib, golden_dir):
+    check_chamfer_against_golden(lib, golden_dir, device="cpu")
+
+
+def test_chamfer_random_vs_oracle(lib):
+    check_chamfer_vs_oracle_random(lib, device="cpu", sizes=[(1, 1), (5, 700), (513, 129), (1100, 1030)])
+
+
+def test_adam(lib):
+    check_adam(lib, device="cpu")
+
+
+def test_trajectory(lib, golden_dir):
+    check_trajectory_teacher_forced(lib, golden_dir, device="cpu")
+
+
+def test_solver_small(lib):
+    check_solver_against_oracle(lib, device="cpu", host=True, npairs=2, n=300, m=260, samples=200, levels=2,
+                                iters=5, early_stop=False)
+
+
+def test_solver_early_stop_and_ragged(lib):
+    # samples > cloud size for pair 1 -> ragged counts; aggressive early stop -> ragged termination
+    check_solver_against_oracle(lib, device="cpu", host=True, npairs=2, n=150, m=140, samples=160, levels=2,
+                                iters=12, early_stop=True, ratio=0.05, max_break=2)
