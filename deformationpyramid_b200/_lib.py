@@ -22,7 +22,7 @@ EXPORTS = [
     "ndp_pack_params", "ndp_layer_forward", "ndp_layer_backward", "ndp_chamfer", "ndp_adam_step",
     "ndp_solver_create", "ndp_solver_destroy", "ndp_solver_params_per_pair",
     "ndp_solver_register_host", "ndp_solver_register_device", "ndp_solver_losses",
-    "ndp_solver_launch_count",
+    "ndp_solver_launch_count", "ndp_solver_profile",
 ]
 
 
@@ -36,7 +36,7 @@ class SolverCfg(ctypes.Structure):
                 ("samples", c_int32), ("levels", c_int32), ("k0", c_int32), ("depth", c_int32),
                 ("width", c_int32), ("motion", c_int32), ("rot_format", c_int32), ("iters", c_int32),
                 ("max_break_count", c_int32), ("break_threshold_ratio", c_float), ("lr", c_double),
-                ("trunc", c_float), ("record_loss", c_int32)]
+                ("trunc", c_float), ("record_loss", c_int32), ("profile_every", c_int32)]
 
 
 def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
@@ -73,6 +73,8 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.ndp_solver_register_device.argtypes = [c_void_p, c_int32, pp, P(c_int32), pp, P(c_int32), pp, pp,
                                                pp, pp, c_void_p, c_void_p, c_void_p]
     lib.ndp_solver_losses.argtypes = [c_void_p, c_int32, c_void_p, c_void_p]
+    lib.ndp_solver_profile.argtypes = [c_void_p, P(c_double), P(c_int64)]
+    lib.ndp_solver_profile.restype = ctypes.c_int
     for name in ("ndp_pack_params", "ndp_layer_forward", "ndp_layer_backward", "ndp_chamfer",
                  "ndp_adam_step", "ndp_solver_create", "ndp_solver_register_host",
                  "ndp_solver_register_device", "ndp_solver_losses"):

@@ -235,7 +235,25 @@ struct ndp_solver {
     int* h_counts = nullptr;
     long long launches = 0;
     std::vector<void*> allocs;
+    // sampled per-kernel timing (profile_every > 0): 6 events bracket the 5 kernels of an iteration
+    std::vector<cudaEvent_t> events;
+    int ev_used = 0;
+    double prof_ms[5] = {0, 0, 0, 0, 0};
+    long long prof_samples = 0;
 };
+
+static int prof_flush(ndp_solver* s) {   // call after a stream synchronisation
+    for (int i = 0; i + 6 <= s->ev_used; i += 6) {
+        for (int k = 0; k < 5; ++k) {
+            float ms = 0.0f;
+            CK(cudaEventElapsedTime(&ms, s->events[i + k], s->events[i + k + 1]));
+            s->prof_ms[k] += ms;
+        }
+        s->prof_samples += 1;
+    }
+    s->ev_used = 0;
+    return NDP_OK;
+}
 
 template <class T> static int dalloc(ndp_solver* s, T** p, long long count) {
     void* q = nullptr;
@@ -248,6 +266,7 @@ template <class T> static int dalloc(ndp_solver* s, T** p, long long count) {
 extern "C" void ndp_solver_destroy(ndp_solver* s) {
     if (!s) return;
     for (void* p : s->allocs) cudaFree(p);
+    for (cudaEvent_t e : s->events) cudaEventDestroy(e);
     if (s->h_state) cudaFreeHost(s->h_state);
     if (s->h_counts) cudaFreeHost(s->h_counts);
     delete s;
@@ -293,6 +312,12 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
 
 extern "C" int64_t ndp_solver_params_per_pair(const ndp_solver* s) { return s ? (int64_t)s->cfg.levels * s->P : -1; }
 extern "C" int64_t ndp_solver_launch_count(const ndp_solver* s) { return s ? s->launches : -1; }
+extern "C" int ndp_solver_profile(const ndp_solver* s, double* ms, int64_t* samples) {
+    if (!s || !ms || !samples) return fail(NDP_E_INVALID, "NULL argument");
+    for (int k = 0; k < 5; ++k) ms[k] = s->prof_ms[k];
+    *samples = s->prof_samples;
+    return NDP_OK;
+}
 
 // Optimise all levels for the npairs pairs whose raw clouds / perms / params are already in the
 // solver's device buffers; leaves the warped full clouds in s->wbuf[final] and returns which.
@@ -369,15 +394,33 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         ad.fixed_step = 0; ad.lr = c.lr; ad.beta1 = 0.9; ad.beta2 = 0.999; ad.eps = 1e-8; ad.do_adam = 1; ad.npairs = npairs;
 
         for (int it = 0; it < c.iters; ++it) {
+            const bool prof = c.profile_every > 0 && (it % c.profile_every) == c.profile_every / 2;
+            cudaEvent_t* ev = nullptr;
+            if (prof) {
+                while ((int)s->events.size() < s->ev_used + 6) {
+                    cudaEvent_t e;
+                    CK(cudaEventCreate(&e));
+                    s->events.push_back(e);
+                }
+                ev = s->events.data() + s->ev_used;
+                s->ev_used += 6;
+                CK(cudaEventRecord(ev[0], st));
+            }
             ndp_launch_fwd(f, st);
+            if (prof) CK(cudaEventRecord(ev[1], st));
             ndp_launch_nn(ch.nn, st);
+            if (prof) CK(cudaEventRecord(ev[2], st));
             ndp_launch_chamfer_reduce(ch, st);
+            if (prof) CK(cudaEventRecord(ev[3], st));
             ndp_launch_bwd(b, st);
+            if (prof) CK(cudaEventRecord(ev[4], st));
             ndp_launch_adam(ad, st);
+            if (prof) CK(cudaEventRecord(ev[5], st));
             s->launches += 5;
             if ((it + 1) % poll == 0 && it + 1 < c.iters) {
                 CK(cudaMemcpyAsync(s->h_state, s->state, sizeof(NdpPairState) * npairs, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
+                if (int e = prof_flush(s)) return e;
                 bool all = true;
                 for (int p = 0; p < npairs; ++p) all = all && s->h_state[p].stopped;
                 if (all) break;
@@ -386,6 +429,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         CK(cudaMemcpyAsync(s->h_state, s->state, sizeof(NdpPairState) * npairs, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
+        if (int e = prof_flush(s)) return e;
         for (int p = 0; p < npairs; ++p) {
             if (iters_out) iters_out[(long long)p * c.levels + level] = s->h_state[p].evals - (s->h_state[p].stopped ? 1 : 0);
             if (loss_out) loss_out[(long long)p * c.levels + level] = s->h_state[p].last_loss;

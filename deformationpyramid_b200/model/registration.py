@@ -1,0 +1,254 @@
+"""Host-side mirror of the reference model/registration.py for deformation_model == "NDP".
+
+Registration keeps the reference surface (model/registration.py:24-34, 93-123): attributes
+src_pcd / tgt_pcd / device / config / deformation_model / landmarks, load_pcds(), register(),
+optimize_deformation_pyramid(visualize=False, timer=None) -> (warped_pcd, {}, timer).
+
+Two execution routes, both on the sm_100a kernels:
+  * fused  -- landmarks is None and w_reg == 0 (config/NDP.yaml): the whole level / iteration
+              loop of registration.py:170-249 runs inside the native solver (ndp_solver_*), with the
+              early-stop rule evaluated on the device instead of three .item() syncs per iteration;
+  * stepwise -- landmarks (LNDP, registration.py:187-203) or the nonrigidity regulariser
+              (:216-220): the reference's Python loop over autograd-capable CUDA ops
+              (NDPLayer / compute_truncated_chamfer_distance) and torch.optim.Adam.
+The comparison methods of the paper (Nerfies, ED/N-ICP, NSFP, Sinkhorn) are out of scope.
+RNG order per pair is the reference's: weights first (:133-140), then two randperm (:156-157).
+"""
+from __future__ import annotations
+
+import time
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.optim as optim
+
+from .. import ops
+from .loss import compute_truncated_chamfer_distance
+from .nets import Deformation_Pyramid
+
+BCE = nn.BCELoss()
+
+
+def _cfg_get(config, key, default=None):
+    try:
+        return getattr(config, key)
+    except (AttributeError, KeyError):
+        return default
+
+
+class Registration():
+
+    def __init__(self, config):
+        self.tgt_pcd = None
+        self.src_pcd = None
+        self.device = config.device
+        self.config = config
+        self.deformation_model = config.deformation_model
+        self.landmarks = None
+        self._solver = None
+        self._solver_key = None
+        self.NDP = None
+        self.last_iters = None
+        self.last_losses = None
+
+    def load_pcds(self, src, tgt, landmarks=None):
+        if type(src) in [np.ndarray]:
+            src = torch.from_numpy(src)
+            tgt = torch.from_numpy(tgt)
+        self.src_pcd = src.to(self.device)
+        self.tgt_pcd = tgt.to(self.device)
+        self.landmarks = landmarks
+
+    def register(self, **kwargs):
+        if self.deformation_model == "NDP":  # deformation pyramid
+            return self.optimize_deformation_pyramid(**kwargs)
+        if self.deformation_model in ("Sinkhorn", "ED", "NSFP", "Nerfies"):
+            raise NotImplementedError(
+                f"deformation_model {self.deformation_model!r} is one of the paper's comparison methods "
+                "(model/registration.py:265-572) and is outside the scope of the B200 NDP path")
+        raise KeyError()
+
+    # ------------------------------------------------------------------------------------------
+    def _get_solver(self, npairs: int, ns: int, nt: int) -> ops.Solver:
+        c = self.config
+        key = (c.samples, c.m, c.k0, c.depth, c.width, c.motion_type, c.rotation_format, c.iters,
+               c.max_break_count, c.break_threshold_ratio, c.lr, str(self.src_pcd.device))
+        s = self._solver
+        if (s is None or self._solver_key != key or s.cfg.max_pairs < npairs or s.cfg.max_src_points < ns
+                or s.cfg.max_tgt_points < nt):
+            if s is not None:
+                s.close()
+            cap = lambda v: int(max(v, 1024) * 1.25)
+            self._solver = ops.Solver(max_pairs=npairs, max_src_points=cap(ns), max_tgt_points=cap(nt),
+                                      samples=c.samples, levels=c.m, k0=c.k0, depth=c.depth, width=c.width,
+                                      motion=c.motion_type, rotation_format=c.rotation_format, iters=c.iters,
+                                      max_break_count=c.max_break_count,
+                                      break_threshold_ratio=c.break_threshold_ratio, lr=c.lr, trunc=1e9)
+            self._solver_key = key
+        return self._solver
+
+    def _build_pyramid(self):
+        config = self.config
+        return Deformation_Pyramid(depth=config.depth, width=config.width, device=self.device, k0=config.k0,
+                                   m=config.m, nonrigidity_est=config.w_reg > 0,
+                                   rotation_format=config.rotation_format, motion=config.motion_type)
+
+    def optimize_deformation_pyramid(self, visualize=False, timer=None):
+        config = self.config
+        if visualize:
+            raise NotImplementedError("visualisation (mayavi, utils/vis.py) is outside the scope of this package")
+        if self.landmarks is not None or config.w_reg > 0:
+            return self._optimize_stepwise(timer)
+
+        NDP = self._build_pyramid()                              # consumes the RNG first (:133-140)
+        self.src_pcd = self.src_pcd.to(self.device)
+        src, tgt = self.src_pcd.contiguous(), self.tgt_pcd.contiguous()
+        if src.dtype != torch.float32 or tgt.dtype != torch.float32:
+            raise ValueError("float32 point clouds expected")
+        sp = torch.randperm(src.shape[0])[:config.samples].to(torch.int32)     # :156-159
+        tp = torch.randperm(tgt.shape[0])[:config.samples].to(torch.int32)
+        dev = src.device
+        flat = NDP.flat_parameters()
+        solver = self._get_solver(1, src.shape[0], tgt.shape[0])
+        if timer: timer.tic("ndp_fused")
+        warped, iters, losses = solver.register([src], [tgt], [flat], [sp.to(dev)], [tp.to(dev)])
+        if timer: timer.toc("ndp_fused")
+        NDP.load_flat_parameters(flat)
+        NDP.gradient_setup(optimized_level=-1)
+        self.NDP, self.last_iters, self.last_losses = NDP, iters[0], losses[0]
+        iter_cnt = {}
+        return warped[0], iter_cnt, timer
+
+    # ------------------------------------------------------------------------------------------
+    def register_batch(self, pairs: Sequence[Tuple[torch.Tensor, torch.Tensor]], seeds: Optional[Sequence[int]] = None,
+                       host: bool = False):
+        """Throughput entry point (not in the reference, which is strictly one pair at a time,
+        eval_nolearned.py:70): registers independent pairs concurrently on one GPU.  With `seeds`,
+        torch.manual_seed(seeds[p]) is applied before pair p's weights and permutations are drawn,
+        which makes every pair's result independent of batching and of the rank it runs on.
+        host=True: clouds are CPU tensors; host<->device copies happen inside the native call.
+        Returns (list of warped clouds, iters [npairs, m], last loss [npairs, m])."""
+        config = self.config
+        if config.w_reg > 0:
+            raise NotImplementedError("register_batch covers the Chamfer-only NDP objective")
+        srcs, tgts, flats, sps, tps = [], [], [], [], []
+        dev = torch.device("cuda", self.device) if isinstance(self.device, int) else torch.device(self.device)
+        for p, (src, tgt) in enumerate(pairs):
+            if seeds is not None:
+                torch.manual_seed(int(seeds[p]))
+            layers_cpu = _init_flat_cpu(config)
+            sp = torch.randperm(src.shape[0])[:config.samples].to(torch.int32)
+            tp = torch.randperm(tgt.shape[0])[:config.samples].to(torch.int32)
+            if host:
+                srcs.append(src.contiguous()); tgts.append(tgt.contiguous()); flats.append(layers_cpu)
+                sps.append(sp); tps.append(tp)
+            else:
+                srcs.append(src.to(dev).contiguous()); tgts.append(tgt.to(dev).contiguous())
+                flats.append(layers_cpu.to(dev)); sps.append(sp.to(dev)); tps.append(tp.to(dev))
+        self.src_pcd = srcs[0] if not host else srcs[0].to(dev)   # keeps _get_solver's device key valid
+        solver = self._get_solver(len(pairs), max(s.shape[0] for s in srcs), max(t.shape[0] for t in tgts))
+        warped, iters, losses = solver.register(srcs, tgts, flats, sps, tps, host=host)
+        self.last_iters, self.last_losses = iters, losses
+        return warped, iters, losses
+
+    # ------------------------------------------------------------------------------------------
+    def _optimize_stepwise(self, timer=None):
+        """registration.py:126-262 with landmarks and/or the nonrigidity regulariser: the
+        reference's control flow over the CUDA autograd ops."""
+        config = self.config
+        max_break_count = config.max_break_count
+        break_threshold_ratio = config.break_threshold_ratio
+        NDP = self._build_pyramid()
+        self.src_pcd = self.src_pcd.to(self.device)
+        src_mean = self.src_pcd.mean(dim=0, keepdims=True)
+        tgt_mean = self.tgt_pcd.mean(dim=0, keepdims=True)
+        src_pcd = self.src_pcd - src_mean
+        tgt_pcd = self.tgt_pcd - tgt_mean
+        src = torch.randperm(src_pcd.shape[0])
+        tgt = torch.randperm(tgt_pcd.shape[0])
+        s_sample = src_pcd[src[: config.samples].to(src_pcd.device)].contiguous()
+        t_sample = tgt_pcd[tgt[: config.samples].to(tgt_pcd.device)].contiguous()
+        use_ldmk = self.landmarks is not None
+        if use_ldmk:
+            src_ldmk = (self.landmarks[0].to(src_pcd.device) - src_mean).contiguous()
+            tgt_ldmk = (self.landmarks[1].to(src_pcd.device) - tgt_mean).contiguous()
+        w_cd = _cfg_get(config, "w_cd", 0.0)
+        iters_done, losses = [], []
+        for level in range(NDP.n_hierarchy):
+            NDP.gradient_setup(optimized_level=level)
+            optimizer = optim.Adam(NDP.pyramid[level].parameters(), lr=config.lr)
+            break_counter = 0
+            loss_prev = 1e+6
+            steps = 0
+            for it in range(config.iters):
+                if use_ldmk:
+                    if w_cd > 0:
+                        src_pts = torch.cat([src_ldmk, s_sample])
+                        warped_pts, data = NDP.warp(src_pts, max_level=level, min_level=level)
+                        warped_ldmk = warped_pts[: len(src_ldmk)]
+                        s_sample_warped = warped_pts[len(src_ldmk):]
+                        loss_ldmk = torch.mean(torch.sum((warped_ldmk - tgt_ldmk) ** 2, dim=-1))
+                        loss_CD = compute_truncated_chamfer_distance(s_sample_warped[None].contiguous(),
+                                                                     t_sample[None], trunc=config.trunc_cd)
+                        loss = loss_ldmk + w_cd * loss_CD
+                    else:
+                        warped_ldmk, data = NDP.warp(src_ldmk, max_level=level, min_level=level)
+                        loss = torch.mean(torch.sum((warped_ldmk - tgt_ldmk) ** 2, dim=-1))
+                else:
+                    if timer: timer.tic("lvl_warp")
+                    s_sample_warped, data = NDP.warp(s_sample, max_level=level, min_level=level)
+                    if timer: timer.toc("lvl_warp")
+                    if timer: timer.tic("Chamfer")
+                    loss = compute_truncated_chamfer_distance(s_sample_warped[None], t_sample[None], trunc=1e+9)
+                    if timer: timer.toc("Chamfer")
+                if level > 0 and config.w_reg > 0:
+                    nonrigidity = data[level][1]
+                    target = torch.zeros_like(nonrigidity)
+                    reg_loss = BCE(nonrigidity, target)
+                    loss = loss + config.w_reg * reg_loss
+                # early stop (registration.py:225-232)
+                lv = loss.item()
+                if lv < 1e-4:
+                    break
+                if abs(loss_prev - lv) < loss_prev * break_threshold_ratio:
+                    break_counter += 1
+                if break_counter >= max_break_count:
+                    break
+                loss_prev = lv
+                if timer: timer.tic("backprop")
+                optimizer.zero_grad()
+                loss.backward()
+                optimizer.step()
+                if timer: timer.toc("backprop")
+                steps += 1
+            iters_done.append(steps)
+            losses.append(lv if config.iters > 0 else float("nan"))
+            if use_ldmk:
+                src_ldmk = warped_ldmk.detach()
+                if w_cd > 0:
+                    s_sample = s_sample_warped.detach().contiguous()
+            else:
+                s_sample = s_sample_warped.detach()
+        NDP.gradient_setup(optimized_level=-1)
+        with torch.no_grad():
+            warped_pcd, data = NDP.warp(src_pcd.contiguous())
+        warped_pcd = warped_pcd + tgt_mean
+        self.NDP = NDP
+        self.last_iters = torch.tensor(iters_done, dtype=torch.int32)
+        self.last_losses = torch.tensor(losses, dtype=torch.float32)
+        iter_cnt = {}
+        return warped_pcd, iter_cnt, timer
+
+
+def _init_flat_cpu(config) -> torch.Tensor:
+    """Fresh weights of a whole pyramid drawn on the CPU in the reference's RNG order, flattened
+    (level 0 first).  Building the nn.Modules on the CPU never touches the CUDA library."""
+    from .nets import NDPLayer
+    chunks = []
+    for i in range(config.m):
+        layer = NDPLayer(config.depth, config.width, config.k0, i + 1, config.rotation_format,
+                         nonrigidity_est=False, motion=config.motion_type)
+        chunks += [p.detach().reshape(-1) for p in layer.parameters()]
+    return torch.cat(chunks).contiguous()

@@ -164,7 +164,7 @@ class Solver:
     def __init__(self, *, max_pairs: int, max_src_points: int, max_tgt_points: int, samples: int, levels: int,
                  k0: int, depth: int, width: int, motion: str, rotation_format: str, iters: int,
                  max_break_count: int, break_threshold_ratio: float, lr: float, trunc: float = 1e9,
-                 record_loss: bool = False, lib=None):
+                 record_loss: bool = False, profile_every: int = 0, lib=None):
         self.lib = _get(lib)
         if motion not in MOTION:
             raise AssertionError(f"motion must be one of {list(MOTION)}")
@@ -172,7 +172,7 @@ class Solver:
                              int(k0), int(depth), int(width), MOTION[motion],
                              ROT_FORMAT.get(rotation_format, 0), int(iters),
                              int(min(max_break_count, 2 ** 31 - 1)), float(break_threshold_ratio), float(lr),
-                             float(trunc), int(bool(record_loss)))
+                             float(trunc), int(bool(record_loss)), int(profile_every))
         h = ctypes.c_void_p(0)
         _lib.check(self.lib, self.lib.ndp_solver_create(ctypes.byref(self.cfg), ctypes.byref(h)), "ndp_solver_create")
         self.handle = h
@@ -245,6 +245,15 @@ class Solver:
                                                 _ptr(iters), _ptr(loss), stream)
             _lib.check(lib, rc, "ndp_solver_register_device")
         return warped, iters, loss
+
+    KERNELS = ("warp_fwd", "nn_search", "chamfer_epilogue", "warp_bwd", "reduce_adam")
+
+    def profile(self):
+        """Sampled device time: ({kernel: accumulated ms}, number of sampled iterations)."""
+        ms = (ctypes.c_double * 5)()
+        n = ctypes.c_int64(0)
+        _lib.check(self.lib, self.lib.ndp_solver_profile(self.handle, ms, ctypes.byref(n)), "ndp_solver_profile")
+        return dict(zip(self.KERNELS, [float(v) for v in ms])), int(n.value)
 
     def losses(self, pair: int) -> torch.Tensor:
         out = torch.full((self.cfg.levels, self.cfg.iters), float("nan"), dtype=torch.float32)

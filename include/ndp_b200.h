@@ -108,6 +108,8 @@ typedef struct ndp_solver_cfg {
     double lr;                  /* NDP.yaml:9 (Python float in torch.optim.Adam => double)        */
     float trunc;                /* 1e9 on the NDP path (registration.py:212)                      */
     int32_t record_loss;        /* 1: keep the per-iteration loss curve (see ndp_solver_losses)   */
+    int32_t profile_every;      /* k > 0: bracket the kernels of every k-th iteration with CUDA
+                                   events on `stream` (see ndp_solver_profile); 0: off            */
 } ndp_solver_cfg;
 
 typedef struct ndp_solver ndp_solver;
@@ -144,6 +146,10 @@ int ndp_solver_register_device(ndp_solver* s, int32_t npairs, const float* const
 int ndp_solver_losses(ndp_solver* s, int32_t pair, float* out, void* stream);
 /* Number of kernels launched by this solver since creation (bench.py's gpu_launches). */
 int64_t ndp_solver_launch_count(const ndp_solver* s);
+/* Sampled device time per kernel since creation (profile_every > 0): ms[5] = accumulated
+ * milliseconds of {warp forward, NN search, Chamfer epilogue, warp backward, reduce+Adam} over
+ * *samples sampled iterations (each sample is one launch of each kernel over all active pairs). */
+int ndp_solver_profile(const ndp_solver* s, double* ms, int64_t* samples);
 
 #ifdef __cplusplus
 }

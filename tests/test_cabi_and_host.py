@@ -1,0 +1,135 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/ndp_b200.h declares (no compute
+calls without a GPU), the host-side mirror constructs like the reference, config shim, loud failure
+without a GPU."""
+import ctypes
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from deformationpyramid_b200 import _lib, build as ndp_build
+from deformationpyramid_b200.config import AttrDict, load_config, ndp_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "ndp_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(ndp_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_and_binding_agree():
+    assert _header_symbols() == sorted(_lib.EXPORTS)
+
+
+def test_library_builds_loads_and_exports_every_symbol():
+    path = ndp_build.build()
+    lib = ctypes.CDLL(path)                      # loading needs no GPU
+    for name in _header_symbols():
+        assert hasattr(lib, name), name
+    _lib.bind(lib)
+    assert lib.ndp_version() >= 100
+    # pure host arithmetic entry points may be called without a device
+    cfg = _lib.LayerCfg(128, 3, 0, 0, 0, 2.0 ** -7, 0.001)
+    assert lib.ndp_param_count(ctypes.byref(cfg)) == 34694
+    cfg2 = _lib.LayerCfg(128, 3, 1, 1, 0, 2.0 ** -7, 0.001)
+    assert lib.ndp_param_count(ctypes.byref(cfg2)) == 34823
+    assert lib.ndp_saved_floats_per_point(ctypes.byref(cfg)) == 3 * 128 + 12
+    bad = _lib.LayerCfg(64, 3, 0, 0, 0, 1.0, 0.001)
+    assert lib.ndp_param_count(ctypes.byref(bad)) == -1
+    assert b"width" in lib.ndp_last_error()
+
+
+def test_sass_shows_bulk_tma_and_fp32_pipeline():
+    """The built cubin carries the Blackwell bulk-copy (UBLKCP) path and was built for sm_100a."""
+    import subprocess
+    path = ndp_build.build()
+    out = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert "UBLKCP" in out          # cp.async.bulk (TMA) staging of the MLP weights
+    assert "FFMA" in out
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the GPU-less failure mode")
+def test_product_path_fails_loudly_without_gpu():
+    _lib._LIB = None
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+    from deformationpyramid_b200.model.registration import Registration
+    reg = Registration(ndp_config(device=torch.device("cpu"), samples=10, m=1, iters=1))
+    reg.load_pcds(np.zeros((20, 3), np.float32), np.ones((20, 3), np.float32))
+    with pytest.raises((RuntimeError, ValueError)):
+        reg.register()
+
+
+def test_no_product_module_imports_the_oracle():
+    pkg = os.path.join(ROOT, "deformationpyramid_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("oracle/knn_oracle.c", "").replace("see oracle", "") or f == "build.py", \
+                    os.path.join(dirpath, f)
+
+
+def test_constructor_matches_reference_rng_stream(golden_dir):
+    from deformationpyramid_b200.model.nets import NDPLayer
+    G = np.load(os.path.join(golden_dir, "layers.npz"))
+    for vi, meta in enumerate(G["meta"]):
+        motion, fmt, nr, m, seed, depth = str(meta).split(",")
+        torch.manual_seed(int(seed))
+        layer = NDPLayer(int(depth), 128, -8, int(m), fmt, nonrigidity_est=bool(int(nr)), motion=motion)
+        flat = torch.cat([p.detach().reshape(-1) for p in layer.parameters()]).numpy()
+        assert hashlib.sha256(flat.tobytes()).hexdigest() == str(G[f"v{vi}_init_sha"]), meta
+        assert [n for n, _ in layer.named_parameters()] == list(G[f"v{vi}_names"])
+
+
+def test_flatten_parameters_keeps_values_and_optimizer_semantics():
+    from deformationpyramid_b200.model.nets import NDPLayer
+    torch.manual_seed(0)
+    layer = NDPLayer(3, 128, -8, 2, "axis_angle")
+    before = [p.detach().clone() for p in layer.parameters()]
+    flat = layer.flatten_parameters_()
+    for p, b in zip(layer.parameters(), before):
+        assert torch.equal(p, b)
+    assert layer._flat_view(tuple(layer.parameters())) is flat
+    opt = torch.optim.Adam(layer.parameters(), lr=0.1)
+    for p in layer.parameters():
+        p.grad = torch.ones_like(p)
+    opt.step()
+    assert layer._flat_view(tuple(layer.parameters())) is flat            # in-place update keeps the views
+    assert torch.allclose(flat[:5], torch.cat([b.reshape(-1) for b in before])[:5] - 0.1, atol=1e-6)
+
+
+def test_config_shim(tmp_path):
+    p = tmp_path / "c.yaml"
+    p.write_text("iters: 500\nlr: 0.01\nfolder: a\nexp_dir: !join [x, 3]\nsplit: {test: '4DMatch-F'}\n")
+    c = load_config(str(p))
+    assert c.iters == 500 and c.exp_dir == "x_3" and c.split.test == "4DMatch-F"
+    c.device = 0
+    assert c["device"] == 0
+    with pytest.raises(AttributeError):
+        c.missing
+    d = ndp_config(samples=8192)
+    assert d.samples == 8192 and d.m == 9 and d.k0 == -8 and d.motion_type == "SE3"
+
+
+def test_install_as_model_aliases():
+    import sys
+    import deformationpyramid_b200 as pkg
+    saved = {k: sys.modules.get(k) for k in ("model", "model.nets", "model.loss", "model.registration")}
+    try:
+        pkg.install_as_model()
+        from model.nets import Deformation_Pyramid            # noqa: F401  (the reference scripts' imports)
+        from model.loss import compute_truncated_chamfer_distance  # noqa: F401
+        from model.registration import Registration           # noqa: F401
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

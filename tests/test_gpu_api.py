@@ -1,0 +1,178 @@
+"""The reference-shaped Python API on the GPU: NDPLayer / Deformation_Pyramid autograd path
+(shape_transfer.py's usage), compute_truncated_chamfer_distance, Registration.register()."""
+import numpy as np
+import pytest
+import torch
+
+from deformationpyramid_b200.config import ndp_config
+from deformationpyramid_b200.synthetic import make_pair
+from oracle import ndp_oracle as O
+from parity_cases import REL_TOL, rel
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+
+
+def _oracle_params(layer):
+    return {n: p.detach().cpu().clone() for n, p in layer.named_parameters()}
+
+
+@pytest.mark.parametrize("motion,fmt,nr", [("SE3", "axis_angle", False), ("Sim3", "euler", False),
+                                           ("SE3", "quaternion", True), ("sflow", "axis_angle", True),
+                                           ("Sim3", "6D", False)])
+def test_ndplayer_autograd_matches_oracle(motion, fmt, nr):
+    from deformationpyramid_b200.model.nets import NDPLayer
+    torch.manual_seed(3)
+    layer = NDPLayer(3, 128, -8, 4, fmt, nonrigidity_est=nr, motion=motion)
+    with torch.no_grad():
+        for p in layer.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+        if hasattr(layer, "rot_brach"):
+            layer.rot_brach.bias.add_(200.0)
+    layer = layer.to(DEV)
+    layer.flatten_parameters_()
+    spec = O.LayerSpec(3, 128, -8, 4, fmt, nr, motion)
+    P = {n: v.requires_grad_(True) for n, v in _oracle_params(layer).items()}
+    x = (torch.rand(333, 3) - 0.5)
+    xo = x.clone().requires_grad_(True)
+    yo, nuo = O.layer_forward(spec, P, xo)
+    w = torch.randn(333, 3)
+    obj = (yo * w).sum() + (0 if nuo is None else (nuo * nuo).sum())
+    go = torch.autograd.grad(obj, [xo] + [P[n] for n, _ in O.param_layout(spec)])
+
+    xg = x.to(DEV).requires_grad_(True)
+    y, nu = layer(xg)
+    assert (nu is None) == (not nr)
+    obj2 = (y * w.to(DEV)).sum() + (0 if nu is None else (nu * nu).sum())
+    obj2.backward()
+    assert rel(y.detach().cpu().numpy(), yo.detach().numpy()) < REL_TOL
+    assert rel(xg.grad.cpu().numpy(), go[0].numpy()) < REL_TOL
+    for (n, p), g in zip(layer.named_parameters(), go[1:]):
+        assert rel(p.grad.cpu().numpy(), g.numpy()) < 5 * REL_TOL, n
+
+
+def test_constructor_rng_and_state_dict_match_reference_layout(golden_dir):
+    import hashlib, os
+    from deformationpyramid_b200.model.nets import NDPLayer
+    G = np.load(os.path.join(golden_dir, "layers.npz"))
+    for vi, meta in enumerate(G["meta"]):
+        motion, fmt, nr, m, seed, depth = str(meta).split(",")
+        torch.manual_seed(int(seed))
+        layer = NDPLayer(int(depth), 128, -8, int(m), fmt, nonrigidity_est=bool(int(nr)), motion=motion)
+        flat = torch.cat([p.detach().reshape(-1) for p in layer.parameters()]).numpy()
+        assert hashlib.sha256(flat.tobytes()).hexdigest() == str(G[f"v{vi}_init_sha"])
+        assert [n for n, _ in layer.named_parameters()] == list(G[f"v{vi}_names"])
+
+
+def test_shape_transfer_style_loop_matches_oracle():
+    """shape_transfer.py:116-157 verbatim control flow (stock torch.optim.Adam on the layer's
+    parameters, loss.item() early stop) over the CUDA ops vs the oracle driver."""
+    import torch.optim as optim
+    from deformationpyramid_b200.model.nets import Deformation_Pyramid
+    from deformationpyramid_b200.model.loss import compute_truncated_chamfer_distance
+    src, tgt = make_pair(7, 500, 450)
+    levels, iters = 2, 6
+    torch.manual_seed(11)
+    NDP = Deformation_Pyramid(depth=3, width=128, device=DEV, k0=-8, m=levels, nonrigidity_est=False,
+                              rotation_format="euler", motion="Sim3")
+    init = [_oracle_params(l) for l in NDP.pyramid]
+    cfgo = O.NDPConfig(iters=iters, samples=10 ** 6, m=levels, motion_type="Sim3", rotation_format="euler",
+                       max_break_count=10 ** 9)
+    ref = O.optimize_pair(cfgo, src, tgt, init=init, src_perm=torch.arange(500), tgt_perm=torch.arange(450))
+
+    s = src.to(DEV); t = tgt.to(DEV)
+    s_mean, t_mean = s.mean(0, keepdim=True), t.mean(0, keepdim=True)
+    s_sample, t_sample = s - s_mean, t - t_mean
+    curve = []
+    for level in range(NDP.n_hierarchy):
+        NDP.gradient_setup(optimized_level=level)
+        optimizer = optim.Adam(NDP.pyramid[level].parameters(), lr=0.01)
+        for it in range(iters):
+            s_warped, data = NDP.warp(s_sample, max_level=level, min_level=level)
+            loss = compute_truncated_chamfer_distance(s_warped[None], t_sample[None], trunc=1e+9)
+            curve.append(loss.item())
+            optimizer.zero_grad()
+            loss.backward()
+            optimizer.step()
+        s_sample = s_warped.detach()
+    NDP.gradient_setup(optimized_level=-1)
+    warped, data = NDP.warp(s - s_mean)
+    refc = np.array([l for c in ref.loss_curve for l in c])
+    assert np.allclose(np.array(curve), refc, rtol=2e-4)
+    assert rel((warped + t_mean).detach().cpu().numpy(), ref.warped.numpy()) < 1e-3
+    assert set(data.keys()) == set(range(levels)) and data[0][1] is None
+
+
+def test_registration_register_matches_oracle():
+    from deformationpyramid_b200.model.registration import Registration
+    cfg = ndp_config(samples=400, m=3, iters=6, max_break_count=10 ** 9, device=0)
+    src, tgt = make_pair(31, 900, 820)
+    torch.manual_seed(4)
+    reg = Registration(cfg)
+    reg.load_pcds(src.numpy(), tgt.numpy())
+    warped, iter_cnt, timer = reg.register(timer=None)
+    assert iter_cnt == {} and warped.shape == (900, 3) and warped.is_cuda
+    assert reg.src_pcd.is_cuda
+    cfgo = O.NDPConfig(iters=6, samples=400, m=3, max_break_count=10 ** 9)
+    torch.manual_seed(4)
+    ref = O.optimize_pair(cfgo, src, tgt)
+    assert [int(v) for v in reg.last_iters] == ref.iters_per_level
+    assert np.allclose(reg.last_losses.numpy(), np.array(ref.loss_per_level), rtol=2e-4)
+    assert rel(warped.cpu().numpy(), ref.warped.numpy()) < 1e-3
+
+
+def test_registration_stepwise_landmarks_and_nonrigidity():
+    """LNDP branch (registration.py:187-203) and the w_reg branch (:216-220) run on the CUDA ops."""
+    from deformationpyramid_b200.model.registration import Registration
+    src, tgt = make_pair(33, 600, 600)
+    ldmk_s, ldmk_t = src[:40].clone(), src[:40].clone() + 0.03
+    cfg = ndp_config(samples=300, m=2, iters=5, w_cd=0.1, trunc_cd=0.25, device=0)
+    torch.manual_seed(9)
+    reg = Registration(cfg)
+    reg.load_pcds(src, tgt, landmarks=(ldmk_s.cuda(), ldmk_t.cuda()))
+    warped, _, _ = reg.register()
+    cfgo = O.NDPConfig(iters=5, samples=300, m=2, w_cd=0.1, trunc_cd=0.25)
+    torch.manual_seed(9)
+    ref = O.optimize_pair(cfgo, src, tgt, landmarks=(ldmk_s, ldmk_t))
+    assert rel(warped.cpu().numpy(), ref.warped.numpy()) < 1e-3
+    cfg2 = ndp_config(samples=300, m=2, iters=4, w_reg=0.1, device=0)
+    torch.manual_seed(10)
+    reg2 = Registration(cfg2)
+    reg2.load_pcds(src, tgt)
+    warped2, _, _ = reg2.register()
+    cfgo2 = O.NDPConfig(iters=4, samples=300, m=2, w_reg=0.1)
+    torch.manual_seed(10)
+    ref2 = O.optimize_pair(cfgo2, src, tgt)
+    assert rel(warped2.cpu().numpy(), ref2.warped.numpy()) < 1e-3
+
+
+def test_register_batch_seeded_is_batch_independent():
+    from deformationpyramid_b200.model.registration import Registration
+    cfg = ndp_config(samples=256, m=2, iters=10, device=0)
+    pairs = [make_pair(40 + p, 500, 480) for p in range(3)]
+    reg = Registration(cfg)
+    w_all, it_all, _ = reg.register_batch(pairs, seeds=[5, 6, 7])
+    w_one, it_one, _ = reg.register_batch([pairs[2]], seeds=[7])
+    assert torch.equal(w_all[2], w_one[0]) and torch.equal(it_all[2], it_one[0])
+    w_host, _, _ = reg.register_batch([(s.pin_memory(), t.pin_memory()) for s, t in pairs], seeds=[5, 6, 7], host=True)
+    assert torch.equal(w_host[1], w_all[1].cpu())
+
+
+def test_errors_are_loud():
+    from deformationpyramid_b200.model.loss import compute_truncated_chamfer_distance
+    from deformationpyramid_b200.model.nets import Deformation_Pyramid
+    with pytest.raises(AssertionError):
+        Deformation_Pyramid(3, 128, DEV, -8, 2, "euler", motion="rigid")
+    with pytest.raises(ValueError):
+        compute_truncated_chamfer_distance(torch.zeros(5, 3, device=DEV), torch.zeros(1, 5, 3, device=DEV))
+    with pytest.raises(ValueError):
+        compute_truncated_chamfer_distance(torch.zeros(1, 5, 3, device=DEV), torch.zeros(2, 5, 3, device=DEV))
+    with pytest.raises(RuntimeError):
+        compute_truncated_chamfer_distance(torch.zeros(1, 5, 3), torch.zeros(1, 5, 3))
+    from deformationpyramid_b200.model.registration import Registration
+    with pytest.raises(KeyError):
+        Registration(ndp_config(deformation_model="bogus", device=0)).register()
+    with pytest.raises(ValueError):
+        from deformationpyramid_b200 import ops
+        ops.Solver(max_pairs=1, max_src_points=10, max_tgt_points=10, samples=10, levels=1, k0=-8, depth=3, width=64,
+                   motion="SE3", rotation_format="euler", iters=1, max_break_count=1, break_threshold_ratio=0.1, lr=0.01)
