@@ -27,8 +27,8 @@ def test_ndplayer_autograd_matches_oracle(motion, fmt, nr):
     with torch.no_grad():
         for p in layer.parameters():
             p.add_(0.05 * torch.randn_like(p))
-        if hasattr(layer, "rot_brach"):
-            layer.rot_brach.bias.add_(200.0)
+        if hasattr(layer, "rot_brach"):     # O(0.3 rad) generic rotations (well-conditioned for 6D too)
+            layer.rot_brach.bias.add_(300.0 * torch.randn(layer.rot_brach.bias.shape))
     layer = layer.to(DEV)
     layer.flatten_parameters_()
     spec = O.LayerSpec(3, 128, -8, 4, fmt, nr, motion)
