@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--mode", default="fixed", choices=["fixed", "asconfigured"])
     ap.add_argument("--cpu-sample-iters", type=int, default=3, help="iterations per level of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nn-mode", type=int, default=0, help="0: exact culled NN search (default), 1: brute force")
     return ap.parse_args()
 
 
@@ -56,7 +57,7 @@ def workload(a):
                         + ("early stop disabled (fixed-iter mode A)" if a.mode == "fixed"
                            else "shipped early-stop thresholds (mode B)"),
             "points": a.points, "levels": a.levels, "iters_per_level": a.iters, "mode": a.mode,
-            "pairs_per_step_per_gpu": a.pairs, "width": 128, "depth": 3, "motion": "SE3", "rotation": "axis_angle",
+            "pairs_per_step_per_gpu": a.pairs, "nn_search": "exact culled (Morton blocks + boxes + seeds)" if a.nn_mode == 0 else "brute force", "width": 128, "depth": 3, "motion": "SE3", "rotation": "axis_angle",
             "l2": "flushed (256 MiB write) between timed steps; one step streams ~100 MiB of saved activations "
                   "and gradient partials per iteration"}
 
@@ -202,7 +203,7 @@ def main():
     solver = ops.Solver(max_pairs=B, max_src_points=N, max_tgt_points=N, samples=N, levels=a.levels, k0=cfg.k0,
                         depth=cfg.depth, width=cfg.width, motion=cfg.motion_type, rotation_format=cfg.rotation_format,
                         iters=a.iters, max_break_count=mbc, break_threshold_ratio=cfg.break_threshold_ratio, lr=cfg.lr,
-                        profile_every=16)
+                        profile_every=16, nn_mode=a.nn_mode)
     d_src = [s.to(dev) for s, _ in pairs]
     d_tgt = [t.to(dev) for _, t in pairs]
     flats0, sps, tps = [], [], []

@@ -36,7 +36,7 @@ class SolverCfg(ctypes.Structure):
                 ("samples", c_int32), ("levels", c_int32), ("k0", c_int32), ("depth", c_int32),
                 ("width", c_int32), ("motion", c_int32), ("rot_format", c_int32), ("iters", c_int32),
                 ("max_break_count", c_int32), ("break_threshold_ratio", c_float), ("lr", c_double),
-                ("trunc", c_float), ("record_loss", c_int32), ("profile_every", c_int32)]
+                ("trunc", c_float), ("record_loss", c_int32), ("profile_every", c_int32), ("nn_mode", c_int32)]
 
 
 def bind(lib: ctypes.CDLL) -> ctypes.CDLL:

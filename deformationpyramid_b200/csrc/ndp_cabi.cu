@@ -113,7 +113,8 @@ extern "C" int ndp_layer_forward(const ndp_layer_cfg* c, const float* params, co
     a.x = x; a.x_stride = 0; a.y = y; a.y_stride = 0; a.nu = nu; a.nu_stride = 0;
     a.act = saved; a.act_stride = 0; a.act_layer_stride = n * NDP_W;
     a.zsave = saved ? saved + (long long)c->depth * n * NDP_W : nullptr; a.z_stride = 0;
-    a.y_add = nullptr; a.y_add_stride = 0; a.n = (int)n; a.counts = nullptr; a.state = nullptr; a.npairs = 1;
+    a.y_add = nullptr; a.y_add_stride = 0; a.y4 = nullptr; a.y4_stride = 0; a.orig = nullptr; a.orig_stride = 0;
+    a.ybox = nullptr; a.box_stride = 0; a.n = (int)n; a.counts = nullptr; a.state = nullptr; a.npairs = 1;
     ndp_launch_fwd(a, (cudaStream_t)stream);
     CK(cudaGetLastError());
     return NDP_OK;
@@ -227,6 +228,12 @@ struct ndp_solver {
     float *act = nullptr, *zsave = nullptr, *gx = nullptr, *partials = nullptr, *loss = nullptr, *loss_hist = nullptr;
     unsigned long long* gacc = nullptr;
     float2* nnpart = nullptr;
+    // culled NN search (nn_mode 0): Morton order, float4 copies, block boxes, previous-NN seeds
+    unsigned long long* keys = nullptr;
+    float *sraw = nullptr, *traw = nullptr, *bounds = nullptr, *xbox = nullptr, *tbox = nullptr;
+    float4 *x4 = nullptr, *t4 = nullptr;
+    int *orig_s = nullptr, *orig_t = nullptr, *prev_x = nullptr, *prev_y = nullptr;
+    int npad = 0, S128 = 0, nboxes = 0;
     double* blocksums = nullptr;
     int* counters = nullptr;
     NdpPairState* state = nullptr;
@@ -287,6 +294,9 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
     s->B = c->max_pairs; s->S = c->samples; s->NS = c->max_src_points; s->NT = c->max_tgt_points;
     s->tiles = (s->S + NDP_TP - 1) / NDP_TP;
     s->plan = nn_plan(s->S, s->S);
+    if (c->nn_mode == 0) { s->plan.chunks = 1; s->plan.chunk_targets = 1 << 30; }
+    s->S128 = (s->S + NDP_TP - 1) / NDP_TP * NDP_TP; s->nboxes = s->S128 / 32;
+    s->npad = 1; while (s->npad < s->S) s->npad <<= 1;
     const long long B = s->B, S = s->S;
     int e = NDP_OK;
 #define DA(ptr, count) if (!e) e = dalloc(s, &s->ptr, (count))
@@ -299,6 +309,11 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
     DA(partials, B * s->tiles * s->Ppad); DA(loss, B);
     DA(nnpart, B * 2 * s->plan.chunks * s->plan.qpitch); DA(blocksums, B * s->plan.blocks * 2); DA(counters, B);
     DA(state, B);
+    if (c->nn_mode == 0) {
+        DA(keys, B * 2 * s->npad); DA(sraw, B * S * 3); DA(traw, B * S * 3); DA(bounds, B * 12);
+        DA(xbox, B * s->nboxes * 8); DA(tbox, B * s->nboxes * 8); DA(x4, B * s->S128); DA(t4, B * s->S128);
+        DA(orig_s, B * S); DA(orig_t, B * S); DA(prev_x, B * S); DA(prev_y, B * S);
+    }
     if (c->record_loss) DA(loss_hist, B * c->levels * (long long)c->iters);
 #undef DA
     if (!e && cudaMallocHost((void**)&s->h_state, sizeof(NdpPairState) * B) != cudaSuccess) e = fail(NDP_E_NOMEM, "cudaMallocHost failed");
@@ -336,13 +351,26 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
     g.in = s->src_raw; g.in_stride = (long long)s->NS * 3; g.idx = nullptr; g.idx_stride = 0; g.which = 0;
     g.out = s->src_c; g.out_stride = (long long)s->NS * 3; g.n = s->NS; g.counts = s->nscount;
     ndp_launch_gather_center(g, st);
+    const bool culled = c.nn_mode == 0;
     g.idx = have_perm_s ? s->perm_s : nullptr; g.idx_stride = S;
-    g.out = s->smp[0]; g.out_stride = S * 3; g.n = s->S; g.counts = s->ncount;
+    g.out = culled ? s->sraw : s->smp[0]; g.out_stride = S * 3; g.n = s->S; g.counts = s->ncount;
     ndp_launch_gather_center(g, st);
     g.in = s->tgt_raw; g.in_stride = (long long)s->NT * 3; g.idx = have_perm_t ? s->perm_t : nullptr; g.which = 1;
-    g.out = s->tsmp; g.counts = s->mcount;
+    g.out = culled ? s->traw : s->tsmp; g.counts = s->mcount;
     ndp_launch_gather_center(g, st);
     s->launches += 4;
+    if (culled) {
+        // Morton order of both sampled clouds, kept for every level and iteration (ndp_spatial.cu)
+        NdpSortArgs so;
+        so.src = s->sraw; so.tgt = s->traw; so.cloud_stride = S * 3; so.n = s->S; so.ncounts = s->ncount;
+        so.m = s->S; so.mcounts = s->mcount; so.bounds = s->bounds; so.keys = s->keys; so.npad = s->npad;
+        so.src_sorted = s->smp[0]; so.tgt_sorted = s->tsmp; so.src_orig = s->orig_s; so.tgt_orig = s->orig_t;
+        so.orig_stride = S; so.tgt4 = s->t4; so.p4_stride = s->S128; so.tgt_box = s->tbox; so.box_stride = s->nboxes;
+        so.npairs = npairs;
+        s->launches += ndp_launch_sort(so, st);
+        CK(cudaMemsetAsync(s->prev_x, 0xff, sizeof(int) * (size_t)npairs * S, st));
+        CK(cudaMemsetAsync(s->prev_y, 0xff, sizeof(int) * (size_t)npairs * S, st));
+    }
 
     int cur = 0;
     const int poll = (c.max_break_count > c.iters) ? 64 : 8;
@@ -353,6 +381,9 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         ndp_launch_state_reset(s->state, npairs, st);
         CK(cudaMemsetAsync(s->adam_m, 0, sizeof(float) * (size_t)npairs * s->Ppad, st));
         CK(cudaMemsetAsync(s->adam_v, 0, sizeof(float) * (size_t)npairs * s->Ppad, st));
+        // a pair that stops early has scattered its last Chamfer gradient without a backward pass
+        // consuming it: clear the fixed-point accumulators before every level
+        CK(cudaMemsetAsync(s->gacc, 0, sizeof(unsigned long long) * (size_t)npairs * S * 3, st));
         NdpPackArgs pk; pk.lay = L; pk.params = lvl_params; pk.params_stride = pstride; pk.pack = s->pack; pk.pack_stride = s->packn; pk.npairs = npairs;
         ndp_launch_pack(pk, st);
         s->launches += 2;
@@ -362,6 +393,8 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         f.x = s->smp[cur]; f.x_stride = S * 3; f.y = s->smp[cur ^ 1]; f.y_stride = S * 3; f.nu = nullptr; f.nu_stride = 0;
         f.act = s->act; f.act_stride = (long long)c.depth * S * NDP_W; f.act_layer_stride = S * NDP_W;
         f.zsave = s->zsave; f.z_stride = S * NDP_ZPITCH; f.y_add = nullptr; f.y_add_stride = 0;
+        f.y4 = culled ? s->x4 : nullptr; f.y4_stride = s->S128; f.orig = s->orig_s; f.orig_stride = S;
+        f.ybox = culled ? s->xbox : nullptr; f.box_stride = s->nboxes;
         f.n = s->S; f.counts = s->ncount; f.state = s->state; f.npairs = npairs;
 
         NdpChamferArgs ch;
@@ -370,6 +403,11 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         ch.nn.part = s->nnpart; ch.nn.part_pair_stride = 2LL * s->plan.chunks * s->plan.qpitch;
         ch.nn.qpitch = s->plan.qpitch; ch.nn.chunks = s->plan.chunks; ch.nn.chunk_targets = s->plan.chunk_targets;
         ch.nn.state = s->state; ch.nn.npairs = npairs;
+        NdpPrunedArgs pn;
+        pn.x4 = s->x4; pn.y4 = s->t4; pn.p4_stride = s->S128; pn.xbox = s->xbox; pn.ybox = s->tbox; pn.box_stride = s->nboxes;
+        pn.prev_x = s->prev_x; pn.prev_y = s->prev_y; pn.prev_stride = S; pn.n = s->S; pn.ncounts = s->ncount;
+        pn.m = s->S; pn.mcounts = s->mcount; pn.part = s->nnpart; pn.part_pair_stride = ch.nn.part_pair_stride;
+        pn.qpitch = s->plan.qpitch; pn.state = s->state; pn.npairs = npairs;
         ch.trunc = c.trunc; ch.gx = s->gx; ch.gx_stride = S * 3; ch.gacc = s->gacc; ch.gacc_stride = S * 3;
         ch.d2x = nullptr; ch.idxx = nullptr; ch.nx_stride = 0; ch.d2y = nullptr; ch.idxy = nullptr; ch.ny_stride = 0;
         ch.blocksums = s->blocksums; ch.blocks_pitch = s->plan.blocks; ch.counters = s->counters; ch.loss_out = s->loss;
@@ -408,7 +446,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
             }
             ndp_launch_fwd(f, st);
             if (prof) CK(cudaEventRecord(ev[1], st));
-            ndp_launch_nn(ch.nn, st);
+            if (culled) ndp_launch_nn_pruned(pn, st); else ndp_launch_nn(ch.nn, st);
             if (prof) CK(cudaEventRecord(ev[2], st));
             ndp_launch_chamfer_reduce(ch, st);
             if (prof) CK(cudaEventRecord(ev[3], st));
@@ -450,6 +488,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         f.nu = nullptr; f.nu_stride = 0; f.act = nullptr; f.act_stride = 0; f.act_layer_stride = 0; f.zsave = nullptr; f.z_stride = 0;
         const bool last = level == c.levels - 1;
         f.y_add = last ? s->means + 3 : nullptr; f.y_add_stride = 6;
+        f.y4 = nullptr; f.y4_stride = 0; f.orig = nullptr; f.orig_stride = 0; f.ybox = nullptr; f.box_stride = 0;
         f.n = s->NS; f.counts = s->nscount; f.state = nullptr; f.npairs = npairs;
         ndp_launch_fwd(f, st);
         s->launches += 2;

@@ -16,6 +16,11 @@ struct NdpFwdArgs {
     long long act_layer_stride;
     float* zsave;        long long z_stride;        // saved head vectors [pair][n_alloc][12] or null
     const float* y_add; int y_add_stride;            // [pair][stride] 3 floats added to the output, or null
+    // optional extras for the culled NN search (ndp_spatial.cu): float4 copy of the output carrying
+    // the original sample index, and the bounding box of every block of 32 consecutive outputs
+    float4* y4;          long long y4_stride;       // [pair][n_pad32] or null
+    const int* orig;     long long orig_stride;     // [pair][n]
+    float* ybox;         long long box_stride;      // [pair][box_stride boxes][8] or null
     int n; const int* counts;                        // points per pair (counts overrides n when non-null)
     const NdpPairState* state;                       // pairs with state.stopped are skipped, or null
     int npairs;
@@ -105,6 +110,31 @@ struct NdpGradFinalizeArgs {                          // gx += fixed-point gacc 
     int npairs;
 };
 void ndp_launch_grad_finalize(const NdpGradFinalizeArgs& a, cudaStream_t s);
+
+// ---- kernel (2), fused-driver variant: Morton ordering + exact culled NN search (ndp_spatial.cu) ---
+struct NdpSortArgs {
+    const float* src; const float* tgt; long long cloud_stride;      // centred samples [pair][S][3]
+    int n; const int* ncounts; int m; const int* mcounts;
+    float* bounds;                                                    // [pair][2][6]
+    unsigned long long* keys; int npad;                               // [pair][2][npad], npad = pow2 >= max(n, m)
+    float* src_sorted; float* tgt_sorted;                             // [pair][S][3]
+    int* src_orig; int* tgt_orig; long long orig_stride;              // sorted position -> sample index
+    float4* tgt4; long long p4_stride;                                // [pair][S_pad32]
+    float* tgt_box; long long box_stride;                             // [pair][box_stride][8]
+    int npairs;
+};
+int ndp_launch_sort(const NdpSortArgs& a, cudaStream_t s);           // returns the number of launches
+
+struct NdpPrunedArgs {
+    const float4* x4; const float4* y4; long long p4_stride;         // warped source / target, sorted, (x,y,z,orig)
+    const float* xbox; const float* ybox; long long box_stride;
+    int* prev_x; int* prev_y; long long prev_stride;                  // previous NN (sorted index), -1 = none
+    int n; const int* ncounts; int m; const int* mcounts;
+    float2* part; long long part_pair_stride; int qpitch;             // [pair][dir][qpitch] (d2, sorted idx bits)
+    const NdpPairState* state;
+    int npairs;
+};
+void ndp_launch_nn_pruned(const NdpPrunedArgs& a, cudaStream_t s);
 
 // ---- small helpers of the per-pair driver -------------------------------------------------------
 struct NdpCenterArgs {                                // registration.py:150-159

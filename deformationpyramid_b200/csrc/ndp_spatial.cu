@@ -1,0 +1,236 @@
+// Kernel (2), fused-driver variant: EXACT nearest neighbour with spatial culling.
+//
+// Same contract as the brute-force search of ndp_chamfer.cu (same fp32 distance expression,
+// lexicographic (distance, original index) minimum => lowest index wins ties, identical results),
+// but most of the N x M distance evaluations are skipped:
+//   * once per pair both sampled clouds are put in Morton (Z-curve) order (30-bit keys, bitonic
+//     sort); the order is kept for all levels and iterations (the warp field is smooth, so a block
+//     of 32 consecutive source points stays compact while it deforms);
+//   * every block of 32 points carries an axis-aligned bounding box (the target's once, the warped
+//     source's re-computed by the forward kernel every iteration);
+//   * a warp owns 32 consecutive queries; its running minima are seeded with the distance to each
+//     query's nearest neighbour of the PREVIOUS iteration (a real candidate => a valid upper bound);
+//   * a target block is scanned only if its box can contain a point at distance <= the current
+//     minimum of some lane.  Box distances are evaluated with the same monotone fp32 expression
+//     (componentwise gaps -> fma chain), so in floating point lb(box) <= d(q, t) for every t in the
+//     box and culling never discards a candidate, not even an exact tie.
+// Reference semantics: pytorch3d knn_points(K=1) as called at model/loss.py:177-178.
+#include "ndp_kernels.h"
+
+#ifdef NDP_EMU
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+#endif
+
+__device__ __forceinline__ float ndp_sqdist3(float qx, float qy, float qz, float tx, float ty, float tz) {
+    const float dx = __fsub_rn(qx, tx), dy = __fsub_rn(qy, ty), dz = __fsub_rn(qz, tz);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+// gap between [alo,ahi] and [blo,bhi] along one axis (0 when they overlap); NaN-free for finite boxes
+__device__ __forceinline__ float ndp_gap(float alo, float ahi, float blo, float bhi) {
+    return fmaxf(0.0f, fmaxf(__fsub_rn(blo, ahi), __fsub_rn(alo, bhi)));
+}
+__device__ __forceinline__ float ndp_sq3(float gx, float gy, float gz) {
+    return __fmaf_rn(gz, gz, __fmaf_rn(gy, gy, __fmul_rn(gx, gx)));
+}
+
+// ---- cloud bounds (one CTA per (pair, cloud)); deterministic min/max tree -----------------------
+__global__ void __launch_bounds__(256) ndp_bounds_kernel(NdpSortArgs a) {
+    __shared__ float lo[3][256], hi[3][256];
+    const int pair = blockIdx.x, which = blockIdx.y, tid = threadIdx.x;
+    const int n = which ? (a.mcounts ? a.mcounts[pair] : a.m) : (a.ncounts ? a.ncounts[pair] : a.n);
+    const float* P = (which ? a.tgt : a.src) + (long long)pair * a.cloud_stride;
+    const float INF = __int_as_float(0x7f800000);
+    float l0 = INF, l1 = INF, l2 = INF, h0 = -INF, h1 = -INF, h2 = -INF;
+    for (int i = tid; i < n; i += 256) {
+        const float x = P[(long long)i * 3], y = P[(long long)i * 3 + 1], z = P[(long long)i * 3 + 2];
+        l0 = fminf(l0, x); l1 = fminf(l1, y); l2 = fminf(l2, z);
+        h0 = fmaxf(h0, x); h1 = fmaxf(h1, y); h2 = fmaxf(h2, z);
+    }
+    lo[0][tid] = l0; lo[1][tid] = l1; lo[2][tid] = l2; hi[0][tid] = h0; hi[1][tid] = h1; hi[2][tid] = h2;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (tid < off)
+            for (int c = 0; c < 3; ++c) {
+                lo[c][tid] = fminf(lo[c][tid], lo[c][tid + off]);
+                hi[c][tid] = fmaxf(hi[c][tid], hi[c][tid + off]);
+            }
+        __syncthreads();
+    }
+    if (tid < 3) {
+        float* b = a.bounds + ((long long)pair * 2 + which) * 6;
+        b[tid] = lo[tid][0]; b[3 + tid] = hi[tid][0];
+    }
+}
+
+__device__ __forceinline__ unsigned ndp_expand10(unsigned v) {   // 10 bits -> every third bit
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+// key = morton30 << 32 | sample index; slots >= n get the maximum key (sorted to the end)
+__global__ void __launch_bounds__(256) ndp_morton_keys_kernel(NdpSortArgs a) {
+    const int pair = blockIdx.y, which = blockIdx.z;
+    const int n = which ? (a.mcounts ? a.mcounts[pair] : a.m) : (a.ncounts ? a.ncounts[pair] : a.n);
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= a.npad) return;
+    unsigned long long* keys = a.keys + ((long long)pair * 2 + which) * a.npad;
+    if (i >= n) { keys[i] = ~0ull; return; }
+    const float* P = (which ? a.tgt : a.src) + (long long)pair * a.cloud_stride + (long long)i * 3;
+    const float* b = a.bounds + ((long long)pair * 2 + which) * 6;
+    unsigned code = 0;
+    for (int c = 0; c < 3; ++c) {
+        const float ext = b[3 + c] - b[c];
+        float u = ext > 0.0f ? (P[c] - b[c]) / ext : 0.0f;
+        u = fminf(fmaxf(u * 1024.0f, 0.0f), 1023.0f);
+        unsigned q = (u == u) ? (unsigned)u : 0u;     // NaN coordinates sort first
+        code |= ndp_expand10(q) << c;
+    }
+    keys[i] = ((unsigned long long)code << 32) | (unsigned)i;
+}
+
+__global__ void __launch_bounds__(256) ndp_bitonic_step_kernel(unsigned long long* keys, int npad, int k, int j) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= npad) return;
+    unsigned long long* K = keys + (long long)blockIdx.y * npad;
+    const int l = i ^ j;
+    if (l > i) {
+        const unsigned long long x = K[i], y = K[l];
+        const bool up = (i & k) == 0;
+        if ((x > y) == up) { K[i] = y; K[l] = x; }
+    }
+}
+
+// sorted [n][3] copy (+ float4 copy carrying the original sample index) and the 32-point block boxes
+__global__ void __launch_bounds__(256) ndp_apply_order_kernel(NdpSortArgs a) {
+    const int pair = blockIdx.y, which = blockIdx.z;
+    const int n = which ? (a.mcounts ? a.mcounts[pair] : a.m) : (a.ncounts ? a.ncounts[pair] : a.n);
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int npts = which ? a.m : a.n;
+    if (i >= ((npts + 31) / 32) * 32) return;                 // whole warps stay together for the shuffles
+    const unsigned long long* keys = a.keys + ((long long)pair * 2 + which) * a.npad;
+    const float* P = (which ? a.tgt : a.src) + (long long)pair * a.cloud_stride;
+    float* out = (which ? a.tgt_sorted : a.src_sorted) + (long long)pair * a.cloud_stride;
+    const float INF = __int_as_float(0x7f800000);
+    float x = INF, y = INF, z = INF;
+    int o = 0x7fffffff;
+    if (i < n) {
+        o = (int)(unsigned)(keys[i] & 0xffffffffull);
+        x = P[(long long)o * 3]; y = P[(long long)o * 3 + 1]; z = P[(long long)o * 3 + 2];
+        out[(long long)i * 3] = x; out[(long long)i * 3 + 1] = y; out[(long long)i * 3 + 2] = z;
+        (which ? a.tgt_orig : a.src_orig)[(long long)pair * a.orig_stride + i] = o;
+    }
+    if (which) a.tgt4[(long long)pair * a.p4_stride + i] = make_float4(x, y, z, __int_as_float(o));
+    // block box of the (static) target; padded slots (+inf) are excluded
+    float l0 = x, l1 = y, l2 = z, h0 = (i < n) ? x : -INF, h1 = (i < n) ? y : -INF, h2 = (i < n) ? z : -INF;
+    for (int s = 16; s > 0; s >>= 1) {
+        l0 = fminf(l0, __shfl_xor_sync(0xffffffffu, l0, s)); l1 = fminf(l1, __shfl_xor_sync(0xffffffffu, l1, s));
+        l2 = fminf(l2, __shfl_xor_sync(0xffffffffu, l2, s)); h0 = fmaxf(h0, __shfl_xor_sync(0xffffffffu, h0, s));
+        h1 = fmaxf(h1, __shfl_xor_sync(0xffffffffu, h1, s)); h2 = fmaxf(h2, __shfl_xor_sync(0xffffffffu, h2, s));
+    }
+    if (which && lane == 0) {
+        float* bx = a.tgt_box + ((long long)pair * a.box_stride + (i >> 5)) * 8;
+        bx[0] = l0; bx[1] = l1; bx[2] = l2; bx[3] = 0.0f; bx[4] = h0; bx[5] = h1; bx[6] = h2; bx[7] = 0.0f;
+    }
+}
+
+int ndp_launch_sort(const NdpSortArgs& a, cudaStream_t s) {
+    if (a.npairs <= 0) return 0;
+    NDP_LAUNCH(ndp_bounds_kernel, dim3(a.npairs, 2), dim3(256), 0, s, a);
+    NDP_LAUNCH(ndp_morton_keys_kernel, dim3((a.npad + 255) / 256, a.npairs, 2), dim3(256), 0, s, a);
+    int launches = 2;
+    for (int k = 2; k <= a.npad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            NDP_LAUNCH(ndp_bitonic_step_kernel, dim3((a.npad + 255) / 256, a.npairs * 2), dim3(256), 0, s, a.keys, a.npad, k, j);
+            ++launches;
+        }
+    const int nmax = a.n > a.m ? a.n : a.m;
+    NDP_LAUNCH(ndp_apply_order_kernel, dim3((((nmax + 31) / 32) * 32 + 255) / 256, a.npairs, 2), dim3(256), 0, s, a);
+    return launches + 1;
+}
+
+// ---- the culled search ---------------------------------------------------------------------------
+#define NDP_PN_WARPS 4
+__global__ void __launch_bounds__(NDP_PN_WARPS * 32) ndp_nn_pruned_kernel(NdpPrunedArgs a) {
+    __shared__ __align__(16) float4 stage[NDP_PN_WARPS][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int dir = blockIdx.z & 1, pair = blockIdx.z >> 1;
+    if (a.state && a.state[pair].stopped) return;
+    const int n = a.ncounts ? a.ncounts[pair] : a.n;
+    const int m = a.mcounts ? a.mcounts[pair] : a.m;
+    const int nq = dir ? m : n, nt = dir ? n : m;
+    const int qblk = blockIdx.x * NDP_PN_WARPS + w;            // one 32-query block per warp
+    if (qblk * 32 >= nq) return;                               // warp-uniform
+    const float4* Q4 = (dir ? a.y4 : a.x4) + (long long)pair * a.p4_stride;
+    const float4* T4 = (dir ? a.x4 : a.y4) + (long long)pair * a.p4_stride;
+    const float* qbox = (dir ? a.ybox : a.xbox) + ((long long)pair * a.box_stride + qblk) * 8;
+    const float* tbox = (dir ? a.xbox : a.ybox) + (long long)pair * a.box_stride * 8;
+    int* prev = (dir ? a.prev_y : a.prev_x) + (long long)pair * a.prev_stride;
+    const int ntblk = (nt + 31) >> 5;
+    const float INF = __int_as_float(0x7f800000);
+
+    const int q = qblk * 32 + lane;
+    const bool live = q < nq;
+    const float4 qq = Q4[live ? q : (nq - 1)];
+    // seed: nearest neighbour of the previous iteration (or a position-based guess)
+    int js = live ? prev[q] : 0;
+    if (js < 0 || js >= nt) js = (int)(((long long)q * nt) / nq);
+    if (js >= nt) js = nt - 1;
+    const float4 ts = T4[js];
+    float best = ndp_sqdist3(qq.x, qq.y, qq.z, ts.x, ts.y, ts.z);
+    int bo = __float_as_int(ts.w), bj = js;
+    if (!(best == best)) best = INF;                           // NaN seed: fall back to a full scan
+    float wmax = live ? best : 0.0f;                           // dead lanes never widen the search
+    for (int s = 16; s > 0; s >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, s));
+    const float4 qlo = *(const float4*)qbox, qhi = *(const float4*)(qbox + 4);
+
+    for (int base = 0; base < ntblk; base += 32) {
+        const int blk = base + lane;
+        bool need = false;
+        if (blk < ntblk) {
+            const float4 blo = *(const float4*)(tbox + (long long)blk * 8), bhi = *(const float4*)(tbox + (long long)blk * 8 + 4);
+            const float lbw = ndp_sq3(ndp_gap(qlo.x, qhi.x, blo.x, bhi.x), ndp_gap(qlo.y, qhi.y, blo.y, bhi.y),
+                                      ndp_gap(qlo.z, qhi.z, blo.z, bhi.z));
+            need = lbw <= wmax;
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, need);
+        while (mask) {
+            const int b = __ffs((int)mask) - 1;
+            mask &= mask - 1;
+            const int tb = base + b;
+            const float4 blo = *(const float4*)(tbox + (long long)tb * 8), bhi = *(const float4*)(tbox + (long long)tb * 8 + 4);
+            const float lbq = ndp_sq3(ndp_gap(qq.x, qq.x, blo.x, bhi.x), ndp_gap(qq.y, qq.y, blo.y, bhi.y),
+                                      ndp_gap(qq.z, qq.z, blo.z, bhi.z));
+            if (!__any_sync(0xffffffffu, live && lbq <= best)) continue;
+            const int tj = tb * 32 + lane;
+            stage[w][lane] = (tj < nt) ? T4[tj] : make_float4(INF, INF, INF, __int_as_float(0x7fffffff));
+            __syncwarp();
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) {
+                const float4 t = stage[w][j];
+                const float d = ndp_sqdist3(qq.x, qq.y, qq.z, t.x, t.y, t.z);
+                const int o = __float_as_int(t.w);
+                if (d < best || (d == best && o < bo)) { best = d; bo = o; bj = tb * 32 + j; }
+            }
+            __syncwarp();
+        }
+    }
+    if (live) {
+        // NaN query: reference semantics are (NaN, index 0)
+        if (!(qq.x == qq.x) || !(qq.y == qq.y) || !(qq.z == qq.z)) best = __int_as_float(0x7fc00000);
+        a.part[(long long)pair * a.part_pair_stride + (long long)dir * a.qpitch + q] = make_float2(best, __int_as_float(bj));
+        prev[q] = bj;
+    }
+}
+
+void ndp_launch_nn_pruned(const NdpPrunedArgs& a, cudaStream_t s) {
+    if (a.npairs <= 0) return;
+    const int nmax = a.n > a.m ? a.n : a.m;
+    if (nmax <= 0) return;
+    dim3 grid(((nmax + 31) / 32 + NDP_PN_WARPS - 1) / NDP_PN_WARPS, 1, 2 * a.npairs);
+    NDP_LAUNCH(ndp_nn_pruned_kernel, grid, dim3(NDP_PN_WARPS * 32), 0, s, a);
+}

@@ -155,8 +155,10 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_fwd_kernel(NdpFwdArgs
     // ---- per-point rotation + warp composition (nets.py:119-137)
     if (tid < NDP_TP) {
         const int gp = tile * NDP_TP + tid;
+        const float INF = __int_as_float(0x7f800000);
+        float y[3] = {INF, INF, INF};
         if (gp < n) {
-            float z[NDP_MAX_HEAD], y[3], nu = 0.0f;
+            float z[NDP_MAX_HEAD], nu = 0.0f;
 #pragma unroll
             for (int r = 0; r < NDP_MAX_HEAD; ++r) z[r] = (r < HD) ? zs[tid * NDP_ZPITCH + r] : 0.0f;
             ndp_point_forward(L.motion, L.rot, L.nonrigid, z, xs + tid * 4, y, &nu);
@@ -171,6 +173,23 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_fwd_kernel(NdpFwdArgs
                 float* zp = a.zsave + (long long)pair * a.z_stride + (long long)gp * NDP_ZPITCH;
 #pragma unroll
                 for (int r = 0; r < NDP_ZPITCH; ++r) zp[r] = z[r];
+            }
+        }
+        if (a.y4) {
+            // float4 copy (x, y, z, original sample index) and the box of this warp's 32 outputs for
+            // the culled NN search; slots past the cloud hold +inf and are excluded from the box
+            const int o = (gp < n) ? a.orig[(long long)pair * a.orig_stride + gp] : 0x7fffffff;
+            a.y4[(long long)pair * a.y4_stride + gp] = make_float4(y[0], y[1], y[2], __int_as_float(o));
+            float l0 = y[0], l1 = y[1], l2 = y[2];
+            float h0 = (gp < n) ? y[0] : -INF, h1 = (gp < n) ? y[1] : -INF, h2 = (gp < n) ? y[2] : -INF;
+            for (int s = 16; s > 0; s >>= 1) {
+                l0 = fminf(l0, __shfl_xor_sync(0xffffffffu, l0, s)); l1 = fminf(l1, __shfl_xor_sync(0xffffffffu, l1, s));
+                l2 = fminf(l2, __shfl_xor_sync(0xffffffffu, l2, s)); h0 = fmaxf(h0, __shfl_xor_sync(0xffffffffu, h0, s));
+                h1 = fmaxf(h1, __shfl_xor_sync(0xffffffffu, h1, s)); h2 = fmaxf(h2, __shfl_xor_sync(0xffffffffu, h2, s));
+            }
+            if ((tid & 31) == 0 && gp < n) {
+                float* bx = a.ybox + ((long long)pair * a.box_stride + (gp >> 5)) * 8;
+                bx[0] = l0; bx[1] = l1; bx[2] = l2; bx[3] = 0.0f; bx[4] = h0; bx[5] = h1; bx[6] = h2; bx[7] = 0.0f;
             }
         }
     }

@@ -85,7 +85,8 @@ class Registration():
                                       samples=c.samples, levels=c.m, k0=c.k0, depth=c.depth, width=c.width,
                                       motion=c.motion_type, rotation_format=c.rotation_format, iters=c.iters,
                                       max_break_count=c.max_break_count,
-                                      break_threshold_ratio=c.break_threshold_ratio, lr=c.lr, trunc=1e9)
+                                      break_threshold_ratio=c.break_threshold_ratio, lr=c.lr, trunc=1e9,
+                                      nn_mode=int(_cfg_get(c, "nn_mode", 0) or 0))
             self._solver_key = key
         return self._solver
 

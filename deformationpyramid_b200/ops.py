@@ -164,7 +164,7 @@ class Solver:
     def __init__(self, *, max_pairs: int, max_src_points: int, max_tgt_points: int, samples: int, levels: int,
                  k0: int, depth: int, width: int, motion: str, rotation_format: str, iters: int,
                  max_break_count: int, break_threshold_ratio: float, lr: float, trunc: float = 1e9,
-                 record_loss: bool = False, profile_every: int = 0, lib=None):
+                 record_loss: bool = False, profile_every: int = 0, nn_mode: int = 0, lib=None):
         self.lib = _get(lib)
         if motion not in MOTION:
             raise AssertionError(f"motion must be one of {list(MOTION)}")
@@ -172,7 +172,7 @@ class Solver:
                              int(k0), int(depth), int(width), MOTION[motion],
                              ROT_FORMAT.get(rotation_format, 0), int(iters),
                              int(min(max_break_count, 2 ** 31 - 1)), float(break_threshold_ratio), float(lr),
-                             float(trunc), int(bool(record_loss)), int(profile_every))
+                             float(trunc), int(bool(record_loss)), int(profile_every), int(nn_mode))
         h = ctypes.c_void_p(0)
         _lib.check(self.lib, self.lib.ndp_solver_create(ctypes.byref(self.cfg), ctypes.byref(h)), "ndp_solver_create")
         self.handle = h

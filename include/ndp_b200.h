@@ -110,6 +110,8 @@ typedef struct ndp_solver_cfg {
     int32_t record_loss;        /* 1: keep the per-iteration loss curve (see ndp_solver_losses)   */
     int32_t profile_every;      /* k > 0: bracket the kernels of every k-th iteration with CUDA
                                    events on `stream` (see ndp_solver_profile); 0: off            */
+    int32_t nn_mode;            /* 0: exact culled search (Morton blocks + boxes + temporal seeds),
+                                   1: plain brute force; identical results                        */
 } ndp_solver_cfg;
 
 typedef struct ndp_solver ndp_solver;

@@ -146,7 +146,7 @@ def check_trajectory_teacher_forced(lib, golden_dir, device):
 
 
 def check_solver_against_oracle(lib, device, host, npairs, n, m, samples, levels, iters, early_stop,
-                                ratio=0.001, max_break=15, motion="SE3", rot="axis_angle", free_tol=2e-4):
+                                ratio=0.001, max_break=15, motion="SE3", rot="axis_angle", free_tol=2e-4, nn_mode=0):
     """Fused driver vs oracle.optimize_pair (= registration.py:126-262) on identical pairs, weights
     and permutations.  Short free-running horizon (hard part 3)."""
     cfgo = O.NDPConfig(iters=iters, lr=0.01, max_break_count=max_break if early_stop else 10 ** 9,
@@ -166,7 +166,7 @@ def check_solver_against_oracle(lib, device, host, npairs, n, m, samples, levels
     solver = ops.Solver(max_pairs=npairs, max_src_points=n, max_tgt_points=m + 5 * npairs, samples=samples,
                         levels=levels, k0=-8, depth=3, width=128, motion=motion, rotation_format=rot, iters=iters,
                         max_break_count=cfgo.max_break_count, break_threshold_ratio=ratio, lr=0.01, trunc=1e9,
-                        record_loss=True, lib=lib)
+                        record_loss=True, nn_mode=nn_mode, lib=lib)
     params = [torch.cat([O.flatten_params(s, P) for s, P in zip(specs, init)]).contiguous() for init in inits]
     d = "cpu" if host else device
     mv = lambda ts: [t.to(d).contiguous() for t in ts]
@@ -183,3 +183,54 @@ def check_solver_against_oracle(lib, device, host, npairs, n, m, samples, levels
         assert rel(warped[p].cpu().numpy(), ref.warped.numpy()) < 5 * free_tol, p
     assert solver.launch_count > 0
     solver.close()
+
+
+def check_culled_search_equals_brute_force(lib, device, n=700, m=650, samples=600, levels=2, iters=5):
+    """The culled NN search (Morton blocks + boxes + temporal seeds) finds exactly the neighbours of
+    the brute-force search: per-iteration losses agree to summation-order rounding (1e-6), far below
+    what a single wrong neighbour would change."""
+    specs = O.make_specs(3, 128, -8, levels, "axis_angle")
+    curves = []
+    for mode in (0, 1):
+        pairs, params = [], []
+        for p in range(2):
+            src, tgt = make_pair(70 + p, n - 11 * p, m)
+            # duplicate some targets -> exact ties must resolve identically
+            tgt = torch.cat([tgt, tgt[:40]])
+            torch.manual_seed(p)
+            params.append(torch.cat([O.flatten_params(s, O.init_params(s)) for s in specs]).to(device))
+            pairs.append((src.to(device), tgt.to(device)))
+        solver = ops.Solver(max_pairs=2, max_src_points=n, max_tgt_points=m + 40, samples=samples, levels=levels,
+                            k0=-8, depth=3, width=128, motion="SE3", rotation_format="axis_angle", iters=iters,
+                            max_break_count=10 ** 9, break_threshold_ratio=0.001, lr=0.01, record_loss=True,
+                            nn_mode=mode, lib=lib)
+        warped, its, last = solver.register([a for a, _ in pairs], [b for _, b in pairs], params)
+        curves.append((torch.stack([solver.losses(p) for p in range(2)]), [w.cpu() for w in warped]))
+        solver.close()
+    (c0, w0), (c1, w1) = curves
+    assert torch.allclose(c0, c1, rtol=2e-6, atol=0), (c0, c1)
+    for a, b in zip(w0, w1):      # different summation order (sorted vs unsorted) + chaotic trajectory
+        assert rel(a.numpy(), b.numpy()) < 1e-3
+
+
+def check_solver_repeatable(lib, device, n=260, m=240, samples=200, levels=3, iters=10):
+    """Two consecutive register() calls on ONE solver give bit-identical results even when pairs stop
+    early (no state leaks between levels or calls), and equal a fresh solver's result."""
+    specs = O.make_specs(3, 128, -8, levels, "axis_angle")
+    src, tgt = make_pair(90, n, m)
+    torch.manual_seed(1)
+    flat0 = torch.cat([O.flatten_params(s, O.init_params(s)) for s in specs]).to(device)
+    kw = dict(max_pairs=1, max_src_points=n, max_tgt_points=m, samples=samples, levels=levels, k0=-8, depth=3,
+              width=128, motion="SE3", rotation_format="axis_angle", iters=iters, max_break_count=2,
+              break_threshold_ratio=0.02, lr=0.01, lib=lib)
+    outs = []
+    s1 = ops.Solver(**kw)
+    for _ in range(2):
+        w, its, last = s1.register([src.to(device)], [tgt.to(device)], [flat0.clone()])
+        outs.append((w[0].cpu(), its.clone(), last.clone()))
+    s2 = ops.Solver(**kw)
+    w, its, last = s2.register([src.to(device)], [tgt.to(device)], [flat0.clone()])
+    outs.append((w[0].cpu(), its.clone(), last.clone()))
+    assert int(outs[0][1].min()) < iters, "the case must exercise early stop"
+    for o in outs[1:]:
+        assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2])

@@ -16,7 +16,8 @@ from emu_util import emu_lib
 
 from parity_cases import (check_layers_against_golden, check_chamfer_against_golden, check_adam,
                           check_trajectory_teacher_forced, check_solver_against_oracle,
-                          check_chamfer_vs_oracle_random)
+                          check_chamfer_vs_oracle_random, check_culled_search_equals_brute_force,
+                          check_solver_repeatable)
 
 
 @pytest.fixture(scope="module")
@@ -53,3 +54,16 @@ def test_solver_early_stop_and_ragged(lib):
     # samples > cloud size for pair 1 -> ragged counts; aggressive early stop -> ragged termination
     check_solver_against_oracle(lib, device="cpu", host=True, npairs=2, n=150, m=140, samples=160, levels=2,
                                 iters=12, early_stop=True, ratio=0.05, max_break=2)
+
+
+def test_solver_brute_force_mode(lib):
+    check_solver_against_oracle(lib, device="cpu", host=True, npairs=1, n=300, m=260, samples=200, levels=2,
+                                iters=4, early_stop=False, nn_mode=1)
+
+
+def test_culled_search_equals_brute_force(lib):
+    check_culled_search_equals_brute_force(lib, "cpu", n=330, m=300, samples=280, levels=2, iters=4)
+
+
+def test_solver_repeatable_with_early_stop(lib):
+    check_solver_repeatable(lib, "cpu")

@@ -10,7 +10,8 @@ from deformationpyramid_b200.synthetic import make_pair
 from oracle import ndp_oracle as O
 from parity_cases import (REL_TOL, rel, check_layers_against_golden, check_chamfer_against_golden, check_adam,
                           check_trajectory_teacher_forced, check_solver_against_oracle,
-                          check_chamfer_vs_oracle_random)
+                          check_chamfer_vs_oracle_random, check_culled_search_equals_brute_force,
+                          check_solver_repeatable)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -69,12 +70,12 @@ def test_chamfer_full_size_properties(lib):
     # gradient is a finite-difference direction of the loss
     g = torch.Generator().manual_seed(1)
     v = torch.randn(8192, 3, generator=g).to(DEV)
-    eps = 1e-3
+    eps = 2e-4          # the loss is only piecewise smooth (NN switches): a coarse sanity bound
     lp, _ = ops.chamfer((x + eps * v).contiguous(), y, 1e9, lib=lib)
     lm, _ = ops.chamfer((x - eps * v).contiguous(), y, 1e9, lib=lib)
     fd = (float(lp) - float(lm)) / (2 * eps)
     an = float((gx * v).sum())
-    assert abs(fd - an) <= 2e-2 * max(abs(an), 1e-3)
+    assert abs(fd - an) <= 0.1 * max(abs(an), 1e-3)
 
 
 def test_adam(lib):
@@ -110,8 +111,8 @@ def test_solver_sim3_euler(lib):
 def test_solver_batch_invariance(lib):
     """A pair's result does not depend on what it is batched with (deterministic kernels)."""
     cfg = dict(max_src_points=1024, max_tgt_points=1024, samples=512, levels=2, k0=-8, depth=3, width=128,
-               motion="SE3", rotation_format="axis_angle", iters=20, max_break_count=15,
-               break_threshold_ratio=0.001, lr=0.01, lib=lib)
+               motion="SE3", rotation_format="axis_angle", iters=20, max_break_count=3,
+               break_threshold_ratio=0.01, lr=0.01, lib=lib)
     specs = O.make_specs(3, 128, -8, 2, "axis_angle")
     def mk(p):
         src, tgt = make_pair(p, 900, 800)
@@ -126,3 +127,17 @@ def test_solver_batch_invariance(lib):
     w_batch, it2, _ = s2.register([b[0], a[0]], [b[1], a[1]], [b[2].clone(), a[2].clone()])
     assert torch.equal(w_single[0], w_again[0])                 # run-to-run bit reproducible
     assert torch.equal(w_single[0], w_batch[1]) and torch.equal(it1[0], it2[1])
+
+
+def test_solver_brute_force_mode(lib):
+    check_solver_against_oracle(lib, DEV, host=False, npairs=2, n=700, m=650, samples=512, levels=2, iters=6,
+                                early_stop=False, nn_mode=1)
+
+
+def test_culled_search_equals_brute_force(lib):
+    check_culled_search_equals_brute_force(lib, DEV)
+    check_culled_search_equals_brute_force(lib, DEV, n=4200, m=4100, samples=4096, levels=2, iters=12)
+
+
+def test_solver_repeatable_with_early_stop(lib):
+    check_solver_repeatable(lib, DEV)
