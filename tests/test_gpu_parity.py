@@ -67,15 +67,15 @@ def test_chamfer_full_size_properties(lib):
     sel = torch.randperm(8192, generator=torch.Generator().manual_seed(0))[:512]
     od, oi = O.knn1(src[sel], tgt, threads=O.max_threads())
     assert torch.equal(oi, ix.cpu()[sel]) and torch.equal(od, d2x.cpu()[sel])
-    # gradient is a finite-difference direction of the loss
-    g = torch.Generator().manual_seed(1)
-    v = torch.randn(8192, 3, generator=g).to(DEV)
-    eps = 2e-4          # the loss is only piecewise smooth (NN switches): a coarse sanity bound
+    # directional derivative along a rigid translation of x (a smooth direction: with an independent
+    # random direction per point the NN assignments flip inside the finite-difference interval)
+    v = torch.tensor([1.0, 0.5, -0.3], device=DEV).expand(8192, 3).contiguous()
+    eps = 1e-3
     lp, _ = ops.chamfer((x + eps * v).contiguous(), y, 1e9, lib=lib)
     lm, _ = ops.chamfer((x - eps * v).contiguous(), y, 1e9, lib=lib)
     fd = (float(lp) - float(lm)) / (2 * eps)
     an = float((gx * v).sum())
-    assert abs(fd - an) <= 0.1 * max(abs(an), 1e-3)
+    assert abs(fd - an) <= 2e-2 * max(abs(an), 1e-2), (fd, an)
 
 
 def test_adam(lib):
