@@ -57,7 +57,7 @@ def workload(a):
                         + ("early stop disabled (fixed-iter mode A)" if a.mode == "fixed"
                            else "shipped early-stop thresholds (mode B)"),
             "points": a.points, "levels": a.levels, "iters_per_level": a.iters, "mode": a.mode,
-            "pairs_per_step_per_gpu": a.pairs, "nn_search": "exact culled (Morton blocks + boxes + seeds)" if a.nn_mode == 0 else "brute force", "width": 128, "depth": 3, "motion": "SE3", "rotation": "axis_angle",
+            "pairs_per_step_per_gpu": a.pairs, "mlp": "tcgen05 bf16x3 (fp32-accurate)" if os.environ.get("NDP_MLP_MODE", "0") == "0" else "fp32 pipes", "nn_search": "exact culled (Morton blocks + boxes + seeds)" if a.nn_mode == 0 else "brute force", "width": 128, "depth": 3, "motion": "SE3", "rotation": "axis_angle",
             "l2": "flushed (256 MiB write) between timed steps; one step streams ~100 MiB of saved activations "
                   "and gradient partials per iteration"}
 
@@ -181,6 +181,8 @@ def main():
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    mlp_mode = int(os.environ.get("NDP_MLP_MODE", "0"))      # 0: tcgen05 tensor cores (default), 1: FP32 pipes
+    ops.set_mlp_mode(mlp_mode)
     dist = None
     if world > 1:
         import torch.distributed as dist

@@ -18,7 +18,7 @@ ROT_FORMAT = {"axis_angle": 0, "euler": 1, "quaternion": 2, "6D": 3}
 
 EXPORTS = [
     "ndp_last_error", "ndp_version", "ndp_param_count", "ndp_pack_count",
-    "ndp_saved_floats_per_point", "ndp_backward_workspace_bytes", "ndp_chamfer_workspace_bytes",
+    "ndp_saved_floats", "ndp_set_mlp_mode", "ndp_get_mlp_mode", "ndp_backward_workspace_bytes", "ndp_chamfer_workspace_bytes",
     "ndp_pack_params", "ndp_layer_forward", "ndp_layer_backward", "ndp_chamfer", "ndp_adam_step",
     "ndp_solver_create", "ndp_solver_destroy", "ndp_solver_params_per_pair",
     "ndp_solver_register_host", "ndp_solver_register_device", "ndp_solver_losses",
@@ -44,9 +44,14 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.ndp_last_error.restype = c_char_p
     lib.ndp_last_error.argtypes = []
     lib.ndp_version.restype = c_int32
-    for name in ("ndp_param_count", "ndp_pack_count", "ndp_saved_floats_per_point"):
+    for name in ("ndp_param_count", "ndp_pack_count"):
         getattr(lib, name).restype = c_int64
         getattr(lib, name).argtypes = [P(LayerCfg)]
+    lib.ndp_saved_floats.restype = c_int64
+    lib.ndp_saved_floats.argtypes = [P(LayerCfg), c_int64]
+    lib.ndp_set_mlp_mode.argtypes = [c_int32]
+    lib.ndp_set_mlp_mode.restype = ctypes.c_int
+    lib.ndp_get_mlp_mode.restype = c_int32
     lib.ndp_backward_workspace_bytes.restype = c_int64
     lib.ndp_backward_workspace_bytes.argtypes = [P(LayerCfg), c_int64]
     lib.ndp_chamfer_workspace_bytes.restype = c_int64
@@ -54,7 +59,7 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.ndp_pack_params.argtypes = [P(LayerCfg), c_void_p, c_void_p, c_void_p]
     lib.ndp_layer_forward.argtypes = [P(LayerCfg), c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                       c_void_p, c_void_p, c_void_p]
-    lib.ndp_layer_backward.argtypes = [P(LayerCfg), c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+    lib.ndp_layer_backward.argtypes = [P(LayerCfg), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.ndp_chamfer.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_float, c_float, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]

@@ -8,6 +8,7 @@
 // A fresh optimiser per level (registration.py:176) => t restarts at 1 and m = v = 0.
 // Also: small helper kernels of the per-pair driver (means, gather+centre, state reset, pack).
 #include "ndp_kernels.h"
+#include "ndp_tc.cuh"
 
 __device__ __forceinline__ void ndp_pack_store(const NdpLayout& L, float* pack, int idx, float val) {
     // canonical index -> transposed copy (W_in[o][c] -> WT_in[c][o]; W_l[o][i] -> WT_l[i][o])
@@ -21,6 +22,13 @@ __device__ __forceinline__ void ndp_pack_store(const NdpLayout& L, float* pack, 
         if (rel >= 0 && rel < NDP_W * NDP_W) {
             const int o = rel >> 7, i = rel & 127;
             pack[L.pack_w[l] + i * NDP_W + o] = val;
+            // bf16 tri-image of W_l (row o, column i) for the tensor-core kernels
+            unsigned h1, h2, h3;
+            ndp_split3(val, h1, h2, h3);
+            unsigned char* img = (unsigned char*)(pack + L.pack_img) + (long long)l * NDP_TRI128 + ndp_img_off(o, i, NDP_IMG_RS(128));
+            *(unsigned short*)img = (unsigned short)h1;
+            *(unsigned short*)(img + NDP_IMG128) = (unsigned short)h2;
+            *(unsigned short*)(img + 2 * NDP_IMG128) = (unsigned short)h3;
             return;
         }
     }
@@ -68,9 +76,21 @@ __global__ void __launch_bounds__(256) ndp_pack_kernel(NdpPackArgs a) {
     const int pair = blockIdx.y;
     const int idx = blockIdx.x * 256 + threadIdx.x;
     const NdpLayout& L = a.lay;
-    if (idx >= L.pack_count) return;
+    if (idx >= L.pack_img + L.hidden * NDP_W * NDP_W) return;
     const float* params = a.params + (long long)pair * a.params_stride;
     float* pack = a.pack + (long long)pair * a.pack_stride;
+    if (idx >= L.pack_img) {        // one thread per hidden weight: its three bf16 image entries
+        const int rel = idx - L.pack_img;
+        const int l = rel / (NDP_W * NDP_W), r2 = rel - l * NDP_W * NDP_W;
+        const int o = r2 >> 7, i = r2 & 127;
+        unsigned h1, h2, h3;
+        ndp_split3(params[L.off_w[l] + o * NDP_W + i], h1, h2, h3);
+        unsigned char* img = (unsigned char*)(pack + L.pack_img) + (long long)l * NDP_TRI128 + ndp_img_off(o, i, NDP_IMG_RS(128));
+        *(unsigned short*)img = (unsigned short)h1;
+        *(unsigned short*)(img + NDP_IMG128) = (unsigned short)h2;
+        *(unsigned short*)(img + 2 * NDP_IMG128) = (unsigned short)h3;
+        return;
+    }
     float v;
     if (idx < 6 * NDP_W) {
         const int c = idx >> 7, o = idx & 127;
@@ -86,7 +106,7 @@ __global__ void __launch_bounds__(256) ndp_pack_kernel(NdpPackArgs a) {
 
 void ndp_launch_pack(const NdpPackArgs& a, cudaStream_t s) {
     if (a.npairs <= 0) return;
-    dim3 grid((a.lay.pack_count + 255) / 256, a.npairs);
+    dim3 grid((a.lay.pack_img + a.lay.hidden * NDP_W * NDP_W + 255) / 256, a.npairs);
     NDP_LAUNCH(ndp_pack_kernel, grid, dim3(256), 0, s, a);
 }
 

@@ -2,6 +2,7 @@
 // host-side orchestration of the kernels.  No torch types, no CPU fallback.
 #include "../../include/ndp_b200.h"
 #include "ndp_kernels.h"
+#include "ndp_tc.cuh"
 
 #include <mutex>
 #include <string>
@@ -19,12 +20,24 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 extern "C" const char* ndp_last_error(void) { return g_err.c_str(); }
 extern "C" int32_t ndp_version(void) { return 100; }
 
+// 0: hidden layers on the tensor cores (tcgen05, bf16x3 split, fp32 accumulate) -- default;
+// 1: everything on the FP32 pipes.  Process-wide; solvers capture it at creation.
+static int g_mlp_mode = 0;
+extern "C" int ndp_set_mlp_mode(int32_t mode) {
+    if (mode != 0 && mode != 1) return fail(NDP_E_INVALID, "mlp mode must be 0 (tensor cores) or 1 (fp32 pipes)");
+    g_mlp_mode = mode;
+    return NDP_OK;
+}
+extern "C" int32_t ndp_get_mlp_mode(void) { return g_mlp_mode; }
+
 static int init_once() {
     static std::once_flag once;
     static int rc = 0;
     std::call_once(once, [] {
         int e = ndp_fwd_init();
         if (e == 0) e = ndp_bwd_init();
+        if (e == 0) e = ndp_fwd_tc_init();
+        if (e == 0) e = ndp_bwd_tc_init();
         rc = e;
     });
     if (rc != 0) return fail(NDP_E_CUDA, std::string("kernel init: ") + cudaGetErrorString((cudaError_t)rc));
@@ -48,8 +61,13 @@ static long long pad256(long long v) { return (v + 255) / 256 * 256; }
 
 extern "C" int64_t ndp_param_count(const ndp_layer_cfg* c) { return check_cfg(c) ? -1 : layout_of(c).param_count; }
 extern "C" int64_t ndp_pack_count(const ndp_layer_cfg* c) { return check_cfg(c) ? -1 : layout_of(c).pack_count; }
-extern "C" int64_t ndp_saved_floats_per_point(const ndp_layer_cfg* c) {
-    return check_cfg(c) ? -1 : (int64_t)c->depth * NDP_W + NDP_ZPITCH;
+static long long act_floats(int depth, long long n, int mode) {   // saved activations of one pair
+    const long long tiles = (n + NDP_TP - 1) / NDP_TP;
+    return mode == 0 ? tiles * depth * (long long)(NDP_TRI128 / 4) : (long long)depth * n * NDP_W;
+}
+extern "C" int64_t ndp_saved_floats(const ndp_layer_cfg* c, int64_t n) {
+    if (check_cfg(c) || n < 0) return -1;
+    return act_floats(c->depth, n, g_mlp_mode) + n * NDP_ZPITCH;
 }
 extern "C" int64_t ndp_backward_workspace_bytes(const ndp_layer_cfg* c, int64_t n) {
     if (check_cfg(c)) return -1;
@@ -112,33 +130,33 @@ extern "C" int ndp_layer_forward(const ndp_layer_cfg* c, const float* params, co
     a.params = params; a.params_stride = 0; a.pack = pack; a.pack_stride = 0;
     a.x = x; a.x_stride = 0; a.y = y; a.y_stride = 0; a.nu = nu; a.nu_stride = 0;
     a.act = saved; a.act_stride = 0; a.act_layer_stride = n * NDP_W;
-    a.zsave = saved ? saved + (long long)c->depth * n * NDP_W : nullptr; a.z_stride = 0;
+    a.zsave = saved ? saved + act_floats(c->depth, n, g_mlp_mode) : nullptr; a.z_stride = 0;
     a.y_add = nullptr; a.y_add_stride = 0; a.y4 = nullptr; a.y4_stride = 0; a.orig = nullptr; a.orig_stride = 0;
     a.ybox = nullptr; a.box_stride = 0; a.n = (int)n; a.counts = nullptr; a.state = nullptr; a.npairs = 1;
-    ndp_launch_fwd(a, (cudaStream_t)stream);
+    if (g_mlp_mode == 0) ndp_launch_fwd_tc(a, (cudaStream_t)stream); else ndp_launch_fwd(a, (cudaStream_t)stream);
     CK(cudaGetLastError());
     return NDP_OK;
 }
 
-extern "C" int ndp_layer_backward(const ndp_layer_cfg* c, const float* params, const float* x, int64_t n,
+extern "C" int ndp_layer_backward(const ndp_layer_cfg* c, const float* params, const float* pack, const float* x, int64_t n,
                                   const float* saved, const float* grad_y, const float* grad_nu,
                                   float* grad_params, float* grad_x, void* workspace, void* stream) {
     if (int e = check_cfg(c)) return e;
     if (int e = init_once()) return e;
     if (n <= 0 || n > 0x7fffffff / 4) return fail(NDP_E_INVALID, "bad point count");
-    if (!params || !x || !saved || !grad_y || !grad_params || !workspace) return fail(NDP_E_INVALID, "NULL buffer");
-    if (!aligned16(params) || !aligned16(saved) || !aligned16(workspace))
+    if (!params || !pack || !x || !saved || !grad_y || !grad_params || !workspace) return fail(NDP_E_INVALID, "NULL buffer");
+    if (!aligned16(params) || !aligned16(pack) || !aligned16(saved) || !aligned16(workspace))
         return fail(NDP_E_INVALID, "params, saved and workspace must be 16-byte aligned");
     NdpLayout L = layout_of(c);
     NdpBwdArgs b;
-    b.lay = L; b.params = params; b.params_stride = 0; b.x = x; b.x_stride = 0;
+    b.lay = L; b.params = params; b.params_stride = 0; b.pack = pack; b.pack_stride = 0; b.x = x; b.x_stride = 0;
     b.act = saved; b.act_stride = 0; b.act_layer_stride = n * NDP_W;
-    b.zsave = saved + (long long)c->depth * n * NDP_W; b.z_stride = 0;
+    b.zsave = saved + act_floats(c->depth, n, g_mlp_mode); b.z_stride = 0;
     b.gy = grad_y; b.gy_stride = 0; b.gacc = nullptr; b.gacc_stride = 0; b.m = 1; b.mcounts = nullptr;
     b.gnu = grad_nu; b.gnu_stride = 0;
     b.partials = (float*)workspace; b.partials_stride = 0; b.partial_pitch = (int)pad4(L.param_count);
     b.gx = grad_x; b.gx_stride = 0; b.n = (int)n; b.counts = nullptr; b.state = nullptr; b.npairs = 1;
-    ndp_launch_bwd(b, (cudaStream_t)stream);
+    if (g_mlp_mode == 0) ndp_launch_bwd_tc(b, (cudaStream_t)stream); else ndp_launch_bwd(b, (cudaStream_t)stream);
     NdpAdamArgs r;
     r.lay = L; r.params = nullptr; r.params_stride = 0; r.pack = nullptr; r.pack_stride = 0;
     r.m = nullptr; r.v = nullptr; r.mv_stride = 0;
@@ -233,7 +251,8 @@ struct ndp_solver {
     float *sraw = nullptr, *traw = nullptr, *bounds = nullptr, *xbox = nullptr, *tbox = nullptr;
     float4 *x4 = nullptr, *t4 = nullptr;
     int *orig_s = nullptr, *orig_t = nullptr, *prev_x = nullptr, *prev_y = nullptr;
-    int npad = 0, S128 = 0, nboxes = 0;
+    int npad = 0, S128 = 0, nboxes = 0, mlp_mode = 0;
+    long long act_pair = 0;
     double* blocksums = nullptr;
     int* counters = nullptr;
     NdpPairState* state = nullptr;
@@ -293,6 +312,8 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
     s->P = s->lay[0].param_count; s->Ppad = (int)pad4(s->P); s->packn = s->lay[0].pack_count;
     s->B = c->max_pairs; s->S = c->samples; s->NS = c->max_src_points; s->NT = c->max_tgt_points;
     s->tiles = (s->S + NDP_TP - 1) / NDP_TP;
+    s->mlp_mode = g_mlp_mode;
+    s->act_pair = act_floats(c->depth, s->S, s->mlp_mode);
     s->plan = nn_plan(s->S, s->S);
     if (c->nn_mode == 0) { s->plan.chunks = 1; s->plan.chunk_targets = 1 << 30; }
     s->S128 = (s->S + NDP_TP - 1) / NDP_TP * NDP_TP; s->nboxes = s->S128 / 32;
@@ -305,7 +326,7 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
     DA(means, B * 6); DA(smp[0], B * S * 3); DA(smp[1], B * S * 3); DA(tsmp, B * S * 3);
     DA(perm_s, B * S); DA(perm_t, B * S); DA(ncount, B); DA(mcount, B); DA(nscount, B); DA(ntcount, B);
     DA(params, B * c->levels * s->Ppad); DA(pack, B * s->packn); DA(adam_m, B * s->Ppad); DA(adam_v, B * s->Ppad);
-    DA(act, B * c->depth * S * NDP_W); DA(zsave, B * S * NDP_ZPITCH); DA(gx, B * S * 3); DA(gacc, B * S * 3);
+    DA(act, B * s->act_pair); DA(zsave, B * S * NDP_ZPITCH); DA(gx, B * S * 3); DA(gacc, B * S * 3);
     DA(partials, B * s->tiles * s->Ppad); DA(loss, B);
     DA(nnpart, B * 2 * s->plan.chunks * s->plan.qpitch); DA(blocksums, B * s->plan.blocks * 2); DA(counters, B);
     DA(state, B);
@@ -391,7 +412,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         NdpFwdArgs f;
         f.lay = L; f.params = lvl_params; f.params_stride = pstride; f.pack = s->pack; f.pack_stride = s->packn;
         f.x = s->smp[cur]; f.x_stride = S * 3; f.y = s->smp[cur ^ 1]; f.y_stride = S * 3; f.nu = nullptr; f.nu_stride = 0;
-        f.act = s->act; f.act_stride = (long long)c.depth * S * NDP_W; f.act_layer_stride = S * NDP_W;
+        f.act = s->act; f.act_stride = s->act_pair; f.act_layer_stride = S * NDP_W;
         f.zsave = s->zsave; f.z_stride = S * NDP_ZPITCH; f.y_add = nullptr; f.y_add_stride = 0;
         f.y4 = culled ? s->x4 : nullptr; f.y4_stride = s->S128; f.orig = s->orig_s; f.orig_stride = S;
         f.ybox = culled ? s->xbox : nullptr; f.box_stride = s->nboxes;
@@ -417,7 +438,8 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         ch.max_break_count = c.max_break_count; ch.break_ratio = (double)c.break_threshold_ratio;
 
         NdpBwdArgs b;
-        b.lay = L; b.params = lvl_params; b.params_stride = pstride; b.x = s->smp[cur]; b.x_stride = S * 3;
+        b.lay = L; b.params = lvl_params; b.params_stride = pstride; b.pack = s->pack; b.pack_stride = s->packn;
+        b.x = s->smp[cur]; b.x_stride = S * 3;
         b.act = s->act; b.act_stride = f.act_stride; b.act_layer_stride = f.act_layer_stride;
         b.zsave = s->zsave; b.z_stride = f.z_stride; b.gy = s->gx; b.gy_stride = S * 3;
         b.gacc = s->gacc; b.gacc_stride = S * 3; b.m = s->S; b.mcounts = s->mcount; b.gnu = nullptr; b.gnu_stride = 0;
@@ -444,13 +466,13 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
                 s->ev_used += 6;
                 CK(cudaEventRecord(ev[0], st));
             }
-            ndp_launch_fwd(f, st);
+            if (s->mlp_mode == 0) ndp_launch_fwd_tc(f, st); else ndp_launch_fwd(f, st);
             if (prof) CK(cudaEventRecord(ev[1], st));
             if (culled) ndp_launch_nn_pruned(pn, st); else ndp_launch_nn(ch.nn, st);
             if (prof) CK(cudaEventRecord(ev[2], st));
             ndp_launch_chamfer_reduce(ch, st);
             if (prof) CK(cudaEventRecord(ev[3], st));
-            ndp_launch_bwd(b, st);
+            if (s->mlp_mode == 0) ndp_launch_bwd_tc(b, st); else ndp_launch_bwd(b, st);
             if (prof) CK(cudaEventRecord(ev[4], st));
             ndp_launch_adam(ad, st);
             if (prof) CK(cudaEventRecord(ev[5], st));
@@ -490,7 +512,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         f.y_add = last ? s->means + 3 : nullptr; f.y_add_stride = 6;
         f.y4 = nullptr; f.y4_stride = 0; f.orig = nullptr; f.orig_stride = 0; f.ybox = nullptr; f.box_stride = 0;
         f.n = s->NS; f.counts = s->nscount; f.state = nullptr; f.npairs = npairs;
-        ndp_launch_fwd(f, st);
+        if (s->mlp_mode == 0) ndp_launch_fwd_tc(f, st); else ndp_launch_fwd(f, st);
         s->launches += 2;
         xin = s->wbuf[wb];
         *final_buf = wb;

@@ -40,6 +40,7 @@ struct NdpLayout {
     int head_w[NDP_MAX_HEAD], head_b[NDP_MAX_HEAD];   // per head row: weight row / bias offsets
     int param_count;
     int pack_in, pack_w[NDP_MAX_HIDDEN], pack_count;
+    int pack_img;               // float offset of the bf16 tri-images of the hidden weights (tensor-core kernels)
     float freq, mu;
 };
 
@@ -72,6 +73,7 @@ static inline NdpLayout ndp_make_layout(int depth, int motion, int rot, int nonr
     int p = 0;
     L.pack_in = p; p += 6 * NDP_W;
     for (int l = 0; l < L.hidden; ++l) { L.pack_w[l] = p; p += NDP_W * NDP_W; }
+    L.pack_img = p; p += L.hidden * (3 * 128 * 128 * 2 / 4);   // 3 bf16 images of 128x128 per hidden layer
     L.pack_count = p;
     return L;
 }
@@ -90,7 +92,11 @@ static inline void ndp_bulk_g2s(void* dst, const void* src, unsigned bytes, NdpM
     if (left == 0) __atomic_fetch_add((unsigned*)&b->phase, 1u, __ATOMIC_SEQ_CST);
 }
 static inline void ndp_mbar_wait(NdpMbar* b, unsigned parity) {
-    while ((__atomic_load_n((unsigned*)&b->phase, __ATOMIC_SEQ_CST) & 1u) == parity) std::this_thread::yield();
+    int us = 1;   // sleep instead of spinning: the emulated MMA runs in ONE of ~256 OS threads
+    while ((__atomic_load_n((unsigned*)&b->phase, __ATOMIC_SEQ_CST) & 1u) == parity) {
+        std::this_thread::sleep_for(std::chrono::microseconds(us));
+        if (us < 2000) us *= 2;
+    }
 }
 static inline void ndp_fence_proxy_async() {}
 #else
@@ -108,14 +114,16 @@ __device__ __forceinline__ void ndp_bulk_g2s(void* dst, const void* src, unsigne
                  ::"r"(ndp_smem_u32(dst)), "l"(src), "r"(bytes), "r"(ndp_smem_u32(b)) : "memory");
 }
 __device__ __forceinline__ void ndp_mbar_wait(NdpMbar* b, unsigned parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "NDP_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra NDP_DONE;\n\t"
-        "bra NDP_WAIT;\n\t"
-        "NDP_DONE:\n\t}"
-        ::"r"(ndp_smem_u32(b)), "r"(parity) : "memory");
+    // try_wait suspends the thread in hardware for a bounded time; the loop is bounded too, so a
+    // protocol error surfaces as a trapped kernel (CUDA error) instead of a hung GPU
+    const unsigned addr = ndp_smem_u32(b);
+    for (unsigned spin = 0; spin < (1u << 24); ++spin) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
 }
 __device__ __forceinline__ void ndp_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif

@@ -25,12 +25,15 @@ struct NdpFwdArgs {
     const NdpPairState* state;                       // pairs with state.stopped are skipped, or null
     int npairs;
 };
-void ndp_launch_fwd(const NdpFwdArgs& a, cudaStream_t s);
+void ndp_launch_fwd(const NdpFwdArgs& a, cudaStream_t s);      // FP32-pipe version (act: fp32 [L+1][n][128])
+// tensor-core version: act = [tile][L+1] bf16 tri-images (98304 bytes each), act_stride in floats per pair
+void ndp_launch_fwd_tc(const NdpFwdArgs& a, cudaStream_t s);
 
 // ---- kernel (3a): backward of kernel (1) -> per-tile parameter-gradient partials -----------------
 struct NdpBwdArgs {
     NdpLayout lay;
     const float* params; long long params_stride;
+    const float* pack;   long long pack_stride;       // tensor-core version only (weight tri-images)
     const float* x;      long long x_stride;
     const float* act;    long long act_stride; long long act_layer_stride;
     const float* zsave;  long long z_stride;
@@ -45,6 +48,7 @@ struct NdpBwdArgs {
     int npairs;
 };
 void ndp_launch_bwd(const NdpBwdArgs& a, cudaStream_t s);
+void ndp_launch_bwd_tc(const NdpBwdArgs& a, cudaStream_t s);   // needs `pack` (weight tri-images)
 
 // ---- kernel (3b): fixed-order reduction of the partials + Adam + transposed-copy refresh ---------
 struct NdpAdamArgs {
@@ -161,3 +165,7 @@ size_t ndp_fwd_smem_bytes();
 size_t ndp_bwd_smem_bytes();
 int ndp_fwd_init();   // opt-in dynamic shared memory size; returns cudaError_t
 int ndp_bwd_init();
+int ndp_fwd_tc_init();
+int ndp_bwd_tc_init();
+size_t ndp_fwd_tc_smem_bytes();
+size_t ndp_bwd_tc_smem_bytes();

@@ -1,0 +1,180 @@
+// tcgen05 (5th-generation tensor core) + TMEM primitives for the warp-field kernels, and the
+// shared-memory "image" layout they use.
+//
+// Precision scheme: every fp32 operand x is split exactly into three bf16 terms x = x1 + x2 + x3
+// (8 + 8 + 8 significand bits) and the product is accumulated in fp32 in TMEM from the six partial
+// products x1y1, x1y2, x2y1, x1y3, x2y2, x3y1 (dropped terms are O(2^-24)): fp32-level accuracy
+// (measured 2e-6 of the largest entry for K = 128) at 1.5 PFLOP/s of dense bf16 issue
+// (scripts/microbench/umma_test.cu: 2.45 us per 128x128x128 product per SM vs 12.7 us on the FP32
+// pipes), which keeps the 1e-4 parity contract that single-pass TF32/BF16 would break.
+//
+// Image layout: a [128][C] bf16 matrix is stored as 8x8 "core matrices" of 8 rows x 16 bytes,
+//     byte offset(r, c) = (r/8) * RS + (c/8) * 128 + (r%8) * 16 + (c%8) * 2,   RS = (C/8) * 128
+// which is BOTH canonical no-swizzle UMMA layouts at once: as a K-major operand (K = c) with
+// LBO = 128, SBO = RS, and as an MN-major operand (MN = c, K = r) with SBO = 128, LBO = RS.  One
+// image of the weights therefore serves h W^T (forward) and delta W (backward), one image of delta
+// serves delta W and delta^T h, without any transposed copy.
+// Descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
+#pragma once
+#include "ndp_common.cuh"
+
+#define NDP_IMG_CS 128                                   // bytes between 8-column chunks
+#define NDP_IMG_RS(C) (((C) / 8) * 128)                  // bytes between 8-row groups
+#define NDP_IMG_BYTES(C) (16 * NDP_IMG_RS(C))            // 128 rows
+#define NDP_IMG128 NDP_IMG_BYTES(128)                    // 32768
+#define NDP_TRI128 (3 * NDP_IMG128)                      // 98304: hi / mid / lo images
+
+__device__ __forceinline__ unsigned ndp_img_off(int r, int c, int rs) {
+    return (unsigned)((r >> 3) * rs + (c >> 3) * NDP_IMG_CS + (r & 7) * 16 + (c & 7) * 2);
+}
+
+// bf16 round-to-nearest-even of an fp32 value, returned as the 16 high bits; and back
+__device__ __forceinline__ unsigned ndp_bf16_rn(float x) {
+    unsigned u = __float_as_uint(x);
+    if ((u & 0x7f800000u) == 0x7f800000u) return u >> 16;           // inf / nan: truncate
+    return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
+}
+__device__ __forceinline__ float ndp_bf16_to_f32(unsigned h) { return __uint_as_float(h << 16); }
+
+// x -> (x1, x2, x3) bf16 bit patterns with x1 + x2 + x3 == x to fp32 precision
+__device__ __forceinline__ void ndp_split3(float x, unsigned& h1, unsigned& h2, unsigned& h3) {
+    h1 = ndp_bf16_rn(x);
+    const float r1 = x - ndp_bf16_to_f32(h1);
+    h2 = ndp_bf16_rn(r1);
+    const float r2 = r1 - ndp_bf16_to_f32(h2);
+    h3 = ndp_bf16_rn(r2);
+}
+
+// split 8 consecutive values and store them as one 16-byte chunk in each of the three images
+__device__ __forceinline__ void ndp_store_chunk3(unsigned char* tri, unsigned img_bytes, unsigned off, const float (&v)[8]) {
+    unsigned a[8], b[8], c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ndp_split3(v[j], a[j], b[j], c[j]);
+    uint4 p0, p1, p2;
+    p0.x = a[0] | (a[1] << 16); p0.y = a[2] | (a[3] << 16); p0.z = a[4] | (a[5] << 16); p0.w = a[6] | (a[7] << 16);
+    p1.x = b[0] | (b[1] << 16); p1.y = b[2] | (b[3] << 16); p1.z = b[4] | (b[5] << 16); p1.w = b[6] | (b[7] << 16);
+    p2.x = c[0] | (c[1] << 16); p2.y = c[2] | (c[3] << 16); p2.z = c[4] | (c[5] << 16); p2.w = c[6] | (c[7] << 16);
+    *(uint4*)(tri + off) = p0;
+    *(uint4*)(tri + img_bytes + off) = p1;
+    *(uint4*)(tri + 2 * img_bytes + off) = p2;
+}
+
+// instruction descriptor: D = f32, A = B = bf16, M x N tile, operand majors (0 = K-major, 1 = MN-major)
+__device__ __forceinline__ unsigned ndp_idesc_bf16(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)a_mn << 15) | ((unsigned)b_mn << 16) |
+           ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+
+#ifdef NDP_EMU
+// ---------------------------------------------------------------- CPU emulation (tests only)
+struct NdpUmmaDesc { const unsigned char* p; unsigned lbo, sbo; };
+namespace ndp_emu { extern float tmem[128][512]; }
+static inline NdpUmmaDesc ndp_umma_desc(const void* p, unsigned lbo, unsigned sbo) { return NdpUmmaDesc{(const unsigned char*)p, lbo, sbo}; }
+static inline NdpUmmaDesc ndp_umma_desc_adv(NdpUmmaDesc d, unsigned bytes) { d.p += bytes; return d; }
+static inline unsigned ndp_tmem_alloc(unsigned* slot, int) { *slot = 0; return 0; }
+static inline void ndp_tmem_dealloc(unsigned, int) {}
+static inline void ndp_tc_fence_before() {}
+static inline void ndp_tc_fence_after() {}
+static inline void ndp_umma_bf16(unsigned tmem_d, NdpUmmaDesc da, NdpUmmaDesc db, unsigned idesc, unsigned acc) {
+    const int N = (int)((idesc >> 17) & 0x3f) << 3, M = (int)((idesc >> 24) & 0x1f) << 4;
+    const int a_mn = (idesc >> 15) & 1, b_mn = (idesc >> 16) & 1;
+    const int col0 = (int)(tmem_d & 0xffff), lane0 = (int)(tmem_d >> 16);
+    auto ld = [](NdpUmmaDesc d, int mn, int k, int is_mn) -> float {
+        const unsigned off = is_mn ? (unsigned)((mn >> 3) * d.sbo + (mn & 7) * 2 + (k >> 3) * d.lbo + (k & 7) * 16)
+                                   : (unsigned)((mn >> 3) * d.sbo + (mn & 7) * 16 + (k >> 3) * d.lbo + (k & 7) * 2);
+        unsigned short h; memcpy(&h, d.p + off, 2);
+        return __uint_as_float((unsigned)h << 16);
+    };
+    for (int m = 0; m < M; ++m)
+        for (int n = 0; n < N; ++n) {
+            float s = acc ? ndp_emu::tmem[lane0 + m][col0 + n] : 0.0f;
+            for (int k = 0; k < 16; ++k) s += ld(da, m, k, a_mn) * ld(db, n, k, b_mn);
+            ndp_emu::tmem[lane0 + m][col0 + n] = s;
+        }
+}
+static inline void ndp_umma_commit(NdpMbar* b) { __atomic_fetch_add((unsigned*)&b->phase, 1u, __ATOMIC_SEQ_CST); }
+static inline void ndp_tmem_ld32(unsigned taddr, float (&v)[32]) {
+    const int col0 = (int)(taddr & 0xffff), lane = (int)(taddr >> 16) + (int)(threadIdx.x & 31);
+    for (int j = 0; j < 32; ++j) v[j] = ndp_emu::tmem[lane][col0 + j];
+}
+static inline void ndp_bulk_s2g(void* g, const void* s, unsigned bytes) { memcpy(g, s, bytes); }
+static inline void ndp_bulk_commit() {}
+static inline void ndp_bulk_wait_read0() {}
+static inline void ndp_bulk_wait0() {}
+#else
+// ---------------------------------------------------------------- sm_100a
+typedef unsigned long long NdpUmmaDesc;
+__device__ __forceinline__ NdpUmmaDesc ndp_umma_desc(const void* p, unsigned lbo, unsigned sbo) {
+    const unsigned saddr = ndp_smem_u32(p);
+    unsigned long long d = (unsigned long long)((saddr & 0x3FFFFu) >> 4);
+    d |= (unsigned long long)(lbo >> 4) << 16;      // leading-dimension byte offset
+    d |= (unsigned long long)(sbo >> 4) << 32;      // stride-dimension byte offset
+    d |= 1ull << 46;                                // descriptor version (Blackwell); no swizzle, base offset 0
+    return d;
+}
+__device__ __forceinline__ NdpUmmaDesc ndp_umma_desc_adv(NdpUmmaDesc d, unsigned bytes) { return d + (bytes >> 4); }
+// warp-collective: allocate ncols (power of two >= 32) TMEM columns, base address written to *slot
+__device__ __forceinline__ void ndp_tmem_alloc_warp(unsigned* slot, int ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ndp_smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void ndp_tmem_dealloc(unsigned taddr, int ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void ndp_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void ndp_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void ndp_umma_bf16(unsigned tmem_d, NdpUmmaDesc da, NdpUmmaDesc db, unsigned idesc, unsigned acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+// arrive on the mbarrier once every previously issued MMA of this thread has completed
+__device__ __forceinline__ void ndp_umma_commit(NdpMbar* b) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ndp_smem_u32(b)) : "memory");
+}
+// this warp's 32 TMEM lanes x 32 consecutive columns -> 32 registers per thread (blocking)
+__device__ __forceinline__ void ndp_tmem_ld32(unsigned taddr, float (&v)[32]) {
+    unsigned r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+// bulk asynchronous copy shared -> global (TMA store, SASS UBLKCP) in the calling thread's bulk group
+__device__ __forceinline__ void ndp_bulk_s2g(void* g, const void* s, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(ndp_smem_u32(s)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ndp_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ndp_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void ndp_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+#endif
+
+#ifdef NDP_EMU
+static inline void ndp_tmem_alloc_warp(unsigned* slot, int n) { ndp_tmem_alloc(slot, n); }
+#endif
+
+// One fp32-accurate product D[128 x N] (+)= A . B over K = 16 * ksteps from tri-images:
+// the six bf16 partial products, issued by ONE thread.  a_step / b_step: descriptor byte advance
+// per 16-deep k-step; a_img / b_img: byte distance between the hi / mid / lo images.
+__device__ __forceinline__ void ndp_umma_gemm6(unsigned tmem_d, NdpUmmaDesc a0, unsigned a_img, unsigned a_step,
+                                               NdpUmmaDesc b0, unsigned b_img, unsigned b_step, int ksteps,
+                                               unsigned idesc, bool accumulate) {
+    unsigned acc = accumulate ? 1u : 0u;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; i + j < 3; ++j) {
+            NdpUmmaDesc da = ndp_umma_desc_adv(a0, i * a_img), db = ndp_umma_desc_adv(b0, j * b_img);
+            for (int ks = 0; ks < ksteps; ++ks) {
+                ndp_umma_bf16(tmem_d, da, db, idesc, acc);
+                acc = 1u;
+                da = ndp_umma_desc_adv(da, a_step);
+                db = ndp_umma_desc_adv(db, b_step);
+            }
+        }
+}

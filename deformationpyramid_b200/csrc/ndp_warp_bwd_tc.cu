@@ -1,0 +1,326 @@
+// Kernel (3a), tensor-core version: backward of kernel (1) over a tile of 128 points -> this
+// tile's partial parameter gradients (reduced in fixed order by kernel (3b)).
+//
+// Replaces the autograd backward of NDPLayer.forward (model/nets.py:111-140) that the reference
+// runs in loss.backward() (model/registration.py:236).
+//
+// Every reduction over the tile's 128 points is a tcgen05 GEMM with K = points (operands as bf16
+// tri-images, fp32 accumulation in TMEM, see ndp_tc.cuh), issued by one thread:
+//     head grads   dW_h  = hg^T h_L          A = hg image   (MN-major)  B = h_L   (MN-major)
+//     weight grads dW_l  = delta^T h_l       A = delta      (MN-major)  B = h_l   (MN-major)
+//     bias grads   db_l  = delta^T 1         A = delta      (MN-major)  B = E[:,6] = 1
+//     input layer  dW_in = delta_0^T e       A = delta_0    (MN-major)  B = E[:,0:6] = posenc
+//     back-prop    delta_l = (delta W_l).relu'   A = delta  (K-major)   B = W_l   (MN-major)
+// The SAME delta image is the MN-major operand of the dW products and the K-major operand of the
+// back-propagation product, and the SAME weight image serves forward and backward (the core-matrix
+// layout is both canonical UMMA layouts at once), so nothing is ever transposed.  h_l tri-images
+// come back from HBM by TMA bulk copies exactly as the forward kernel's bulk stores wrote them;
+// the weight image of the layer replaces h_l in shared memory as soon as the dW MMAs retire,
+// overlapping with the TMEM -> HBM epilogue of dW.  No atomics: one partial row per tile.
+#include "ndp_kernels.h"
+#include "ndp_tc.cuh"
+
+#define NDP_IMG16 NDP_IMG_BYTES(16)     // [128][16] bf16 image: 4096 bytes
+struct BwdTcSmem {
+    unsigned char D[NDP_TRI128];        // delta tri-image (hosts the head-gradient image first)
+    unsigned char X[NDP_TRI128];        // h_l tri-image, then W_l tri-image
+    unsigned char E[3 * NDP_IMG16];     // [128 points][16]: cols 0..5 positional encoding, col 6 = 1
+    float hw[NDP_MAX_HEAD * NDP_W];
+    float hg[NDP_TP * NDP_ZPITCH];      // mlp_scale * dL/dz
+    float xs[NDP_TP * 4];
+    float gxs[NDP_TP * 4];
+    NdpMbar bar_x, bar_mma;
+    unsigned tmem_slot, pad[3];
+};
+size_t ndp_bwd_tc_smem_bytes() { return sizeof(BwdTcSmem) + 1024; }
+
+#define TM_DW 0u
+#define TM_DH 128u
+#define TM_SM 256u
+
+__global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdArgs a) {
+    NDP_DYN_SMEM(smem_raw);
+    BwdTcSmem& S = *(BwdTcSmem*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+
+    const int tid = threadIdx.x, pair = blockIdx.y, tile = blockIdx.x;
+    const int n = a.counts ? a.counts[pair] : a.n;
+    if (tile * NDP_TP >= n) return;
+    if (a.state && a.state[pair].stopped) return;
+    const NdpLayout& L = a.lay;
+    const float* params = a.params + (long long)pair * a.params_stride;
+    const unsigned char* wimg = (const unsigned char*)(a.pack + (long long)pair * a.pack_stride + L.pack_img);
+    const int LH = L.hidden, HD = L.head_dim;
+    const unsigned char* gact = (const unsigned char*)a.act + ((long long)pair * a.act_stride) * 4 +
+                                (long long)tile * (LH + 1) * NDP_TRI128;
+    float* part = a.partials + (long long)pair * a.partials_stride + (long long)tile * a.partial_pitch;
+    const int warp = tid >> 5, lane = tid & 31, p = tid & (NDP_TP - 1), half = tid >> 7;
+    const int RS = NDP_IMG_RS(128), CS = NDP_IMG_CS;
+    unsigned xph = 0, mph = 0;
+
+    if (warp == 0) ndp_tmem_alloc_warp(&S.tmem_slot, 512);
+    if (tid == 0) { ndp_mbar_init(&S.bar_x, 1); ndp_mbar_init(&S.bar_mma, 1); }
+    for (int i = tid; i < HD * NDP_W; i += NDP_THREADS) S.hw[i] = __ldg(params + L.head_w[i >> 7] + (i & 127));
+    ndp_tc_fence_before();
+    __syncthreads();
+    ndp_tc_fence_after();
+    const unsigned tmem = S.tmem_slot;
+    const unsigned tlane = tmem + ((unsigned)((warp & 3) * 32) << 16);
+    if (tid == 0) ndp_stage_bulk(S.X, gact + (long long)LH * NDP_TRI128, NDP_TRI128, &S.bar_x);
+
+    // ---- per point: dL/dy -> dL/dz (heads) and the direct part of dL/dx; E and head-gradient images
+    if (tid < NDP_TP) {
+        const int gp = tile * NDP_TP + tid;
+        float gz[NDP_MAX_HEAD];
+#pragma unroll
+        for (int r = 0; r < NDP_MAX_HEAD; ++r) gz[r] = 0.0f;
+        float x[3] = {0.0f, 0.0f, 0.0f}, gxd[3] = {0.0f, 0.0f, 0.0f};
+        if (gp < n) {
+            const float* xp = a.x + (long long)pair * a.x_stride + (long long)gp * 3;
+            x[0] = __ldg(xp); x[1] = __ldg(xp + 1); x[2] = __ldg(xp + 2);
+            const float* gp_ = a.gy + (long long)pair * a.gy_stride + (long long)gp * 3;
+            float gy[3] = {gp_[0], gp_[1], gp_[2]};
+            if (a.gacc) {   // scattered Chamfer term, 2^-40 fixed point (order independent)
+                unsigned long long* ga = a.gacc + (long long)pair * a.gacc_stride + (long long)gp * 3;
+                const int m = a.mcounts ? a.mcounts[pair] : a.m;
+                const double sc = 9.094947017729282e-13 / (double)m;
+                const long long a0 = (long long)ga[0], a1 = (long long)ga[1], a2 = (long long)ga[2];
+                const bool poison = (a0 >= (1LL << 60)) || (a0 <= -(1LL << 60));
+                gy[0] += poison ? __int_as_float(0x7fc00000) : (float)((double)a0 * sc);
+                gy[1] += (float)((double)a1 * sc);
+                gy[2] += (float)((double)a2 * sc);
+                ga[0] = 0ull; ga[1] = 0ull; ga[2] = 0ull;
+            }
+            float z[NDP_MAX_HEAD];
+            const float* zp = a.zsave + (long long)pair * a.z_stride + (long long)gp * NDP_ZPITCH;
+#pragma unroll
+            for (int r = 0; r < NDP_MAX_HEAD; ++r) z[r] = zp[r];
+            const float gnu = (a.gnu && L.nonrigid) ? a.gnu[(long long)pair * a.gnu_stride + gp] : 0.0f;
+            ndp_point_backward(L.motion, L.rot, L.nonrigid, z, x, gy, gnu, gz, gxd);
+        }
+        float v0[8], v1[8];
+#pragma unroll
+        for (int r = 0; r < NDP_MAX_HEAD; ++r) {
+            const float g = L.mu * gz[r];
+            S.hg[tid * NDP_ZPITCH + r] = g;
+            if (r < 8) v0[r] = g; else v1[r - 8] = g;
+        }
+#pragma unroll
+        for (int r = NDP_MAX_HEAD - 8; r < 8; ++r) v1[r] = 0.0f;
+        ndp_store_chunk3(S.D, NDP_IMG128, ndp_img_off(tid, 0, RS), v0);     // head-gradient image, cols 0..15
+        ndp_store_chunk3(S.D, NDP_IMG128, ndp_img_off(tid, 8, RS), v1);
+        S.xs[tid * 4 + 0] = x[0]; S.xs[tid * 4 + 1] = x[1]; S.xs[tid * 4 + 2] = x[2];
+        S.gxs[tid * 4 + 0] = gxd[0]; S.gxs[tid * 4 + 1] = gxd[1]; S.gxs[tid * 4 + 2] = gxd[2];
+        float e0[8], e1[8], s, c;
+        sincosf(x[0] * L.freq, &s, &c); e0[0] = s; e0[1] = c;
+        sincosf(x[1] * L.freq, &s, &c); e0[2] = s; e0[3] = c;
+        sincosf(x[2] * L.freq, &s, &c); e0[4] = s; e0[5] = c;
+        e0[6] = 1.0f; e0[7] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e1[j] = 0.0f;
+        ndp_store_chunk3(S.E, NDP_IMG16, ndp_img_off(tid, 0, NDP_IMG_RS(16)), e0);
+        ndp_store_chunk3(S.E, NDP_IMG16, ndp_img_off(tid, 8, NDP_IMG_RS(16)), e1);
+    }
+    ndp_fence_proxy_async();
+    __syncthreads();
+
+    const unsigned id_nn = ndp_idesc_bf16(128, 128, 1, 1), id_sm = ndp_idesc_bf16(128, 16, 1, 1), id_kn = ndp_idesc_bf16(128, 128, 0, 1);
+    // ---- head gradients: dW_h = hg^T h_L (rows >= head_dim of the result are never read), db_h = hg^T 1
+    ndp_mbar_wait(&S.bar_x, xph); xph ^= 1;
+    if (tid == 0) {
+        ndp_tc_fence_after();
+        ndp_umma_gemm6(tmem + TM_DH, ndp_umma_desc(S.D, RS, CS), NDP_IMG128, 2 * RS,
+                       ndp_umma_desc(S.X, RS, CS), NDP_IMG128, 2 * RS, 8, id_nn, false);
+        ndp_umma_gemm6(tmem + TM_SM, ndp_umma_desc(S.D, RS, CS), NDP_IMG128, 2 * RS,
+                       ndp_umma_desc(S.E, NDP_IMG_RS(16), CS), NDP_IMG16, 2 * NDP_IMG_RS(16), 8, id_sm, false);
+        ndp_umma_commit(&S.bar_mma);
+    }
+    // ---- delta at the top activation, in registers while the head GEMMs run: (W_h^T hg) . relu'(h_L)
+    float dt[64];
+    {
+        float g[NDP_MAX_HEAD];
+#pragma unroll
+        for (int r = 0; r < NDP_MAX_HEAD; ++r) g[r] = (r < HD) ? S.hg[p * NDP_ZPITCH + r] : 0.0f;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+            const int o0 = half * 64 + ch * 8;
+            const uint4 hq = *(const uint4*)(S.X + ndp_img_off(p, o0, RS));       // hi parts of h_L: sign/zero test
+            const unsigned hh[4] = {hq.x, hq.y, hq.z, hq.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float s = 0.0f;
+#pragma unroll
+                for (int r = 0; r < NDP_MAX_HEAD; ++r) s = fmaf(g[r], (r < HD) ? S.hw[r * NDP_W + o0 + j] : 0.0f, s);
+                const unsigned hb = (hh[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
+                const bool pos = ((hb & 0x8000u) == 0u) && ((hb & 0x7fffu) != 0u);
+                dt[ch * 8 + j] = pos ? s : 0.0f;
+            }
+        }
+    }
+    ndp_mbar_wait(&S.bar_mma, mph); mph ^= 1;
+    ndp_tc_fence_after();
+    if ((warp & 3) == 0) {      // TMEM lanes 0..31 hold the head rows
+#pragma unroll 1
+        for (int c32 = 0; c32 < 2; ++c32) {
+            float v[32];
+            const int col0 = half * 64 + c32 * 32;
+            ndp_tmem_ld32(tlane + TM_DH + col0, v);
+            if (lane < HD)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) part[L.head_w[lane] + col0 + j] = v[j];
+        }
+        if (half == 0) {
+            float v[32];
+            ndp_tmem_ld32(tlane + TM_SM, v);
+            if (lane < HD) part[L.head_b[lane]] = v[6];
+        }
+    }
+    // delta_top replaces the head-gradient image
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+        float u[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) u[j] = dt[ch * 8 + j];
+        ndp_store_chunk3(S.D, NDP_IMG128, ndp_img_off(p, half * 64 + ch * 8, RS), u);
+    }
+    ndp_tc_fence_before();
+    ndp_fence_proxy_async();
+    __syncthreads();
+    ndp_tc_fence_after();
+
+    for (int l = LH - 1; l >= 0; --l) {
+        if (tid == 0) ndp_stage_bulk(S.X, gact + (long long)l * NDP_TRI128, NDP_TRI128, &S.bar_x);     // h_l
+        ndp_mbar_wait(&S.bar_x, xph); xph ^= 1;
+        // relu' mask of h_l (hi part > 0) for this thread's row / column half, before W_l replaces h_l
+        unsigned mask[2] = {0u, 0u};
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+            const uint4 hq = *(const uint4*)(S.X + ndp_img_off(p, half * 64 + ch * 8, RS));
+            const unsigned hh[4] = {hq.x, hq.y, hq.z, hq.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const unsigned hb = (hh[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
+                const bool pos = ((hb & 0x8000u) == 0u) && ((hb & 0x7fffu) != 0u);
+                mask[ch >> 2] |= (pos ? 1u : 0u) << ((ch & 3) * 8 + j);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            ndp_tc_fence_after();
+            // dW_l[o][i] = sum_p delta[p][o] h_l[p][i];  db_l[o] = sum_p delta[p][o]
+            ndp_umma_gemm6(tmem + TM_DW, ndp_umma_desc(S.D, RS, CS), NDP_IMG128, 2 * RS,
+                           ndp_umma_desc(S.X, RS, CS), NDP_IMG128, 2 * RS, 8, id_nn, false);
+            ndp_umma_gemm6(tmem + TM_SM, ndp_umma_desc(S.D, RS, CS), NDP_IMG128, 2 * RS,
+                           ndp_umma_desc(S.E, NDP_IMG_RS(16), CS), NDP_IMG16, 2 * NDP_IMG_RS(16), 8, id_sm, false);
+            ndp_umma_commit(&S.bar_mma);
+        }
+        ndp_mbar_wait(&S.bar_mma, mph); mph ^= 1;
+        ndp_tc_fence_after();
+        if (tid == 0) ndp_stage_bulk(S.X, wimg + (long long)l * NDP_TRI128, NDP_TRI128, &S.bar_x);     // W_l over h_l
+        // dW epilogue: TMEM -> this tile's partial row (thread = output row o, 64 input columns)
+        {
+            const int o = (warp & 3) * 32 + lane;
+#pragma unroll 1
+            for (int c32 = 0; c32 < 2; ++c32) {
+                float v[32];
+                const int col0 = half * 64 + c32 * 32;
+                ndp_tmem_ld32(tlane + TM_DW + col0, v);
+                float* dst = part + L.off_w[l] + o * NDP_W + col0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *(float4*)(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            if (half == 0) {
+                float v[32];
+                ndp_tmem_ld32(tlane + TM_SM, v);
+                part[L.off_b[l] + o] = v[6];
+            }
+        }
+        ndp_mbar_wait(&S.bar_x, xph); xph ^= 1;
+        if (tid == 0) {
+            ndp_tc_fence_after();
+            // delta_l[p][i] = sum_o delta[p][o] W_l[o][i]
+            ndp_umma_gemm6(tmem + TM_DH, ndp_umma_desc(S.D, CS, RS), NDP_IMG128, 2 * CS,
+                           ndp_umma_desc(S.X, RS, CS), NDP_IMG128, 2 * RS, 8, id_kn, false);
+            ndp_umma_commit(&S.bar_mma);
+        }
+        ndp_mbar_wait(&S.bar_mma, mph); mph ^= 1;
+        ndp_tc_fence_after();
+        // dH epilogue: relu' mask, re-split, delta image updated in place
+#pragma unroll 1
+        for (int c32 = 0; c32 < 2; ++c32) {
+            float v[32];
+            const int col0 = half * 64 + c32 * 32;
+            ndp_tmem_ld32(tlane + TM_DH + col0, v);
+#pragma unroll
+            for (int s8 = 0; s8 < 4; ++s8) {
+                float u[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) u[j] = ((mask[c32] >> (s8 * 8 + j)) & 1u) ? v[s8 * 8 + j] : 0.0f;
+                ndp_store_chunk3(S.D, NDP_IMG128, ndp_img_off(p, col0 + s8 * 8, RS), u);
+            }
+        }
+        ndp_tc_fence_before();
+        ndp_fence_proxy_async();
+        __syncthreads();
+        ndp_tc_fence_after();
+    }
+
+    // ---- input layer: [dW_in | db_in][o][0..6] = sum_p delta_0[p][o] E[p][0..6]
+    if (tid == 0) {
+        ndp_umma_gemm6(tmem + TM_SM, ndp_umma_desc(S.D, RS, CS), NDP_IMG128, 2 * RS,
+                       ndp_umma_desc(S.E, NDP_IMG_RS(16), CS), NDP_IMG16, 2 * NDP_IMG_RS(16), 8, id_sm, false);
+        ndp_umma_commit(&S.bar_mma);
+    }
+    ndp_mbar_wait(&S.bar_mma, mph); mph ^= 1;
+    ndp_tc_fence_after();
+    if (half == 0) {
+        float v[32];
+        const int o = (warp & 3) * 32 + lane;
+        ndp_tmem_ld32(tlane + TM_SM, v);
+        float* dst = part + L.off_w_in + o * 6;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) dst[c] = v[c];
+        part[L.off_b_in + o] = v[6];
+    }
+    if (a.gx && tid < NDP_TP) {     // optional dL/dx: direct part + path through the positional encoding
+        const int gp = tile * NDP_TP + tid;
+        if (gp < n) {
+            float de[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+            const float* wi = params + L.off_w_in;
+            for (int ch = 0; ch < 16; ++ch) {
+                const unsigned off = ndp_img_off(tid, ch * 8, RS);
+                const uint4 q0 = *(const uint4*)(S.D + off), q1 = *(const uint4*)(S.D + NDP_IMG128 + off), q2 = *(const uint4*)(S.D + 2 * NDP_IMG128 + off);
+                const unsigned w0[4] = {q0.x, q0.y, q0.z, q0.w}, w1[4] = {q1.x, q1.y, q1.z, q1.w}, w2[4] = {q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int sh = (j & 1) * 16;
+                    const float d = ndp_bf16_to_f32((w0[j >> 1] >> sh) & 0xffffu) + ndp_bf16_to_f32((w1[j >> 1] >> sh) & 0xffffu) +
+                                    ndp_bf16_to_f32((w2[j >> 1] >> sh) & 0xffffu);
+                    const int o = ch * 8 + j;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) de[c] = fmaf(d, __ldg(wi + o * 6 + c), de[c]);
+                }
+            }
+            float* gxp = a.gx + (long long)pair * a.gx_stride + (long long)gp * 3;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                float s, c;
+                sincosf(S.xs[tid * 4 + d] * L.freq, &s, &c);
+                gxp[d] = S.gxs[tid * 4 + d] + L.freq * (c * de[2 * d] - s * de[2 * d + 1]);
+            }
+        }
+    }
+    ndp_tc_fence_before();
+    __syncthreads();
+    if (warp == 0) ndp_tmem_dealloc(tmem, 512);
+}
+
+void ndp_launch_bwd_tc(const NdpBwdArgs& a, cudaStream_t s) {
+    if (a.npairs <= 0 || a.n <= 0) return;
+    dim3 grid((a.n + NDP_TP - 1) / NDP_TP, a.npairs);
+    NDP_LAUNCH(ndp_warp_bwd_tc_kernel, grid, dim3(NDP_THREADS), ndp_bwd_tc_smem_bytes(), s, a);
+}
+
+int ndp_bwd_tc_init() {
+    return (int)cudaFuncSetAttribute(ndp_warp_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)ndp_bwd_tc_smem_bytes());
+}

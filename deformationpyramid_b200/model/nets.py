@@ -44,7 +44,7 @@ class _NDPLayerFn(torch.autograd.Function):
             # the flat block may be updated in place by the optimiser before backward is called
             # a second time; autograd's version counter on `flat` is not tracked here, matching
             # the usage in shape_transfer.py (one backward per forward).
-            ctx.save_for_backward(flat, xc, saved)
+            ctx.save_for_backward(flat, xc, saved, pack)
         if nu is None:
             nu = x.new_empty(0)
         return y, nu
@@ -52,10 +52,10 @@ class _NDPLayerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy, gnu):
         layer = ctx.layer
-        flat, xc, saved = ctx.saved_tensors
+        flat, xc, saved, pack = ctx.saved_tensors
         gy = gy.contiguous()
         gnu_t = gnu.contiguous() if (layer.nonrigidity_est and gnu is not None) else None
-        gflat, gx = ops.layer_backward(layer._cfg, flat, xc, saved, gy, gnu_t, need_grad_x=ctx.x_needs_grad)
+        gflat, gx = ops.layer_backward(layer._cfg, flat, pack, xc, saved, gy, gnu_t, need_grad_x=ctx.x_needs_grad)
         grads, off = [], 0
         for _, shape in layer._layout:
             k = numel(shape)

@@ -86,19 +86,19 @@ def layer_forward(cfg: LayerCfg, params: torch.Tensor, pack: torch.Tensor, x: to
     nu = torch.empty(n, dtype=torch.float32, device=x.device) if cfg.nonrigidity else None
     saved = None
     if need_saved:
-        spp = lib.ndp_saved_floats_per_point(ctypes.byref(cfg))
-        saved = torch.empty(max(1, n * int(spp)), dtype=torch.float32, device=x.device)
+        nf = int(lib.ndp_saved_floats(ctypes.byref(cfg), n))
+        saved = torch.empty(max(4, nf), dtype=torch.float32, device=x.device)
     _lib.check(lib, lib.ndp_layer_forward(ctypes.byref(cfg), _ptr(params), _ptr(pack), _ptr(x), n, _ptr(y),
                                           _ptr(nu), _ptr(saved), _stream(lib, x)), "ndp_layer_forward")
     return y, nu, saved
 
 
-def layer_backward(cfg: LayerCfg, params: torch.Tensor, x: torch.Tensor, saved: torch.Tensor,
+def layer_backward(cfg: LayerCfg, params: torch.Tensor, pack: torch.Tensor, x: torch.Tensor, saved: torch.Tensor,
                    grad_y: torch.Tensor, grad_nu: Optional[torch.Tensor] = None, need_grad_x: bool = False,
                    lib=None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Backward of NDPLayer.forward: -> (dL/dparams flat [P], dL/dx [n,3] | None)."""
     lib = _get(lib)
-    for t, nm in ((params, "params"), (x, "x"), (saved, "saved"), (grad_y, "grad_y")):
+    for t, nm in ((params, "params"), (pack, "pack"), (x, "x"), (saved, "saved"), (grad_y, "grad_y")):
         _chk_tensor(lib, t, nm)
     if grad_nu is not None:
         _chk_tensor(lib, grad_nu, "grad_nu")
@@ -108,10 +108,16 @@ def layer_backward(cfg: LayerCfg, params: torch.Tensor, x: torch.Tensor, saved: 
     gx = torch.empty_like(x) if need_grad_x else None
     wsb = int(lib.ndp_backward_workspace_bytes(ctypes.byref(cfg), n))
     ws = torch.empty(max(4, wsb // 4), dtype=torch.float32, device=x.device)
-    _lib.check(lib, lib.ndp_layer_backward(ctypes.byref(cfg), _ptr(params), _ptr(x), n, _ptr(saved),
+    _lib.check(lib, lib.ndp_layer_backward(ctypes.byref(cfg), _ptr(params), _ptr(pack), _ptr(x), n, _ptr(saved),
                                            _ptr(grad_y), _ptr(grad_nu), _ptr(gparams), _ptr(gx), _ptr(ws),
                                            _stream(lib, x)), "ndp_layer_backward")
     return gparams, gx
+
+
+def set_mlp_mode(mode: int, lib=None) -> None:
+    """0: hidden layers on the tensor cores (default), 1: FP32 pipes.  Affects later calls / solvers."""
+    lib = _get(lib)
+    _lib.check(lib, lib.ndp_set_mlp_mode(int(mode)), "ndp_set_mlp_mode")
 
 
 def chamfer(x: torch.Tensor, y: torch.Tensor, trunc: float, grad_scale: float = 1.0,

@@ -47,8 +47,13 @@ int32_t ndp_version(void);
 int64_t ndp_param_count(const ndp_layer_cfg* cfg);
 /* Floats in the kernel-layout block of transposed weight copies ("pack"). */
 int64_t ndp_pack_count(const ndp_layer_cfg* cfg);
-/* Floats per point saved by the forward pass for the backward pass (activations + head vector). */
-int64_t ndp_saved_floats_per_point(const ndp_layer_cfg* cfg);
+/* Floats the forward pass saves for the backward pass of n points (activations + head vectors). */
+int64_t ndp_saved_floats(const ndp_layer_cfg* cfg, int64_t n);
+/* Where the hidden 128x128 layers run: 0 = tensor cores (tcgen05 / TMEM, operands split exactly into
+ * three bf16 terms, six partial products, fp32 accumulation: fp32-level accuracy) -- the default;
+ * 1 = FP32 pipes.  Process-wide; a solver captures the mode at creation. */
+int ndp_set_mlp_mode(int32_t mode);
+int32_t ndp_get_mlp_mode(void);
 /* Bytes of scratch ndp_layer_backward needs for n points. */
 int64_t ndp_backward_workspace_bytes(const ndp_layer_cfg* cfg, int64_t n);
 /* Bytes of scratch ndp_chamfer needs for clouds of n and m points. */
@@ -58,7 +63,7 @@ int64_t ndp_chamfer_workspace_bytes(int64_t n, int64_t m);
 int ndp_pack_params(const ndp_layer_cfg* cfg, const float* params, float* pack, void* stream);
 
 /* Kernel (1).  Replaces NDPLayer.forward (model/nets.py:111-140): x[n,3] -> y[n,3] and, when
- * cfg->nonrigidity, nu[n].  `saved` (n * ndp_saved_floats_per_point floats) may be NULL when no
+ * cfg->nonrigidity, nu[n].  `saved` (ndp_saved_floats(cfg, n) floats) may be NULL when no
  * backward pass follows (inference, registration.py:254-255).                                  */
 int ndp_layer_forward(const ndp_layer_cfg* cfg, const float* params, const float* pack,
                       const float* x, int64_t n, float* y, float* nu, float* saved, void* stream);
@@ -66,7 +71,7 @@ int ndp_layer_forward(const ndp_layer_cfg* cfg, const float* params, const float
 /* Kernel (3a)+(3b, reduction only).  Replaces the autograd backward of NDPLayer.forward
  * (loss.backward(), model/registration.py:236): given dL/dy[n,3] (and dL/dnu[n] or NULL) writes
  * dL/dparams (flat, parameters() order) and, if grad_x != NULL, dL/dx[n,3].                    */
-int ndp_layer_backward(const ndp_layer_cfg* cfg, const float* params, const float* x, int64_t n,
+int ndp_layer_backward(const ndp_layer_cfg* cfg, const float* params, const float* pack, const float* x, int64_t n,
                        const float* saved, const float* grad_y, const float* grad_nu,
                        float* grad_params, float* grad_x, void* workspace, void* stream);
 

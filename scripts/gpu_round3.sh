@@ -1,0 +1,17 @@
+#!/bin/bash
+OUT=gpurun_out; mkdir -p $OUT
+echo "== TC smoke (bounded)"; timeout 120 python __graft_entry__.py --smoke 2>&1 | tail -3
+echo "== pytest -m gpu"
+timeout 900 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?"
+grep -n "^E  \|Error\|^FAILED\|passed\|failed" $OUT/pytest_gpu.log | cut -c1-250 | head -30
+for MODE in 0 1; do
+  for P in 1 8 16; do
+    NDP_MLP_MODE=$MODE timeout 600 python bench.py --steps 1 --warmup 3 --pairs $P --no-cpu-baseline > $OUT/bench_mlp${MODE}_p$P.json 2> $OUT/bench_mlp${MODE}_p$P.err
+    python - <<PY
+import json
+try:
+    d=json.load(open("$OUT/bench_mlp${MODE}_p$P.json")); print("mlp_mode=$MODE pairs=$P value %.3f e2e %.3f"%(d["value"], d["e2e"]["value"]), {k: round(v,4) for k,v in d["kernel_ms_per_iteration"].items()})
+except Exception as e: print("mlp_mode=$MODE pairs=$P failed", e); print(open("$OUT/bench_mlp${MODE}_p$P.err").read()[-1500:])
+PY
+  done
+done

@@ -8,6 +8,7 @@ Barrier block_barrier;
 std::vector<Barrier*> warp_barriers;
 std::vector<uint64_t> warp_slots;
 unsigned char* dyn_smem_ptr = nullptr;
+float tmem[128][512];
 static size_t dyn_smem_cap = 0;
 
 void prepare(unsigned nthreads, size_t smem) {

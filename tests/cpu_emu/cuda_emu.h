@@ -20,6 +20,7 @@
 #include <functional>
 #include <mutex>
 #include <thread>
+#include <chrono>
 #include <vector>
 
 #define __global__
@@ -43,6 +44,7 @@ struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(8) int2 { int x, y; };
 struct alignas(16) int4 { int x, y, z, w; };
 struct alignas(8) uint2 { unsigned x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float3 make_float3(float x, float y, float z) { return float3{x, y, z}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }

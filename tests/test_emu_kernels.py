@@ -17,7 +17,7 @@ from emu_util import emu_lib
 from parity_cases import (check_layers_against_golden, check_chamfer_against_golden, check_adam,
                           check_trajectory_teacher_forced, check_solver_against_oracle,
                           check_chamfer_vs_oracle_random, check_culled_search_equals_brute_force,
-                          check_solver_repeatable)
+                          check_solver_repeatable, check_fp32_pipe_mode)
 
 
 @pytest.fixture(scope="module")
@@ -67,3 +67,7 @@ def test_culled_search_equals_brute_force(lib):
 
 def test_solver_repeatable_with_early_stop(lib):
     check_solver_repeatable(lib, "cpu")
+
+
+def test_fp32_pipe_mode(lib, golden_dir):
+    check_fp32_pipe_mode(lib, "cpu", golden_dir)

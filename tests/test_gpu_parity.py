@@ -11,7 +11,7 @@ from oracle import ndp_oracle as O
 from parity_cases import (REL_TOL, rel, check_layers_against_golden, check_chamfer_against_golden, check_adam,
                           check_trajectory_teacher_forced, check_solver_against_oracle,
                           check_chamfer_vs_oracle_random, check_culled_search_equals_brute_force,
-                          check_solver_repeatable)
+                          check_solver_repeatable, check_fp32_pipe_mode)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -141,3 +141,7 @@ def test_culled_search_equals_brute_force(lib):
 
 def test_solver_repeatable_with_early_stop(lib):
     check_solver_repeatable(lib, DEV)
+
+
+def test_fp32_pipe_mode(lib, golden_dir):
+    check_fp32_pipe_mode(lib, DEV, golden_dir)
