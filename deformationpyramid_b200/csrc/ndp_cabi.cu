@@ -603,3 +603,12 @@ extern "C" int ndp_solver_losses(ndp_solver* s, int32_t pair, float* out, void* 
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     return NDP_OK;
 }
+
+// Debug aid (not part of the public header): globaltimer stamps of CTA (0,0) of the last
+// tensor-core forward (which = 0) / backward (which = 1) launch; see NDP_T in the kernels.
+int ndp_debug_copy_fwd(unsigned long long* out);
+int ndp_debug_copy_bwd(unsigned long long* out);
+extern "C" int ndp_debug_phase_times(int which, unsigned long long* out) {
+    cudaDeviceSynchronize();
+    return which ? ndp_debug_copy_bwd(out) : ndp_debug_copy_fwd(out);
+}

@@ -95,12 +95,16 @@ NDP_HD void ndp_rot_backward(int rot, const float* a, const float* G, float* ga)
                        w0 * w1, -(w0 * w0 + w2 * w2), w1 * w2,
                        w0 * w2, w1 * w2, -(w0 * w0 + w1 * w1)};
         float gth = 0.0f;
+#pragma unroll
         for (int e = 0; e < 9; ++e) gth += G[e] * (c * K[e] + s * K2[e]);
         // dL/dK = s G + v (G K^T + K^T G)
         float gK[9];
+#pragma unroll
         for (int r = 0; r < 3; ++r)
+#pragma unroll
             for (int q = 0; q < 3; ++q) {
                 float t = 0.0f;
+#pragma unroll
                 for (int m = 0; m < 3; ++m) t += G[r * 3 + m] * K[q * 3 + m] + K[m * 3 + r] * G[m * 3 + q];
                 gK[r * 3 + q] = s * G[r * 3 + q] + v * t;
             }
@@ -116,17 +120,20 @@ NDP_HD void ndp_rot_backward(int rot, const float* a, const float* G, float* ga)
         // A = Ry Rz
         float A[9] = {cy * cz, -cy * sz, sy, sz, cz, 0.0f, -sy * cz, sy * sz, cy};
         float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
+#pragma unroll
         for (int q = 0; q < 3; ++q) {
             g0 += G[3 + q] * (-sx * A[3 + q] - cx * A[6 + q]) + G[6 + q] * (cx * A[3 + q] - sx * A[6 + q]);
         }
         // dR/da1 = Rx Ry' Rz ; Ry' = [[-sy,0,cy],[0,0,0],[-cy,0,-sy]];  B = Ry' Rz
         float B[9] = {-sy * cz, sy * sz, cy, 0.0f, 0.0f, 0.0f, -cy * cz, cy * sz, -sy};
         // Rx B: row0 = B row0; row1 = cx*Brow1 - sx*Brow2 ; row2 = sx*Brow1 + cx*Brow2
+#pragma unroll
         for (int q = 0; q < 3; ++q) {
             g1 += G[q] * B[q] + G[3 + q] * (-sx * B[6 + q]) + G[6 + q] * (cx * B[6 + q]);
         }
         // dR/da2 = (Rx Ry) Rz' ; Rz' = [[-sz,-cz,0],[cz,-sz,0],[0,0,0]];  C = Rx Ry
         float C[9] = {cy, 0.0f, sy, sx * sy, cx, -sx * cy, -cx * sy, sx, cx * cy};
+#pragma unroll
         for (int r = 0; r < 3; ++r) {
             float d0 = C[r * 3 + 0] * (-sz) + C[r * 3 + 1] * cz;
             float d1 = C[r * 3 + 0] * (-cz) + C[r * 3 + 1] * (-sz);
@@ -144,6 +151,7 @@ NDP_HD void ndp_rot_backward(int rot, const float* a, const float* G, float* ga)
                       i * j + k * r, -(i * i + k * k), j * k - i * r,
                       i * k - j * r, j * k + i * r, -(i * i + j * j)};
         float gts = 0.0f;
+#pragma unroll
         for (int e = 0; e < 9; ++e) gts += G[e] * P[e];
         float gPr = -k * G[1] + j * G[2] + k * G[3] - i * G[5] - j * G[6] + i * G[7];
         float gPi = j * (G[1] + G[3]) + k * (G[2] + G[6]) - 2.0f * i * (G[4] + G[8]) + r * (G[7] - G[5]);
@@ -176,21 +184,26 @@ NDP_HD void ndp_rot_backward(int rot, const float* a, const float* G, float* ga)
         float gu[3];
         if (m2 > 1e-12f) {
             float t = gb2[0] * b2[0] + gb2[1] * b2[1] + gb2[2] * b2[2];
+#pragma unroll
             for (int e = 0; e < 3; ++e) gu[e] = (gb2[e] - t * b2[e]) / n2;
         } else {
+#pragma unroll
             for (int e = 0; e < 3; ++e) gu[e] = gb2[e] / n2;
         }
         // u = a2 - d b1 ; d = b1 . a2
         float gd = -(gu[0] * b1[0] + gu[1] * b1[1] + gu[2] * b1[2]);
         float ga2[3];
+#pragma unroll
         for (int e = 0; e < 3; ++e) {
             ga2[e] = gu[e] + gd * b1[e];
             gb1[e] += -d * gu[e] + gd * a[3 + e];
         }
         if (m1 > 1e-12f) {
             float t = gb1[0] * b1[0] + gb1[1] * b1[1] + gb1[2] * b1[2];
+#pragma unroll
             for (int e = 0; e < 3; ++e) ga[e] = (gb1[e] - t * b1[e]) / n1;
         } else {
+#pragma unroll
             for (int e = 0; e < 3; ++e) ga[e] = gb1[e] / n1;
         }
         ga[3] = ga2[0]; ga[4] = ga2[1]; ga[5] = ga2[2];
@@ -261,6 +274,7 @@ NDP_HD void ndp_point_backward(int motion, int rot, int nonrigid, const float* z
         float v = ndp_sigmoid(z[h.nr]);
         float gv = gnu + gy[0] * (y[0] - x[0]) + gy[1] * (y[1] - x[1]) + gy[2] * (y[2] - x[2]);
         gz[h.nr] = gv * v * (1.0f - v);
+#pragma unroll
         for (int e = 0; e < 3; ++e) { gx[e] += (1.0f - v) * gy[e]; gy[e] *= v; }
     }
     gz[h.t] = gy[0]; gz[h.t + 1] = gy[1]; gz[h.t + 2] = gy[2];
@@ -270,7 +284,9 @@ NDP_HD void ndp_point_backward(int motion, int rot, int nonrigid, const float* z
     }
     if (motion == NDP_MOTION_SIM3) gz[h.s] = gy[0] * rx[0] + gy[1] * rx[1] + gy[2] * rx[2];
     float G[9];
+#pragma unroll
     for (int r = 0; r < 3; ++r)
+#pragma unroll
         for (int q = 0; q < 3; ++q) G[r * 3 + q] = s * gy[r] * x[q];
     ndp_rot_backward(rot, z + h.rot, G, gz + h.rot);
     gx[0] += s * (R[0] * gy[0] + R[3] * gy[1] + R[6] * gy[2]);

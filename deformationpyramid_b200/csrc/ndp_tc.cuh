@@ -45,18 +45,49 @@ __device__ __forceinline__ void ndp_split3(float x, unsigned& h1, unsigned& h2, 
     h3 = ndp_bf16_rn(r2);
 }
 
+// two fp32 -> packed bf16x2 (round to nearest even): ONE instruction on sm_100a (F2FP.BF16.PACK_AB)
+#ifdef NDP_EMU
+static inline unsigned ndp_pack2_bf16(float lo, float hi) { return (ndp_bf16_rn(hi) << 16) | (ndp_bf16_rn(lo) & 0xffffu); }
+#else
+__device__ __forceinline__ unsigned ndp_pack2_bf16(float lo, float hi) {
+    unsigned d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+#endif
+
+// exact 3-way split of a pair of values into three packed bf16x2 words (hi, mid, lo parts)
+__device__ __forceinline__ void ndp_split3_pair(float x0, float x1, unsigned& w1, unsigned& w2, unsigned& w3) {
+    w1 = ndp_pack2_bf16(x0, x1);
+    const float r0 = x0 - __uint_as_float(w1 << 16), r1 = x1 - __uint_as_float(w1 & 0xffff0000u);
+    w2 = ndp_pack2_bf16(r0, r1);
+    const float s0 = r0 - __uint_as_float(w2 << 16), s1 = r1 - __uint_as_float(w2 & 0xffff0000u);
+    w3 = ndp_pack2_bf16(s0, s1);
+}
+
 // split 8 consecutive values and store them as one 16-byte chunk in each of the three images
 __device__ __forceinline__ void ndp_store_chunk3(unsigned char* tri, unsigned img_bytes, unsigned off, const float (&v)[8]) {
-    unsigned a[8], b[8], c[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) ndp_split3(v[j], a[j], b[j], c[j]);
     uint4 p0, p1, p2;
-    p0.x = a[0] | (a[1] << 16); p0.y = a[2] | (a[3] << 16); p0.z = a[4] | (a[5] << 16); p0.w = a[6] | (a[7] << 16);
-    p1.x = b[0] | (b[1] << 16); p1.y = b[2] | (b[3] << 16); p1.z = b[4] | (b[5] << 16); p1.w = b[6] | (b[7] << 16);
-    p2.x = c[0] | (c[1] << 16); p2.y = c[2] | (c[3] << 16); p2.z = c[4] | (c[5] << 16); p2.w = c[6] | (c[7] << 16);
+    ndp_split3_pair(v[0], v[1], p0.x, p1.x, p2.x);
+    ndp_split3_pair(v[2], v[3], p0.y, p1.y, p2.y);
+    ndp_split3_pair(v[4], v[5], p0.z, p1.z, p2.z);
+    ndp_split3_pair(v[6], v[7], p0.w, p1.w, p2.w);
     *(uint4*)(tri + off) = p0;
     *(uint4*)(tri + img_bytes + off) = p1;
     *(uint4*)(tri + 2 * img_bytes + off) = p2;
+}
+
+// bit j of the result: element j (0..7) of a 16-byte bf16 chunk is > 0  (relu' of a saved activation)
+__device__ __forceinline__ unsigned ndp_pos_mask8(const uint4& q) {
+    const unsigned w[4] = {q.x, q.y, q.z, q.w};
+    unsigned m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const unsigned lo = w[k] & 0xffffu, hi = w[k] >> 16;
+        m |= ((lo - 1u) < 0x7fffu ? 1u : 0u) << (2 * k);          // 0x0001 .. 0x7fff: positive, non-zero
+        m |= ((hi - 1u) < 0x7fffu ? 1u : 0u) << (2 * k + 1);
+    }
+    return m;
 }
 
 // instruction descriptor: D = f32, A = B = bf16, M x N tile, operand majors (0 = K-major, 1 = MN-major)
@@ -163,13 +194,43 @@ static inline void ndp_tmem_alloc_warp(unsigned* slot, int n) { ndp_tmem_alloc(s
 // One fp32-accurate product D[128 x N] (+)= A . B over K = 16 * ksteps from tri-images:
 // the six bf16 partial products, issued by ONE thread.  a_step / b_step: descriptor byte advance
 // per 16-deep k-step; a_img / b_img: byte distance between the hi / mid / lo images.
-__device__ __forceinline__ void ndp_umma_gemm6(unsigned tmem_d, NdpUmmaDesc a0, unsigned a_img, unsigned a_step,
-                                               NdpUmmaDesc b0, unsigned b_img, unsigned b_step, int ksteps,
-                                               unsigned idesc, bool accumulate) {
+// Same with nb = 1: only the hi image of B (for operands that are exact in bf16, e.g. a column of ones).
+#ifdef NDP_EMU
+static inline
+#else
+static __device__ __noinline__
+#endif
+void ndp_umma_gemm_a3(unsigned tmem_d, NdpUmmaDesc a0, unsigned a_img, unsigned a_step, NdpUmmaDesc b0, unsigned b_step,
+                      int ksteps, unsigned idesc) {
+    unsigned acc = 0u;
+#pragma unroll 1
+    for (int i = 0; i < 3; ++i) {
+        NdpUmmaDesc da = ndp_umma_desc_adv(a0, i * a_img), db = b0;
+#pragma unroll 1
+        for (int ks = 0; ks < ksteps; ++ks) {
+            ndp_umma_bf16(tmem_d, da, db, idesc, acc);
+            acc = 1u;
+            da = ndp_umma_desc_adv(da, a_step);
+            db = ndp_umma_desc_adv(db, b_step);
+        }
+    }
+}
+
+#ifdef NDP_EMU
+static inline
+#else
+static __device__ __noinline__
+#endif
+void ndp_umma_gemm6(unsigned tmem_d, NdpUmmaDesc a0, unsigned a_img, unsigned a_step,
+                    NdpUmmaDesc b0, unsigned b_img, unsigned b_step, int ksteps,
+                    unsigned idesc, bool accumulate) {
     unsigned acc = accumulate ? 1u : 0u;
+#pragma unroll 1
     for (int i = 0; i < 3; ++i)
+#pragma unroll 1
         for (int j = 0; i + j < 3; ++j) {
             NdpUmmaDesc da = ndp_umma_desc_adv(a0, i * a_img), db = ndp_umma_desc_adv(b0, j * b_img);
+#pragma unroll 1
             for (int ks = 0; ks < ksteps; ++ks) {
                 ndp_umma_bf16(tmem_d, da, db, idesc, acc);
                 acc = 1u;

@@ -20,19 +20,27 @@
 #include "ndp_kernels.h"
 #include "ndp_tc.cuh"
 
+// optional phase timestamps of CTA (0,0) (debug aid, read back through ndp_debug_phase_times)
+#ifndef NDP_EMU
+__device__ unsigned long long ndp_dbg_bwd[64];
+#define NDP_T(i) do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ndp_dbg_bwd[i] = t_; } } while (0)
+#else
+#define NDP_T(i) do {} while (0)
+#endif
+
 #define NDP_IMG16 NDP_IMG_BYTES(16)     // [128][16] bf16 image: 4096 bytes
 struct BwdTcSmem {
-    unsigned char D[NDP_TRI128];        // delta tri-image (hosts the head-gradient image first)
+    unsigned char D[NDP_TRI128];        // delta tri-image
     unsigned char X[NDP_TRI128];        // h_l tri-image, then W_l tri-image
+    unsigned char HG[3 * NDP_IMG16];    // [128 points][16]: mlp_scale * dL/dz (head gradients); must precede E:
     unsigned char E[3 * NDP_IMG16];     // [128 points][16]: cols 0..5 positional encoding, col 6 = 1
-    float hw[NDP_MAX_HEAD * NDP_W];
-    float hg[NDP_TP * NDP_ZPITCH];      // mlp_scale * dL/dz
+    float hw[NDP_MAX_HEAD * NDP_W];     // head weights (fp32), rows >= head_dim zero
     float xs[NDP_TP * 4];
     float gxs[NDP_TP * 4];
     NdpMbar bar_x, bar_mma;
     unsigned tmem_slot, pad[3];
 };
-size_t ndp_bwd_tc_smem_bytes() { return sizeof(BwdTcSmem) + 1024; }
+size_t ndp_bwd_tc_smem_bytes() { return sizeof(BwdTcSmem) + 128; }
 
 #define TM_DW 0u
 #define TM_DH 128u
@@ -40,7 +48,7 @@ size_t ndp_bwd_tc_smem_bytes() { return sizeof(BwdTcSmem) + 1024; }
 
 __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdArgs a) {
     NDP_DYN_SMEM(smem_raw);
-    BwdTcSmem& S = *(BwdTcSmem*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    BwdTcSmem& S = *(BwdTcSmem*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
 
     const int tid = threadIdx.x, pair = blockIdx.y, tile = blockIdx.x;
     const int n = a.counts ? a.counts[pair] : a.n;
@@ -54,18 +62,21 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
                                 (long long)tile * (LH + 1) * NDP_TRI128;
     float* part = a.partials + (long long)pair * a.partials_stride + (long long)tile * a.partial_pitch;
     const int warp = tid >> 5, lane = tid & 31, p = tid & (NDP_TP - 1), half = tid >> 7;
-    const int RS = NDP_IMG_RS(128), CS = NDP_IMG_CS;
+    const int RS = NDP_IMG_RS(128), CS = NDP_IMG_CS, RS16 = NDP_IMG_RS(16);
     unsigned xph = 0, mph = 0;
+    NDP_T(0);
 
     if (warp == 0) ndp_tmem_alloc_warp(&S.tmem_slot, 512);
     if (tid == 0) { ndp_mbar_init(&S.bar_x, 1); ndp_mbar_init(&S.bar_mma, 1); }
-    for (int i = tid; i < HD * NDP_W; i += NDP_THREADS) S.hw[i] = __ldg(params + L.head_w[i >> 7] + (i & 127));
+    for (int i = tid; i < NDP_MAX_HEAD * NDP_W; i += NDP_THREADS)
+        S.hw[i] = ((i >> 7) < HD) ? __ldg(params + L.head_w[i >> 7] + (i & 127)) : 0.0f;
     ndp_tc_fence_before();
     __syncthreads();
     ndp_tc_fence_after();
+    NDP_T(1);
     const unsigned tmem = S.tmem_slot;
     const unsigned tlane = tmem + ((unsigned)((warp & 3) * 32) << 16);
-    if (tid == 0) ndp_stage_bulk(S.X, gact + (long long)LH * NDP_TRI128, NDP_TRI128, &S.bar_x);
+    if (tid == 0) ndp_stage_bulk(S.X, gact + (long long)LH * NDP_TRI128, NDP_TRI128, &S.bar_x);      // h_L
 
     // ---- per point: dL/dy -> dL/dz (heads) and the direct part of dL/dx; E and head-gradient images
     if (tid < NDP_TP) {
@@ -91,9 +102,10 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
                 ga[0] = 0ull; ga[1] = 0ull; ga[2] = 0ull;
             }
             float z[NDP_MAX_HEAD];
-            const float* zp = a.zsave + (long long)pair * a.z_stride + (long long)gp * NDP_ZPITCH;
-#pragma unroll
-            for (int r = 0; r < NDP_MAX_HEAD; ++r) z[r] = zp[r];
+            const float4* zp = (const float4*)(a.zsave + (long long)pair * a.z_stride + (long long)gp * NDP_ZPITCH);
+            const float4 z0 = zp[0], z1 = zp[1], z2 = zp[2];
+            z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; z[4] = z1.x; z[5] = z1.y; z[6] = z1.z; z[7] = z1.w;
+            z[8] = z2.x; z[9] = z2.y; z[10] = z2.z; z[11] = z2.w;
             const float gnu = (a.gnu && L.nonrigid) ? a.gnu[(long long)pair * a.gnu_stride + gp] : 0.0f;
             ndp_point_backward(L.motion, L.rot, L.nonrigid, z, x, gy, gnu, gz, gxd);
         }
@@ -101,13 +113,12 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
 #pragma unroll
         for (int r = 0; r < NDP_MAX_HEAD; ++r) {
             const float g = L.mu * gz[r];
-            S.hg[tid * NDP_ZPITCH + r] = g;
             if (r < 8) v0[r] = g; else v1[r - 8] = g;
         }
 #pragma unroll
         for (int r = NDP_MAX_HEAD - 8; r < 8; ++r) v1[r] = 0.0f;
-        ndp_store_chunk3(S.D, NDP_IMG128, ndp_img_off(tid, 0, RS), v0);     // head-gradient image, cols 0..15
-        ndp_store_chunk3(S.D, NDP_IMG128, ndp_img_off(tid, 8, RS), v1);
+        ndp_store_chunk3(S.HG, NDP_IMG16, ndp_img_off(tid, 0, RS16), v0);
+        ndp_store_chunk3(S.HG, NDP_IMG16, ndp_img_off(tid, 8, RS16), v1);
         S.xs[tid * 4 + 0] = x[0]; S.xs[tid * 4 + 1] = x[1]; S.xs[tid * 4 + 2] = x[2];
         S.gxs[tid * 4 + 0] = gxd[0]; S.gxs[tid * 4 + 1] = gxd[1]; S.gxs[tid * 4 + 2] = gxd[2];
         float e0[8], e1[8], s, c;
@@ -117,56 +128,78 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
         e0[6] = 1.0f; e0[7] = 0.0f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) e1[j] = 0.0f;
-        ndp_store_chunk3(S.E, NDP_IMG16, ndp_img_off(tid, 0, NDP_IMG_RS(16)), e0);
-        ndp_store_chunk3(S.E, NDP_IMG16, ndp_img_off(tid, 8, NDP_IMG_RS(16)), e1);
+        ndp_store_chunk3(S.E, NDP_IMG16, ndp_img_off(tid, 0, RS16), e0);
+        ndp_store_chunk3(S.E, NDP_IMG16, ndp_img_off(tid, 8, RS16), e1);
     }
     ndp_fence_proxy_async();
     __syncthreads();
+    NDP_T(2);
 
     const unsigned id_nn = ndp_idesc_bf16(128, 128, 1, 1), id_sm = ndp_idesc_bf16(128, 16, 1, 1), id_kn = ndp_idesc_bf16(128, 128, 0, 1);
-    // ---- head gradients: dW_h = hg^T h_L (rows >= head_dim of the result are never read), db_h = hg^T 1
+    const NdpUmmaDesc dD_mn = ndp_umma_desc(S.D, RS, CS), dD_k = ndp_umma_desc(S.D, CS, RS), dX_mn = ndp_umma_desc(S.X, RS, CS);
+    const NdpUmmaDesc dE = ndp_umma_desc(S.E, RS16, CS), dHG = ndp_umma_desc(S.HG, RS16, CS);
+    // ---- head gradients: dW_h = hg^T h_L, db_h = hg^T 1.  The [128][16] head-gradient image is read as
+    //      a 128-row MN-major operand: rows >= 16 of the result are other rows' data and are never read.
     ndp_mbar_wait(&S.bar_x, xph); xph ^= 1;
+    NDP_T(3);
     if (tid == 0) {
         ndp_tc_fence_after();
-        ndp_umma_gemm6(tmem + TM_DH, ndp_umma_desc(S.D, RS, CS), NDP_IMG128, 2 * RS,
-                       ndp_umma_desc(S.X, RS, CS), NDP_IMG128, 2 * RS, 8, id_nn, false);
-        ndp_umma_gemm6(tmem + TM_SM, ndp_umma_desc(S.D, RS, CS), NDP_IMG128, 2 * RS,
-                       ndp_umma_desc(S.E, NDP_IMG_RS(16), CS), NDP_IMG16, 2 * NDP_IMG_RS(16), 8, id_sm, false);
+        ndp_umma_gemm6(tmem + TM_DH, dHG, NDP_IMG16, 2 * RS16, dX_mn, NDP_IMG128, 2 * RS, 8, id_nn, false);
+        ndp_umma_gemm_a3(tmem + TM_SM, dHG, NDP_IMG16, 2 * RS16, dE, 2 * RS16, 8, id_sm);
         ndp_umma_commit(&S.bar_mma);
     }
-    // ---- delta at the top activation, in registers while the head GEMMs run: (W_h^T hg) . relu'(h_L)
-    float dt[64];
+    // ---- delta at the top activation straight into the delta image while the head GEMMs run:
+    //      (W_h^T hg) . relu'(h_L)
     {
-        float g[NDP_MAX_HEAD];
+        // this row's head gradients, re-assembled from the three bf16 parts of the image
+        float g[16];
 #pragma unroll
-        for (int r = 0; r < NDP_MAX_HEAD; ++r) g[r] = (r < HD) ? S.hg[p * NDP_ZPITCH + r] : 0.0f;
+        for (int c8 = 0; c8 < 2; ++c8) {
+            const unsigned off = ndp_img_off(p, c8 * 8, RS16);
+            const uint4 q0 = *(const uint4*)(S.HG + off), q1 = *(const uint4*)(S.HG + NDP_IMG16 + off), q2 = *(const uint4*)(S.HG + 2 * NDP_IMG16 + off);
+            const unsigned w0[4] = {q0.x, q0.y, q0.z, q0.w}, w1[4] = {q1.x, q1.y, q1.z, q1.w}, w2[4] = {q2.x, q2.y, q2.z, q2.w};
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-            const int o0 = half * 64 + ch * 8;
-            const uint4 hq = *(const uint4*)(S.X + ndp_img_off(p, o0, RS));       // hi parts of h_L: sign/zero test
-            const unsigned hh[4] = {hq.x, hq.y, hq.z, hq.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float s = 0.0f;
-#pragma unroll
-                for (int r = 0; r < NDP_MAX_HEAD; ++r) s = fmaf(g[r], (r < HD) ? S.hw[r * NDP_W + o0 + j] : 0.0f, s);
-                const unsigned hb = (hh[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
-                const bool pos = ((hb & 0x8000u) == 0u) && ((hb & 0x7fffu) != 0u);
-                dt[ch * 8 + j] = pos ? s : 0.0f;
+            for (int k = 0; k < 4; ++k) {
+                g[c8 * 8 + 2 * k] = __uint_as_float(w0[k] << 16) + __uint_as_float(w1[k] << 16) + __uint_as_float(w2[k] << 16);
+                g[c8 * 8 + 2 * k + 1] = __uint_as_float(w0[k] & 0xffff0000u) + __uint_as_float(w1[k] & 0xffff0000u) + __uint_as_float(w2[k] & 0xffff0000u);
             }
         }
+#pragma unroll 1
+        for (int ch = 0; ch < 8; ++ch) {
+            const int o0 = half * 64 + ch * 8;
+            const unsigned pm = ndp_pos_mask8(*(const uint4*)(S.X + ndp_img_off(p, o0, RS)));
+            float u[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j] = 0.0f;
+#pragma unroll
+            for (int r = 0; r < NDP_MAX_HEAD; ++r) {     // rows >= head_dim of hw are zero
+                const float4 wa = *(const float4*)(S.hw + r * NDP_W + o0), wb = *(const float4*)(S.hw + r * NDP_W + o0 + 4);
+                u[0] = fmaf(g[r], wa.x, u[0]); u[1] = fmaf(g[r], wa.y, u[1]); u[2] = fmaf(g[r], wa.z, u[2]); u[3] = fmaf(g[r], wa.w, u[3]);
+                u[4] = fmaf(g[r], wb.x, u[4]); u[5] = fmaf(g[r], wb.y, u[5]); u[6] = fmaf(g[r], wb.z, u[6]); u[7] = fmaf(g[r], wb.w, u[7]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j] = ((pm >> j) & 1u) ? u[j] : 0.0f;
+            ndp_store_chunk3(S.D, NDP_IMG128, ndp_img_off(p, o0, RS), u);
+        }
     }
+    NDP_T(4);
     ndp_mbar_wait(&S.bar_mma, mph); mph ^= 1;
     ndp_tc_fence_after();
+    NDP_T(5);
+    ndp_fence_proxy_async();
+    __syncthreads();            // every thread is done with h_L (relu' masks) and delta_top is complete
+    if (tid == 0 && LH > 0) ndp_stage_bulk(S.X, gact + (long long)(LH - 1) * NDP_TRI128, NDP_TRI128, &S.bar_x);
     if ((warp & 3) == 0) {      // TMEM lanes 0..31 hold the head rows
 #pragma unroll 1
         for (int c32 = 0; c32 < 2; ++c32) {
             float v[32];
             const int col0 = half * 64 + c32 * 32;
             ndp_tmem_ld32(tlane + TM_DH + col0, v);
-            if (lane < HD)
+            if (lane < HD) {
+                float* dst = part + L.head_w[lane] + col0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) part[L.head_w[lane] + col0 + j] = v[j];
+                for (int j = 0; j < 32; ++j) dst[j] = v[j];
+            }
         }
         if (half == 0) {
             float v[32];
@@ -174,47 +207,32 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
             if (lane < HD) part[L.head_b[lane]] = v[6];
         }
     }
-    // delta_top replaces the head-gradient image
-#pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-        float u[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) u[j] = dt[ch * 8 + j];
-        ndp_store_chunk3(S.D, NDP_IMG128, ndp_img_off(p, half * 64 + ch * 8, RS), u);
-    }
     ndp_tc_fence_before();
-    ndp_fence_proxy_async();
     __syncthreads();
     ndp_tc_fence_after();
+    NDP_T(6);
 
     for (int l = LH - 1; l >= 0; --l) {
-        if (tid == 0) ndp_stage_bulk(S.X, gact + (long long)l * NDP_TRI128, NDP_TRI128, &S.bar_x);     // h_l
-        ndp_mbar_wait(&S.bar_x, xph); xph ^= 1;
-        // relu' mask of h_l (hi part > 0) for this thread's row / column half, before W_l replaces h_l
-        unsigned mask[2] = {0u, 0u};
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-            const uint4 hq = *(const uint4*)(S.X + ndp_img_off(p, half * 64 + ch * 8, RS));
-            const unsigned hh[4] = {hq.x, hq.y, hq.z, hq.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const unsigned hb = (hh[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
-                const bool pos = ((hb & 0x8000u) == 0u) && ((hb & 0x7fffu) != 0u);
-                mask[ch >> 2] |= (pos ? 1u : 0u) << ((ch & 3) * 8 + j);
-            }
-        }
-        __syncthreads();
+        const int tb = 8 + 8 * (LH - 1 - l);
+        ndp_mbar_wait(&S.bar_x, xph); xph ^= 1;        // h_l (requested before the previous epilogue)
+        NDP_T(tb + 0);
         if (tid == 0) {
             ndp_tc_fence_after();
-            // dW_l[o][i] = sum_p delta[p][o] h_l[p][i];  db_l[o] = sum_p delta[p][o]
-            ndp_umma_gemm6(tmem + TM_DW, ndp_umma_desc(S.D, RS, CS), NDP_IMG128, 2 * RS,
-                           ndp_umma_desc(S.X, RS, CS), NDP_IMG128, 2 * RS, 8, id_nn, false);
-            ndp_umma_gemm6(tmem + TM_SM, ndp_umma_desc(S.D, RS, CS), NDP_IMG128, 2 * RS,
-                           ndp_umma_desc(S.E, NDP_IMG_RS(16), CS), NDP_IMG16, 2 * NDP_IMG_RS(16), 8, id_sm, false);
+            // dW_l[o][i] = sum_p delta[p][o] h_l[p][i];  db_l[o] = sum_p delta[p][o] (ones column of E)
+            ndp_umma_gemm6(tmem + TM_DW, dD_mn, NDP_IMG128, 2 * RS, dX_mn, NDP_IMG128, 2 * RS, 8, id_nn, false);
+            ndp_umma_gemm_a3(tmem + TM_SM, dD_mn, NDP_IMG128, 2 * RS, dE, 2 * RS16, 8, id_sm);
             ndp_umma_commit(&S.bar_mma);
         }
+        // relu' mask of h_l for this thread's row / column half, before W_l replaces h_l
+        unsigned mask[2] = {0u, 0u};
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+            mask[ch >> 2] |= ndp_pos_mask8(*(const uint4*)(S.X + ndp_img_off(p, half * 64 + ch * 8, RS))) << ((ch & 3) * 8);
+        NDP_T(tb + 1);
         ndp_mbar_wait(&S.bar_mma, mph); mph ^= 1;
         ndp_tc_fence_after();
+        __syncthreads();        // all masks extracted: h_l may be overwritten
+        NDP_T(tb + 2);
         if (tid == 0) ndp_stage_bulk(S.X, wimg + (long long)l * NDP_TRI128, NDP_TRI128, &S.bar_x);     // W_l over h_l
         // dW epilogue: TMEM -> this tile's partial row (thread = output row o, 64 input columns)
         {
@@ -234,27 +252,31 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
                 part[L.off_b[l] + o] = v[6];
             }
         }
+        NDP_T(tb + 3);
         ndp_mbar_wait(&S.bar_x, xph); xph ^= 1;
+        NDP_T(tb + 4);
         if (tid == 0) {
             ndp_tc_fence_after();
             // delta_l[p][i] = sum_o delta[p][o] W_l[o][i]
-            ndp_umma_gemm6(tmem + TM_DH, ndp_umma_desc(S.D, CS, RS), NDP_IMG128, 2 * CS,
-                           ndp_umma_desc(S.X, RS, CS), NDP_IMG128, 2 * RS, 8, id_kn, false);
+            ndp_umma_gemm6(tmem + TM_DH, dD_k, NDP_IMG128, 2 * CS, dX_mn, NDP_IMG128, 2 * RS, 8, id_kn, false);
             ndp_umma_commit(&S.bar_mma);
         }
         ndp_mbar_wait(&S.bar_mma, mph); mph ^= 1;
         ndp_tc_fence_after();
+        NDP_T(tb + 5);
+        if (tid == 0 && l > 0) ndp_stage_bulk(S.X, gact + (long long)(l - 1) * NDP_TRI128, NDP_TRI128, &S.bar_x);   // h_{l-1} over W_l
         // dH epilogue: relu' mask, re-split, delta image updated in place
 #pragma unroll 1
         for (int c32 = 0; c32 < 2; ++c32) {
             float v[32];
             const int col0 = half * 64 + c32 * 32;
             ndp_tmem_ld32(tlane + TM_DH + col0, v);
+            const unsigned mk = mask[c32];
 #pragma unroll
             for (int s8 = 0; s8 < 4; ++s8) {
                 float u[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) u[j] = ((mask[c32] >> (s8 * 8 + j)) & 1u) ? v[s8 * 8 + j] : 0.0f;
+                for (int j = 0; j < 8; ++j) u[j] = ((mk >> (s8 * 8 + j)) & 1u) ? v[s8 * 8 + j] : 0.0f;
                 ndp_store_chunk3(S.D, NDP_IMG128, ndp_img_off(p, col0 + s8 * 8, RS), u);
             }
         }
@@ -262,12 +284,12 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
         ndp_fence_proxy_async();
         __syncthreads();
         ndp_tc_fence_after();
+        NDP_T(tb + 6);
     }
 
     // ---- input layer: [dW_in | db_in][o][0..6] = sum_p delta_0[p][o] E[p][0..6]
     if (tid == 0) {
-        ndp_umma_gemm6(tmem + TM_SM, ndp_umma_desc(S.D, RS, CS), NDP_IMG128, 2 * RS,
-                       ndp_umma_desc(S.E, NDP_IMG_RS(16), CS), NDP_IMG16, 2 * NDP_IMG_RS(16), 8, id_sm, false);
+        ndp_umma_gemm6(tmem + TM_SM, dD_mn, NDP_IMG128, 2 * RS, dE, NDP_IMG16, 2 * RS16, 8, id_sm, false);
         ndp_umma_commit(&S.bar_mma);
     }
     ndp_mbar_wait(&S.bar_mma, mph); mph ^= 1;
@@ -309,8 +331,10 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
             }
         }
     }
+    NDP_T(62);
     ndp_tc_fence_before();
     __syncthreads();
+    NDP_T(63);
     if (warp == 0) ndp_tmem_dealloc(tmem, 512);
 }
 
@@ -324,3 +348,9 @@ int ndp_bwd_tc_init() {
     return (int)cudaFuncSetAttribute(ndp_warp_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)ndp_bwd_tc_smem_bytes());
 }
+
+#ifndef NDP_EMU
+int ndp_debug_copy_bwd(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, ndp_dbg_bwd, sizeof(unsigned long long) * 64); }
+#else
+int ndp_debug_copy_bwd(unsigned long long* out) { for (int i = 0; i < 64; ++i) out[i] = 0; return 0; }
+#endif

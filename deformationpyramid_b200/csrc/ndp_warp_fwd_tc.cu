@@ -16,6 +16,14 @@
 #include "ndp_kernels.h"
 #include "ndp_tc.cuh"
 
+// optional phase timestamps of CTA (0,0) (debug aid, read back through ndp_debug_phase_times)
+#ifndef NDP_EMU
+__device__ unsigned long long ndp_dbg_fwd[64];
+#define NDP_T(i) do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ndp_dbg_fwd[i] = t_; } } while (0)
+#else
+#define NDP_T(i) do {} while (0)
+#endif
+
 struct FwdTcSmem {
     unsigned char A[NDP_TRI128];              // activation tri-image (operand A, K-major)
     unsigned char B[NDP_TRI128];              // weight tri-image of the current layer (operand B, K-major)
@@ -60,6 +68,7 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_fwd_tc_kernel(NdpFwdA
     unsigned char* gact = a.act ? (unsigned char*)a.act + ((long long)pair * a.act_stride) * 4 +
                                       (long long)tile * (LH + 1) * NDP_TRI128 : nullptr;
 
+    NDP_T(0);
     if (warp == 0) ndp_tmem_alloc_warp(&S.tmem_slot, 128);
     if (tid == 0) { ndp_mbar_init(&S.bar_w, 1); ndp_mbar_init(&S.bar_mma, 1); }
     // stage the small fp32 operands
@@ -84,6 +93,7 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_fwd_tc_kernel(NdpFwdA
     ndp_tc_fence_before();
     __syncthreads();
     ndp_tc_fence_after();
+    NDP_T(1);
     const unsigned tmem = S.tmem_slot;
     if (tid == 0 && LH > 0) ndp_stage_bulk(S.B, wimg, NDP_TRI128, &S.bar_w);
 
@@ -114,6 +124,7 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_fwd_tc_kernel(NdpFwdA
     }
     ndp_fence_proxy_async();
     __syncthreads();
+    NDP_T(2);
 
     const unsigned idesc = ndp_idesc_bf16(128, 128, 0, 0);
     for (int l = 0; l < LH; ++l) {
@@ -124,6 +135,7 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_fwd_tc_kernel(NdpFwdA
                 ndp_bulk_commit();
             }
             ndp_mbar_wait(&S.bar_w, (unsigned)(l & 1));
+            NDP_T(8 + 4 * l);
             ndp_tc_fence_after();
             ndp_umma_gemm6(tmem, ndp_umma_desc(S.A, NDP_IMG_CS, NDP_IMG_RS(128)), NDP_IMG128, 2 * NDP_IMG_CS,
                            ndp_umma_desc(S.B, NDP_IMG_CS, NDP_IMG_RS(128)), NDP_IMG128, 2 * NDP_IMG_CS, 8, idesc, false);
@@ -131,11 +143,13 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_fwd_tc_kernel(NdpFwdA
         }
         ndp_mbar_wait(&S.bar_mma, (unsigned)(l & 1));
         ndp_tc_fence_after();
+        NDP_T(9 + 4 * l);
         if (tid == 0) {
             if (gact) ndp_bulk_wait_read0();                      // the store has finished reading A
             if (l + 1 < LH) ndp_stage_bulk(S.B, wimg + (long long)(l + 1) * NDP_TRI128, NDP_TRI128, &S.bar_w);
         }
         __syncthreads();
+        NDP_T(10 + 4 * l);
         // ---- epilogue: TMEM -> registers, bias + ReLU, re-split into the A images (in place)
         const float* bias = params + L.off_b[l];
 #pragma unroll 1
@@ -158,6 +172,7 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_fwd_tc_kernel(NdpFwdA
         ndp_tc_fence_before();
         ndp_fence_proxy_async();
         __syncthreads();
+        NDP_T(11 + 4 * l);
     }
     if (tid == 0 && gact) {      // top activation
         for (int i = 0; i < 3; ++i) ndp_bulk_s2g(gact + (long long)LH * NDP_TRI128 + i * NDP_IMG128, S.A + i * NDP_IMG128, NDP_IMG128);
@@ -209,9 +224,12 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_fwd_tc_kernel(NdpFwdA
             }
         }
     }
+    NDP_T(61);
     if (tid == 0 && gact) ndp_bulk_wait0();     // smem must outlive the bulk stores
+    NDP_T(62);
     ndp_tc_fence_before();
     __syncthreads();
+    NDP_T(63);
     if (warp == 0) ndp_tmem_dealloc(tmem, 128);
 }
 
@@ -225,3 +243,9 @@ int ndp_fwd_tc_init() {
     return (int)cudaFuncSetAttribute(ndp_warp_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)ndp_fwd_tc_smem_bytes());
 }
+
+#ifndef NDP_EMU
+int ndp_debug_copy_fwd(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, ndp_dbg_fwd, sizeof(unsigned long long) * 64); }
+#else
+int ndp_debug_copy_fwd(unsigned long long* out) { for (int i = 0; i < 64; ++i) out[i] = 0; return 0; }
+#endif
