@@ -22,13 +22,12 @@ __device__ __forceinline__ void ndp_pack_store(const NdpLayout& L, float* pack, 
         if (rel >= 0 && rel < NDP_W * NDP_W) {
             const int o = rel >> 7, i = rel & 127;
             pack[L.pack_w[l] + i * NDP_W + o] = val;
-            // bf16 tri-image of W_l (row o, column i) for the tensor-core kernels
-            unsigned h1, h2, h3;
-            ndp_split3(val, h1, h2, h3);
-            unsigned char* img = (unsigned char*)(pack + L.pack_img) + (long long)l * NDP_TRI128 + ndp_img_off(o, i, NDP_IMG_RS(128));
+            // fp16 hi/lo images of W_l (row o, column i) for the tensor-core kernels
+            unsigned h1, h2;
+            ndp_split2(val, h1, h2);
+            unsigned char* img = (unsigned char*)(pack + L.pack_img) + (long long)l * NDP_SET128 + ndp_img_off(o, i, NDP_IMG_RS(128));
             *(unsigned short*)img = (unsigned short)h1;
             *(unsigned short*)(img + NDP_IMG128) = (unsigned short)h2;
-            *(unsigned short*)(img + 2 * NDP_IMG128) = (unsigned short)h3;
             return;
         }
     }
@@ -79,16 +78,15 @@ __global__ void __launch_bounds__(256) ndp_pack_kernel(NdpPackArgs a) {
     if (idx >= L.pack_img + L.hidden * NDP_W * NDP_W) return;
     const float* params = a.params + (long long)pair * a.params_stride;
     float* pack = a.pack + (long long)pair * a.pack_stride;
-    if (idx >= L.pack_img) {        // one thread per hidden weight: its three bf16 image entries
+    if (idx >= L.pack_img) {        // one thread per hidden weight: its two fp16 image entries
         const int rel = idx - L.pack_img;
         const int l = rel / (NDP_W * NDP_W), r2 = rel - l * NDP_W * NDP_W;
         const int o = r2 >> 7, i = r2 & 127;
-        unsigned h1, h2, h3;
-        ndp_split3(params[L.off_w[l] + o * NDP_W + i], h1, h2, h3);
-        unsigned char* img = (unsigned char*)(pack + L.pack_img) + (long long)l * NDP_TRI128 + ndp_img_off(o, i, NDP_IMG_RS(128));
+        unsigned h1, h2;
+        ndp_split2(params[L.off_w[l] + o * NDP_W + i], h1, h2);
+        unsigned char* img = (unsigned char*)(pack + L.pack_img) + (long long)l * NDP_SET128 + ndp_img_off(o, i, NDP_IMG_RS(128));
         *(unsigned short*)img = (unsigned short)h1;
         *(unsigned short*)(img + NDP_IMG128) = (unsigned short)h2;
-        *(unsigned short*)(img + 2 * NDP_IMG128) = (unsigned short)h3;
         return;
     }
     float v;

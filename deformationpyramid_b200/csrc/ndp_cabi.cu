@@ -20,7 +20,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 extern "C" const char* ndp_last_error(void) { return g_err.c_str(); }
 extern "C" int32_t ndp_version(void) { return 100; }
 
-// 0: hidden layers on the tensor cores (tcgen05, bf16x3 split, fp32 accumulate) -- default;
+// 0: hidden layers on the tensor cores (tcgen05, fp16 hi/lo split, fp32 accumulate) -- default;
 // 1: everything on the FP32 pipes.  Process-wide; solvers capture it at creation.
 static int g_mlp_mode = 0;
 extern "C" int ndp_set_mlp_mode(int32_t mode) {
@@ -63,7 +63,7 @@ extern "C" int64_t ndp_param_count(const ndp_layer_cfg* c) { return check_cfg(c)
 extern "C" int64_t ndp_pack_count(const ndp_layer_cfg* c) { return check_cfg(c) ? -1 : layout_of(c).pack_count; }
 static long long act_floats(int depth, long long n, int mode) {   // saved activations of one pair
     const long long tiles = (n + NDP_TP - 1) / NDP_TP;
-    return mode == 0 ? tiles * depth * (long long)(NDP_TRI128 / 4) : (long long)depth * n * NDP_W;
+    return mode == 0 ? tiles * depth * (long long)(NDP_SET128 / 4) : (long long)depth * n * NDP_W;
 }
 extern "C" int64_t ndp_saved_floats(const ndp_layer_cfg* c, int64_t n) {
     if (check_cfg(c) || n < 0) return -1;

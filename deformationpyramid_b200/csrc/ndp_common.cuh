@@ -40,7 +40,7 @@ struct NdpLayout {
     int head_w[NDP_MAX_HEAD], head_b[NDP_MAX_HEAD];   // per head row: weight row / bias offsets
     int param_count;
     int pack_in, pack_w[NDP_MAX_HIDDEN], pack_count;
-    int pack_img;               // float offset of the bf16 tri-images of the hidden weights (tensor-core kernels)
+    int pack_img;               // float offset of the fp16 hi/lo images of the hidden weights (tensor-core kernels)
     float freq, mu;
 };
 
@@ -73,7 +73,7 @@ static inline NdpLayout ndp_make_layout(int depth, int motion, int rot, int nonr
     int p = 0;
     L.pack_in = p; p += 6 * NDP_W;
     for (int l = 0; l < L.hidden; ++l) { L.pack_w[l] = p; p += NDP_W * NDP_W; }
-    L.pack_img = p; p += L.hidden * (3 * 128 * 128 * 2 / 4);   // 3 bf16 images of 128x128 per hidden layer
+    L.pack_img = p; p += L.hidden * (2 * 128 * 128 * 2 / 4);   // hi / lo fp16 images of 128x128 per hidden layer
     L.pack_count = p;
     return L;
 }

@@ -1,14 +1,19 @@
 // tcgen05 (5th-generation tensor core) + TMEM primitives for the warp-field kernels, and the
 // shared-memory "image" layout they use.
 //
-// Precision scheme: every fp32 operand x is split exactly into three bf16 terms x = x1 + x2 + x3
-// (8 + 8 + 8 significand bits) and the product is accumulated in fp32 in TMEM from the six partial
-// products x1y1, x1y2, x2y1, x1y3, x2y2, x3y1 (dropped terms are O(2^-24)): fp32-level accuracy
-// (measured 2e-6 of the largest entry for K = 128) at 1.5 PFLOP/s of dense bf16 issue
-// (scripts/microbench/umma_test.cu: 2.45 us per 128x128x128 product per SM vs 12.7 us on the FP32
-// pipes), which keeps the 1e-4 parity contract that single-pass TF32/BF16 would break.
+// Precision scheme: every fp32 operand x is split into two fp16 terms x ~= x1 + x2 (11 + 11
+// significand bits, |x - x1 - x2| <= 2^-22 |x|, absolute floor 2^-25) and the product is accumulated
+// in fp32 in TMEM from the three partial products x1y1, x1y2, x2y1 (the dropped x2y2 is O(2^-22)):
+// ~fp32-level accuracy (the fp32 pipes' own rounding of a K = 128 dot product is of the same order)
+// at a third of the dense fp16 issue rate, which keeps the 1e-4 parity contract that single-pass
+// TF32/BF16 would break.  fp16 has a narrow exponent range, so
+//   * activations / weights are converted with saturation (|x| <= 65504; the network's
+//     activations are O(1)), and a positive activation is never flushed to zero (relu' is read back
+//     from the image: see ndp_relu_img);
+//   * back-propagated deltas (O(1e-8)) are multiplied by an exact per-tile power of two chosen so
+//     that the tile's largest head gradient lies in [1, 2); the factor is undone in the epilogues.
 //
-// Image layout: a [128][C] bf16 matrix is stored as 8x8 "core matrices" of 8 rows x 16 bytes,
+// Image layout: a [128][C] fp16 matrix is stored as 8x8 "core matrices" of 8 rows x 16 bytes,
 //     byte offset(r, c) = (r/8) * RS + (c/8) * 128 + (r%8) * 16 + (c%8) * 2,   RS = (C/8) * 128
 // which is BOTH canonical no-swizzle UMMA layouts at once: as a K-major operand (K = c) with
 // LBO = 128, SBO = RS, and as an MN-major operand (MN = c, K = r) with SBO = 128, LBO = RS.  One
@@ -22,62 +27,77 @@
 #define NDP_IMG_RS(C) (((C) / 8) * 128)                  // bytes between 8-row groups
 #define NDP_IMG_BYTES(C) (16 * NDP_IMG_RS(C))            // 128 rows
 #define NDP_IMG128 NDP_IMG_BYTES(128)                    // 32768
-#define NDP_TRI128 (3 * NDP_IMG128)                      // 98304: hi / mid / lo images
+#define NDP_SET128 (2 * NDP_IMG128)                      // 65536: hi / lo images of a [128][128] operand
 
 __device__ __forceinline__ unsigned ndp_img_off(int r, int c, int rs) {
     return (unsigned)((r >> 3) * rs + (c >> 3) * NDP_IMG_CS + (r & 7) * 16 + (c & 7) * 2);
 }
 
-// bf16 round-to-nearest-even of an fp32 value, returned as the 16 high bits; and back
-__device__ __forceinline__ unsigned ndp_bf16_rn(float x) {
-    unsigned u = __float_as_uint(x);
-    if ((u & 0x7f800000u) == 0x7f800000u) return u >> 16;           // inf / nan: truncate
-    return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
-}
-__device__ __forceinline__ float ndp_bf16_to_f32(unsigned h) { return __uint_as_float(h << 16); }
+// relu that keeps every positive value representable in the fp16 hi image (>= 2^-24, the smallest
+// fp16 subnormal), so that relu'(h) can be recovered from the saved image as "hi > 0"
+__device__ __forceinline__ float ndp_relu_img(float v) { return v > 0.0f ? fmaxf(v, 5.9604644775390625e-08f) : 0.0f; }
 
-// x -> (x1, x2, x3) bf16 bit patterns with x1 + x2 + x3 == x to fp32 precision
-__device__ __forceinline__ void ndp_split3(float x, unsigned& h1, unsigned& h2, unsigned& h3) {
-    h1 = ndp_bf16_rn(x);
-    const float r1 = x - ndp_bf16_to_f32(h1);
-    h2 = ndp_bf16_rn(r1);
-    const float r2 = r1 - ndp_bf16_to_f32(h2);
-    h3 = ndp_bf16_rn(r2);
-}
-
-// two fp32 -> packed bf16x2 (round to nearest even): ONE instruction on sm_100a (F2FP.BF16.PACK_AB)
 #ifdef NDP_EMU
-static inline unsigned ndp_pack2_bf16(float lo, float hi) { return (ndp_bf16_rn(hi) << 16) | (ndp_bf16_rn(lo) & 0xffffu); }
+static inline unsigned ndp_f16_rn_sat(float x) {
+    if (x == x) x = fminf(fmaxf(x, -65504.0f), 65504.0f);
+    _Float16 h = (_Float16)x;
+    unsigned short u; memcpy(&u, &h, 2);
+    return u;
+}
+static inline float ndp_f16_to_f32(unsigned h) { unsigned short u = (unsigned short)h; _Float16 f; memcpy(&f, &u, 2); return (float)f; }
+static inline unsigned ndp_pack2_f16(float lo, float hi) { return (ndp_f16_rn_sat(hi) << 16) | ndp_f16_rn_sat(lo); }
+static inline void ndp_unpack2_f16(unsigned w, float& lo, float& hi) { lo = ndp_f16_to_f32(w & 0xffffu); hi = ndp_f16_to_f32(w >> 16); }
 #else
-__device__ __forceinline__ unsigned ndp_pack2_bf16(float lo, float hi) {
+// two fp32 -> packed f16x2 (round to nearest even, saturating to +-65504): ONE instruction
+__device__ __forceinline__ unsigned ndp_pack2_f16(float lo, float hi) {
     unsigned d;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
     return d;
 }
+__device__ __forceinline__ void ndp_unpack2_f16(unsigned w, float& lo, float& hi) {
+    asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(lo), "=f"(hi) : "r"(w));
+}
+__device__ __forceinline__ float ndp_f16_to_f32(unsigned h) { float lo, hi; ndp_unpack2_f16(h & 0xffffu, lo, hi); return lo; }
 #endif
 
-// exact 3-way split of a pair of values into three packed bf16x2 words (hi, mid, lo parts)
-__device__ __forceinline__ void ndp_split3_pair(float x0, float x1, unsigned& w1, unsigned& w2, unsigned& w3) {
-    w1 = ndp_pack2_bf16(x0, x1);
-    const float r0 = x0 - __uint_as_float(w1 << 16), r1 = x1 - __uint_as_float(w1 & 0xffff0000u);
-    w2 = ndp_pack2_bf16(r0, r1);
-    const float s0 = r0 - __uint_as_float(w2 << 16), s1 = r1 - __uint_as_float(w2 & 0xffff0000u);
-    w3 = ndp_pack2_bf16(s0, s1);
+// 2-way split of a pair of values into two packed f16x2 words (hi and lo parts)
+__device__ __forceinline__ void ndp_split2_pair(float x0, float x1, unsigned& w1, unsigned& w2) {
+    w1 = ndp_pack2_f16(x0, x1);
+    float f0, f1;
+    ndp_unpack2_f16(w1, f0, f1);
+    w2 = ndp_pack2_f16(x0 - f0, x1 - f1);
+}
+// one value -> its two fp16 bit patterns
+__device__ __forceinline__ void ndp_split2(float x, unsigned& h1, unsigned& h2) {
+    unsigned w1, w2;
+    ndp_split2_pair(x, 0.0f, w1, w2);
+    h1 = w1 & 0xffffu; h2 = w2 & 0xffffu;
 }
 
-// split 8 consecutive values and store them as one 16-byte chunk in each of the three images
-__device__ __forceinline__ void ndp_store_chunk3(unsigned char* tri, unsigned img_bytes, unsigned off, const float (&v)[8]) {
-    uint4 p0, p1, p2;
-    ndp_split3_pair(v[0], v[1], p0.x, p1.x, p2.x);
-    ndp_split3_pair(v[2], v[3], p0.y, p1.y, p2.y);
-    ndp_split3_pair(v[4], v[5], p0.z, p1.z, p2.z);
-    ndp_split3_pair(v[6], v[7], p0.w, p1.w, p2.w);
-    *(uint4*)(tri + off) = p0;
-    *(uint4*)(tri + img_bytes + off) = p1;
-    *(uint4*)(tri + 2 * img_bytes + off) = p2;
+// split 8 consecutive values and store them as one 16-byte chunk in each of the two images
+__device__ __forceinline__ void ndp_store_chunk2(unsigned char* set, unsigned img_bytes, unsigned off, const float (&v)[8]) {
+    uint4 p0, p1;
+    ndp_split2_pair(v[0], v[1], p0.x, p1.x);
+    ndp_split2_pair(v[2], v[3], p0.y, p1.y);
+    ndp_split2_pair(v[4], v[5], p0.z, p1.z);
+    ndp_split2_pair(v[6], v[7], p0.w, p1.w);
+    *(uint4*)(set + off) = p0;
+    *(uint4*)(set + img_bytes + off) = p1;
+}
+// the 8 values of a 16-byte chunk re-assembled from the two images
+__device__ __forceinline__ void ndp_load_chunk2(const unsigned char* set, unsigned img_bytes, unsigned off, float (&v)[8]) {
+    const uint4 q0 = *(const uint4*)(set + off), q1 = *(const uint4*)(set + img_bytes + off);
+    const unsigned w0[4] = {q0.x, q0.y, q0.z, q0.w}, w1[4] = {q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float a0, a1, b0, b1;
+        ndp_unpack2_f16(w0[k], a0, a1);
+        ndp_unpack2_f16(w1[k], b0, b1);
+        v[2 * k] = a0 + b0; v[2 * k + 1] = a1 + b1;
+    }
 }
 
-// bit j of the result: element j (0..7) of a 16-byte bf16 chunk is > 0  (relu' of a saved activation)
+// bit j of the result: element j (0..7) of a 16-byte fp16 chunk is > 0  (relu' of a saved activation)
 __device__ __forceinline__ unsigned ndp_pos_mask8(const uint4& q) {
     const unsigned w[4] = {q.x, q.y, q.z, q.w};
     unsigned m = 0;
@@ -90,9 +110,18 @@ __device__ __forceinline__ unsigned ndp_pos_mask8(const uint4& q) {
     return m;
 }
 
-// instruction descriptor: D = f32, A = B = bf16, M x N tile, operand majors (0 = K-major, 1 = MN-major)
-__device__ __forceinline__ unsigned ndp_idesc_bf16(int M, int N, int a_mn, int b_mn) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)a_mn << 15) | ((unsigned)b_mn << 16) |
+// exact power-of-two scale that brings m (finite, > 0) into [1, 2); 1 for m == 0 / non-finite
+__device__ __forceinline__ void ndp_pow2_scale(float m, float& scale, float& inv_scale) {
+    int e = (int)((__float_as_uint(m) >> 23) & 0xffu) - 127;
+    if (!(m > 0.0f) || e == 128) e = 0;
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+    scale = __uint_as_float((unsigned)(127 - e) << 23);
+    inv_scale = __uint_as_float((unsigned)(127 + e) << 23);
+}
+
+// instruction descriptor: D = f32, A = B = f16 (format code 0), M x N tile, operand majors (0 = K-major, 1 = MN-major)
+__device__ __forceinline__ unsigned ndp_idesc_f16(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | ((unsigned)a_mn << 15) | ((unsigned)b_mn << 16) |
            ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
 }
 
@@ -106,7 +135,7 @@ static inline unsigned ndp_tmem_alloc(unsigned* slot, int) { *slot = 0; return 0
 static inline void ndp_tmem_dealloc(unsigned, int) {}
 static inline void ndp_tc_fence_before() {}
 static inline void ndp_tc_fence_after() {}
-static inline void ndp_umma_bf16(unsigned tmem_d, NdpUmmaDesc da, NdpUmmaDesc db, unsigned idesc, unsigned acc) {
+static inline void ndp_umma_f16(unsigned tmem_d, NdpUmmaDesc da, NdpUmmaDesc db, unsigned idesc, unsigned acc) {
     const int N = (int)((idesc >> 17) & 0x3f) << 3, M = (int)((idesc >> 24) & 0x1f) << 4;
     const int a_mn = (idesc >> 15) & 1, b_mn = (idesc >> 16) & 1;
     const int col0 = (int)(tmem_d & 0xffff), lane0 = (int)(tmem_d >> 16);
@@ -114,7 +143,7 @@ static inline void ndp_umma_bf16(unsigned tmem_d, NdpUmmaDesc da, NdpUmmaDesc db
         const unsigned off = is_mn ? (unsigned)((mn >> 3) * d.sbo + (mn & 7) * 2 + (k >> 3) * d.lbo + (k & 7) * 16)
                                    : (unsigned)((mn >> 3) * d.sbo + (mn & 7) * 16 + (k >> 3) * d.lbo + (k & 7) * 2);
         unsigned short h; memcpy(&h, d.p + off, 2);
-        return __uint_as_float((unsigned)h << 16);
+        return ndp_f16_to_f32(h);
     };
     for (int m = 0; m < M; ++m)
         for (int n = 0; n < N; ++n) {
@@ -154,7 +183,7 @@ __device__ __forceinline__ void ndp_tmem_dealloc(unsigned taddr, int ncols) {
 }
 __device__ __forceinline__ void ndp_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void ndp_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void ndp_umma_bf16(unsigned tmem_d, NdpUmmaDesc da, NdpUmmaDesc db, unsigned idesc, unsigned acc) {
+__device__ __forceinline__ void ndp_umma_f16(unsigned tmem_d, NdpUmmaDesc da, NdpUmmaDesc db, unsigned idesc, unsigned acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -191,24 +220,24 @@ __device__ __forceinline__ void ndp_bulk_wait0() { asm volatile("cp.async.bulk.w
 static inline void ndp_tmem_alloc_warp(unsigned* slot, int n) { ndp_tmem_alloc(slot, n); }
 #endif
 
-// One fp32-accurate product D[128 x N] (+)= A . B over K = 16 * ksteps from tri-images:
-// the six bf16 partial products, issued by ONE thread.  a_step / b_step: descriptor byte advance
-// per 16-deep k-step; a_img / b_img: byte distance between the hi / mid / lo images.
-// Same with nb = 1: only the hi image of B (for operands that are exact in bf16, e.g. a column of ones).
+// One fp32-accurate product D[128 x N] (+)= A . B over K = 16 * ksteps from hi/lo image sets:
+// the three fp16 partial products, issued by ONE thread.  a_step / b_step: descriptor byte advance
+// per 16-deep k-step; a_img / b_img: byte distance between the hi and lo images.
+// ndp_umma_gemm_a2: only the hi image of B (for operands that are exact in fp16, e.g. a column of ones).
 #ifdef NDP_EMU
 static inline
 #else
 static __device__ __noinline__
 #endif
-void ndp_umma_gemm_a3(unsigned tmem_d, NdpUmmaDesc a0, unsigned a_img, unsigned a_step, NdpUmmaDesc b0, unsigned b_step,
+void ndp_umma_gemm_a2(unsigned tmem_d, NdpUmmaDesc a0, unsigned a_img, unsigned a_step, NdpUmmaDesc b0, unsigned b_step,
                       int ksteps, unsigned idesc) {
     unsigned acc = 0u;
 #pragma unroll 1
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 1; i >= 0; --i) {
         NdpUmmaDesc da = ndp_umma_desc_adv(a0, i * a_img), db = b0;
 #pragma unroll 1
         for (int ks = 0; ks < ksteps; ++ks) {
-            ndp_umma_bf16(tmem_d, da, db, idesc, acc);
+            ndp_umma_f16(tmem_d, da, db, idesc, acc);
             acc = 1u;
             da = ndp_umma_desc_adv(da, a_step);
             db = ndp_umma_desc_adv(db, b_step);
@@ -221,21 +250,21 @@ static inline
 #else
 static __device__ __noinline__
 #endif
-void ndp_umma_gemm6(unsigned tmem_d, NdpUmmaDesc a0, unsigned a_img, unsigned a_step,
+void ndp_umma_gemm3(unsigned tmem_d, NdpUmmaDesc a0, unsigned a_img, unsigned a_step,
                     NdpUmmaDesc b0, unsigned b_img, unsigned b_step, int ksteps,
                     unsigned idesc, bool accumulate) {
     unsigned acc = accumulate ? 1u : 0u;
+    // small cross terms first, the hi x hi product last
 #pragma unroll 1
-    for (int i = 0; i < 3; ++i)
+    for (int t = 0; t < 3; ++t) {
+        const int i = (t == 0) ? 1 : 0, j = (t == 1) ? 1 : 0;
+        NdpUmmaDesc da = ndp_umma_desc_adv(a0, i * a_img), db = ndp_umma_desc_adv(b0, j * b_img);
 #pragma unroll 1
-        for (int j = 0; i + j < 3; ++j) {
-            NdpUmmaDesc da = ndp_umma_desc_adv(a0, i * a_img), db = ndp_umma_desc_adv(b0, j * b_img);
-#pragma unroll 1
-            for (int ks = 0; ks < ksteps; ++ks) {
-                ndp_umma_bf16(tmem_d, da, db, idesc, acc);
-                acc = 1u;
-                da = ndp_umma_desc_adv(da, a_step);
-                db = ndp_umma_desc_adv(db, b_step);
-            }
+        for (int ks = 0; ks < ksteps; ++ks) {
+            ndp_umma_f16(tmem_d, da, db, idesc, acc);
+            acc = 1u;
+            da = ndp_umma_desc_adv(da, a_step);
+            db = ndp_umma_desc_adv(db, b_step);
         }
+    }
 }

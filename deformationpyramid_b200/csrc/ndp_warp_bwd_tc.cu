@@ -4,8 +4,8 @@
 // Replaces the autograd backward of NDPLayer.forward (model/nets.py:111-140) that the reference
 // runs in loss.backward() (model/registration.py:236).
 //
-// Every reduction over the tile's 128 points is a tcgen05 GEMM with K = points (operands as bf16
-// tri-images, fp32 accumulation in TMEM, see ndp_tc.cuh), issued by one thread:
+// Every reduction over the tile's 128 points is a tcgen05 GEMM with K = points (operands as fp16
+// hi/lo image sets, fp32 accumulation in TMEM, see ndp_tc.cuh), issued by one thread:
 //     head grads   dW_h  = hg^T h_L          A = hg image   (MN-major)  B = h_L   (MN-major)
 //     weight grads dW_l  = delta^T h_l       A = delta      (MN-major)  B = h_l   (MN-major)
 //     bias grads   db_l  = delta^T 1         A = delta      (MN-major)  B = E[:,6] = 1
@@ -13,7 +13,7 @@
 //     back-prop    delta_l = (delta W_l).relu'   A = delta  (K-major)   B = W_l   (MN-major)
 // The SAME delta image is the MN-major operand of the dW products and the K-major operand of the
 // back-propagation product, and the SAME weight image serves forward and backward (the core-matrix
-// layout is both canonical UMMA layouts at once), so nothing is ever transposed.  h_l tri-images
+// layout is both canonical UMMA layouts at once), so nothing is ever transposed.  h_l image sets
 // come back from HBM by TMA bulk copies exactly as the forward kernel's bulk stores wrote them;
 // the weight image of the layer replaces h_l in shared memory as soon as the dW MMAs retire,
 // overlapping with the TMEM -> HBM epilogue of dW.  No atomics: one partial row per tile.
@@ -28,15 +28,16 @@ __device__ unsigned long long ndp_dbg_bwd[64];
 #define NDP_T(i) do {} while (0)
 #endif
 
-#define NDP_IMG16 NDP_IMG_BYTES(16)     // [128][16] bf16 image: 4096 bytes
+#define NDP_IMG16 NDP_IMG_BYTES(16)     // [128][16] fp16 image: 4096 bytes
 struct BwdTcSmem {
-    unsigned char D[NDP_TRI128];        // delta tri-image
-    unsigned char X[NDP_TRI128];        // h_l tri-image, then W_l tri-image
-    unsigned char HG[3 * NDP_IMG16];    // [128 points][16]: mlp_scale * dL/dz (head gradients); must precede E:
-    unsigned char E[3 * NDP_IMG16];     // [128 points][16]: cols 0..5 positional encoding, col 6 = 1
+    unsigned char D[NDP_SET128];        // delta hi/lo images (scaled by the tile's power of two)
+    unsigned char X[NDP_SET128];        // h_l images, then W_l images
+    unsigned char HG[2 * NDP_IMG16];    // [128 points][16]: mlp_scale * dL/dz (head gradients); must precede E:
+    unsigned char E[2 * NDP_IMG16];     // [128 points][16]: cols 0..5 positional encoding, col 6 = 1
     float hw[NDP_MAX_HEAD * NDP_W];     // head weights (fp32), rows >= head_dim zero
     float xs[NDP_TP * 4];
     float gxs[NDP_TP * 4];
+    float red[4];                       // per-warp max |head gradient| of the tile
     NdpMbar bar_x, bar_mma;
     unsigned tmem_slot, pad[3];
 };
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
     const unsigned char* wimg = (const unsigned char*)(a.pack + (long long)pair * a.pack_stride + L.pack_img);
     const int LH = L.hidden, HD = L.head_dim;
     const unsigned char* gact = (const unsigned char*)a.act + ((long long)pair * a.act_stride) * 4 +
-                                (long long)tile * (LH + 1) * NDP_TRI128;
+                                (long long)tile * (LH + 1) * NDP_SET128;
     float* part = a.partials + (long long)pair * a.partials_stride + (long long)tile * a.partial_pitch;
     const int warp = tid >> 5, lane = tid & 31, p = tid & (NDP_TP - 1), half = tid >> 7;
     const int RS = NDP_IMG_RS(128), CS = NDP_IMG_CS, RS16 = NDP_IMG_RS(16);
@@ -76,9 +77,12 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
     NDP_T(1);
     const unsigned tmem = S.tmem_slot;
     const unsigned tlane = tmem + ((unsigned)((warp & 3) * 32) << 16);
-    if (tid == 0) ndp_stage_bulk(S.X, gact + (long long)LH * NDP_TRI128, NDP_TRI128, &S.bar_x);      // h_L
+    if (tid == 0) ndp_stage_bulk(S.X, gact + (long long)LH * NDP_SET128, NDP_SET128, &S.bar_x);      // h_L
 
     // ---- per point: dL/dy -> dL/dz (heads) and the direct part of dL/dx; E and head-gradient images
+    float hgv[16], e0[8];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) hgv[r] = 0.0f;
     if (tid < NDP_TP) {
         const int gp = tile * NDP_TP + tid;
         float gz[NDP_MAX_HEAD];
@@ -109,33 +113,38 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
             const float gnu = (a.gnu && L.nonrigid) ? a.gnu[(long long)pair * a.gnu_stride + gp] : 0.0f;
             ndp_point_backward(L.motion, L.rot, L.nonrigid, z, x, gy, gnu, gz, gxd);
         }
-        float v0[8], v1[8];
+        float mx = 0.0f;
 #pragma unroll
-        for (int r = 0; r < NDP_MAX_HEAD; ++r) {
-            const float g = L.mu * gz[r];
-            if (r < 8) v0[r] = g; else v1[r - 8] = g;
-        }
-#pragma unroll
-        for (int r = NDP_MAX_HEAD - 8; r < 8; ++r) v1[r] = 0.0f;
-        ndp_store_chunk3(S.HG, NDP_IMG16, ndp_img_off(tid, 0, RS16), v0);
-        ndp_store_chunk3(S.HG, NDP_IMG16, ndp_img_off(tid, 8, RS16), v1);
+        for (int r = 0; r < NDP_MAX_HEAD; ++r) { hgv[r] = L.mu * gz[r]; mx = fmaxf(mx, fabsf(hgv[r])); }
+        for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+        if (lane == 0) S.red[warp] = mx;
         S.xs[tid * 4 + 0] = x[0]; S.xs[tid * 4 + 1] = x[1]; S.xs[tid * 4 + 2] = x[2];
         S.gxs[tid * 4 + 0] = gxd[0]; S.gxs[tid * 4 + 1] = gxd[1]; S.gxs[tid * 4 + 2] = gxd[2];
-        float e0[8], e1[8], s, c;
+        float s, c;
         sincosf(x[0] * L.freq, &s, &c); e0[0] = s; e0[1] = c;
         sincosf(x[1] * L.freq, &s, &c); e0[2] = s; e0[3] = c;
         sincosf(x[2] * L.freq, &s, &c); e0[4] = s; e0[5] = c;
         e0[6] = 1.0f; e0[7] = 0.0f;
+    }
+    __syncthreads();
+    // the tile's delta scale: an exact power of two that brings the largest head gradient into [1, 2)
+    // (fp16 operand range, see ndp_tc.cuh); undone when the gradients leave TMEM
+    float dscale, dinv;
+    ndp_pow2_scale(fmaxf(fmaxf(S.red[0], S.red[1]), fmaxf(S.red[2], S.red[3])), dscale, dinv);
+    if (tid < NDP_TP) {
+        float v0[8], v1[8], e1[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) e1[j] = 0.0f;
-        ndp_store_chunk3(S.E, NDP_IMG16, ndp_img_off(tid, 0, RS16), e0);
-        ndp_store_chunk3(S.E, NDP_IMG16, ndp_img_off(tid, 8, RS16), e1);
+        for (int r = 0; r < 8; ++r) { v0[r] = hgv[r] * dscale; v1[r] = hgv[8 + r] * dscale; e1[r] = 0.0f; }
+        ndp_store_chunk2(S.HG, NDP_IMG16, ndp_img_off(tid, 0, RS16), v0);
+        ndp_store_chunk2(S.HG, NDP_IMG16, ndp_img_off(tid, 8, RS16), v1);
+        ndp_store_chunk2(S.E, NDP_IMG16, ndp_img_off(tid, 0, RS16), e0);
+        ndp_store_chunk2(S.E, NDP_IMG16, ndp_img_off(tid, 8, RS16), e1);
     }
     ndp_fence_proxy_async();
     __syncthreads();
     NDP_T(2);
 
-    const unsigned id_nn = ndp_idesc_bf16(128, 128, 1, 1), id_sm = ndp_idesc_bf16(128, 16, 1, 1), id_kn = ndp_idesc_bf16(128, 128, 0, 1);
+    const unsigned id_nn = ndp_idesc_f16(128, 128, 1, 1), id_sm = ndp_idesc_f16(128, 16, 1, 1), id_kn = ndp_idesc_f16(128, 128, 0, 1);
     const NdpUmmaDesc dD_mn = ndp_umma_desc(S.D, RS, CS), dD_k = ndp_umma_desc(S.D, CS, RS), dX_mn = ndp_umma_desc(S.X, RS, CS);
     const NdpUmmaDesc dE = ndp_umma_desc(S.E, RS16, CS), dHG = ndp_umma_desc(S.HG, RS16, CS);
     // ---- head gradients: dW_h = hg^T h_L, db_h = hg^T 1.  The [128][16] head-gradient image is read as
@@ -144,25 +153,23 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
     NDP_T(3);
     if (tid == 0) {
         ndp_tc_fence_after();
-        ndp_umma_gemm6(tmem + TM_DH, dHG, NDP_IMG16, 2 * RS16, dX_mn, NDP_IMG128, 2 * RS, 8, id_nn, false);
-        ndp_umma_gemm_a3(tmem + TM_SM, dHG, NDP_IMG16, 2 * RS16, dE, 2 * RS16, 8, id_sm);
+        ndp_umma_gemm3(tmem + TM_DH, dHG, NDP_IMG16, 2 * RS16, dX_mn, NDP_IMG128, 2 * RS, 8, id_nn, false);
+        ndp_umma_gemm_a2(tmem + TM_SM, dHG, NDP_IMG16, 2 * RS16, dE, 2 * RS16, 8, id_sm);
         ndp_umma_commit(&S.bar_mma);
     }
     // ---- delta at the top activation straight into the delta image while the head GEMMs run:
     //      (W_h^T hg) . relu'(h_L)
     {
-        // this row's head gradients, re-assembled from the three bf16 parts of the image
+        // this row's (scaled) head gradients, re-assembled from the two fp16 parts of the image
         float g[16];
+        {
+            float t8[8];
+            ndp_load_chunk2(S.HG, NDP_IMG16, ndp_img_off(p, 0, RS16), t8);
 #pragma unroll
-        for (int c8 = 0; c8 < 2; ++c8) {
-            const unsigned off = ndp_img_off(p, c8 * 8, RS16);
-            const uint4 q0 = *(const uint4*)(S.HG + off), q1 = *(const uint4*)(S.HG + NDP_IMG16 + off), q2 = *(const uint4*)(S.HG + 2 * NDP_IMG16 + off);
-            const unsigned w0[4] = {q0.x, q0.y, q0.z, q0.w}, w1[4] = {q1.x, q1.y, q1.z, q1.w}, w2[4] = {q2.x, q2.y, q2.z, q2.w};
+            for (int k = 0; k < 8; ++k) g[k] = t8[k];
+            ndp_load_chunk2(S.HG, NDP_IMG16, ndp_img_off(p, 8, RS16), t8);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                g[c8 * 8 + 2 * k] = __uint_as_float(w0[k] << 16) + __uint_as_float(w1[k] << 16) + __uint_as_float(w2[k] << 16);
-                g[c8 * 8 + 2 * k + 1] = __uint_as_float(w0[k] & 0xffff0000u) + __uint_as_float(w1[k] & 0xffff0000u) + __uint_as_float(w2[k] & 0xffff0000u);
-            }
+            for (int k = 0; k < 8; ++k) g[8 + k] = t8[k];
         }
 #pragma unroll 1
         for (int ch = 0; ch < 8; ++ch) {
@@ -179,7 +186,7 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) u[j] = ((pm >> j) & 1u) ? u[j] : 0.0f;
-            ndp_store_chunk3(S.D, NDP_IMG128, ndp_img_off(p, o0, RS), u);
+            ndp_store_chunk2(S.D, NDP_IMG128, ndp_img_off(p, o0, RS), u);
         }
     }
     NDP_T(4);
@@ -188,7 +195,7 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
     NDP_T(5);
     ndp_fence_proxy_async();
     __syncthreads();            // every thread is done with h_L (relu' masks) and delta_top is complete
-    if (tid == 0 && LH > 0) ndp_stage_bulk(S.X, gact + (long long)(LH - 1) * NDP_TRI128, NDP_TRI128, &S.bar_x);
+    if (tid == 0 && LH > 0) ndp_stage_bulk(S.X, gact + (long long)(LH - 1) * NDP_SET128, NDP_SET128, &S.bar_x);
     if ((warp & 3) == 0) {      // TMEM lanes 0..31 hold the head rows
 #pragma unroll 1
         for (int c32 = 0; c32 < 2; ++c32) {
@@ -198,13 +205,13 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
             if (lane < HD) {
                 float* dst = part + L.head_w[lane] + col0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) dst[j] = v[j];
+                for (int j = 0; j < 32; ++j) dst[j] = v[j] * dinv;
             }
         }
         if (half == 0) {
             float v[32];
             ndp_tmem_ld32(tlane + TM_SM, v);
-            if (lane < HD) part[L.head_b[lane]] = v[6];
+            if (lane < HD) part[L.head_b[lane]] = v[6] * dinv;
         }
     }
     ndp_tc_fence_before();
@@ -219,8 +226,8 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
         if (tid == 0) {
             ndp_tc_fence_after();
             // dW_l[o][i] = sum_p delta[p][o] h_l[p][i];  db_l[o] = sum_p delta[p][o] (ones column of E)
-            ndp_umma_gemm6(tmem + TM_DW, dD_mn, NDP_IMG128, 2 * RS, dX_mn, NDP_IMG128, 2 * RS, 8, id_nn, false);
-            ndp_umma_gemm_a3(tmem + TM_SM, dD_mn, NDP_IMG128, 2 * RS, dE, 2 * RS16, 8, id_sm);
+            ndp_umma_gemm3(tmem + TM_DW, dD_mn, NDP_IMG128, 2 * RS, dX_mn, NDP_IMG128, 2 * RS, 8, id_nn, false);
+            ndp_umma_gemm_a2(tmem + TM_SM, dD_mn, NDP_IMG128, 2 * RS, dE, 2 * RS16, 8, id_sm);
             ndp_umma_commit(&S.bar_mma);
         }
         // relu' mask of h_l for this thread's row / column half, before W_l replaces h_l
@@ -233,7 +240,7 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
         ndp_tc_fence_after();
         __syncthreads();        // all masks extracted: h_l may be overwritten
         NDP_T(tb + 2);
-        if (tid == 0) ndp_stage_bulk(S.X, wimg + (long long)l * NDP_TRI128, NDP_TRI128, &S.bar_x);     // W_l over h_l
+        if (tid == 0) ndp_stage_bulk(S.X, wimg + (long long)l * NDP_SET128, NDP_SET128, &S.bar_x);     // W_l over h_l
         // dW epilogue: TMEM -> this tile's partial row (thread = output row o, 64 input columns)
         {
             const int o = (warp & 3) * 32 + lane;
@@ -244,12 +251,12 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
                 ndp_tmem_ld32(tlane + TM_DW + col0, v);
                 float* dst = part + L.off_w[l] + o * NDP_W + col0;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) *(float4*)(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (int j = 0; j < 32; j += 4) *(float4*)(dst + j) = make_float4(v[j] * dinv, v[j + 1] * dinv, v[j + 2] * dinv, v[j + 3] * dinv);
             }
             if (half == 0) {
                 float v[32];
                 ndp_tmem_ld32(tlane + TM_SM, v);
-                part[L.off_b[l] + o] = v[6];
+                part[L.off_b[l] + o] = v[6] * dinv;
             }
         }
         NDP_T(tb + 3);
@@ -258,13 +265,13 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
         if (tid == 0) {
             ndp_tc_fence_after();
             // delta_l[p][i] = sum_o delta[p][o] W_l[o][i]
-            ndp_umma_gemm6(tmem + TM_DH, dD_k, NDP_IMG128, 2 * CS, dX_mn, NDP_IMG128, 2 * RS, 8, id_kn, false);
+            ndp_umma_gemm3(tmem + TM_DH, dD_k, NDP_IMG128, 2 * CS, dX_mn, NDP_IMG128, 2 * RS, 8, id_kn, false);
             ndp_umma_commit(&S.bar_mma);
         }
         ndp_mbar_wait(&S.bar_mma, mph); mph ^= 1;
         ndp_tc_fence_after();
         NDP_T(tb + 5);
-        if (tid == 0 && l > 0) ndp_stage_bulk(S.X, gact + (long long)(l - 1) * NDP_TRI128, NDP_TRI128, &S.bar_x);   // h_{l-1} over W_l
+        if (tid == 0 && l > 0) ndp_stage_bulk(S.X, gact + (long long)(l - 1) * NDP_SET128, NDP_SET128, &S.bar_x);   // h_{l-1} over W_l
         // dH epilogue: relu' mask, re-split, delta image updated in place
 #pragma unroll 1
         for (int c32 = 0; c32 < 2; ++c32) {
@@ -277,7 +284,7 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
                 float u[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) u[j] = ((mk >> (s8 * 8 + j)) & 1u) ? v[s8 * 8 + j] : 0.0f;
-                ndp_store_chunk3(S.D, NDP_IMG128, ndp_img_off(p, col0 + s8 * 8, RS), u);
+                ndp_store_chunk2(S.D, NDP_IMG128, ndp_img_off(p, col0 + s8 * 8, RS), u);
             }
         }
         ndp_tc_fence_before();
@@ -289,7 +296,7 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
 
     // ---- input layer: [dW_in | db_in][o][0..6] = sum_p delta_0[p][o] E[p][0..6]
     if (tid == 0) {
-        ndp_umma_gemm6(tmem + TM_SM, dD_mn, NDP_IMG128, 2 * RS, dE, NDP_IMG16, 2 * RS16, 8, id_sm, false);
+        ndp_umma_gemm3(tmem + TM_SM, dD_mn, NDP_IMG128, 2 * RS, dE, NDP_IMG16, 2 * RS16, 8, id_sm, false);
         ndp_umma_commit(&S.bar_mma);
     }
     ndp_mbar_wait(&S.bar_mma, mph); mph ^= 1;
@@ -300,8 +307,8 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
         ndp_tmem_ld32(tlane + TM_SM, v);
         float* dst = part + L.off_w_in + o * 6;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) dst[c] = v[c];
-        part[L.off_b_in + o] = v[6];
+        for (int c = 0; c < 6; ++c) dst[c] = v[c] * dinv;
+        part[L.off_b_in + o] = v[6] * dinv;
     }
     if (a.gx && tid < NDP_TP) {     // optional dL/dx: direct part + path through the positional encoding
         const int gp = tile * NDP_TP + tid;
@@ -309,14 +316,11 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
             float de[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
             const float* wi = params + L.off_w_in;
             for (int ch = 0; ch < 16; ++ch) {
-                const unsigned off = ndp_img_off(tid, ch * 8, RS);
-                const uint4 q0 = *(const uint4*)(S.D + off), q1 = *(const uint4*)(S.D + NDP_IMG128 + off), q2 = *(const uint4*)(S.D + 2 * NDP_IMG128 + off);
-                const unsigned w0[4] = {q0.x, q0.y, q0.z, q0.w}, w1[4] = {q1.x, q1.y, q1.z, q1.w}, w2[4] = {q2.x, q2.y, q2.z, q2.w};
+                float d8[8];
+                ndp_load_chunk2(S.D, NDP_IMG128, ndp_img_off(tid, ch * 8, RS), d8);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int sh = (j & 1) * 16;
-                    const float d = ndp_bf16_to_f32((w0[j >> 1] >> sh) & 0xffffu) + ndp_bf16_to_f32((w1[j >> 1] >> sh) & 0xffffu) +
-                                    ndp_bf16_to_f32((w2[j >> 1] >> sh) & 0xffffu);
+                    const float d = d8[j] * dinv;
                     const int o = ch * 8 + j;
 #pragma unroll
                     for (int c = 0; c < 6; ++c) de[c] = fmaf(d, __ldg(wi + o * 6 + c), de[c]);

@@ -5,11 +5,11 @@
 //
 // The hidden 128x128 layers (the only GEMM-shaped work: M = 128 points fills one UMMA tile exactly)
 // run on the 5th-generation tensor cores: tcgen05.mma issued by ONE thread, operands in shared
-// memory as bf16 "tri-images" (ndp_tc.cuh: exact 3-way bf16 split, six partial products, fp32
+// memory as fp16 hi/lo image sets (ndp_tc.cuh: 2-way fp16 split, three partial products, fp32
 // accumulation in TMEM => fp32-level accuracy), accumulator [128 lanes x 128 columns] in TMEM, read
 // back with tcgen05.ld by 8 warps (warp w: lanes 32(w%4).., column half w/4) for the
 // bias + ReLU + re-split epilogue that writes the next layer's A operand in place.
-// Weight tri-images (96 KB/layer, maintained by the Adam kernel) arrive by TMA bulk copies
+// Weight image sets (64 KB/layer, maintained by the Adam kernel) arrive by TMA bulk copies
 // (cp.async.bulk + mbarrier) issued as soon as the previous layer's MMAs have retired; the saved
 // activations leave by TMA bulk stores straight from the operand images.  Input layer (K = 6), heads
 // (K = 128, N <= 11) and the per-point rotation / warp composition stay on the FP32 pipes.
@@ -25,8 +25,8 @@ __device__ unsigned long long ndp_dbg_fwd[64];
 #endif
 
 struct FwdTcSmem {
-    unsigned char A[NDP_TRI128];              // activation tri-image (operand A, K-major)
-    unsigned char B[NDP_TRI128];              // weight tri-image of the current layer (operand B, K-major)
+    unsigned char A[NDP_SET128];              // activation hi/lo images (operand A, K-major)
+    unsigned char B[NDP_SET128];              // weight hi/lo images of the current layer (operand B, K-major)
     float win[NDP_W * 6];
     float bin[NDP_W];
     float hw[NDP_MAX_HEAD * NDP_W];
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_fwd_tc_kernel(NdpFwdA
     const int LH = L.hidden, HD = L.head_dim;
     const int warp = tid >> 5, p = tid & (NDP_TP - 1), half = tid >> 7;
     unsigned char* gact = a.act ? (unsigned char*)a.act + ((long long)pair * a.act_stride) * 4 +
-                                      (long long)tile * (LH + 1) * NDP_TRI128 : nullptr;
+                                      (long long)tile * (LH + 1) * NDP_SET128 : nullptr;
 
     NDP_T(0);
     if (warp == 0) ndp_tmem_alloc_warp(&S.tmem_slot, 128);
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_fwd_tc_kernel(NdpFwdA
     ndp_tc_fence_after();
     NDP_T(1);
     const unsigned tmem = S.tmem_slot;
-    if (tid == 0 && LH > 0) ndp_stage_bulk(S.B, wimg, NDP_TRI128, &S.bar_w);
+    if (tid == 0 && LH > 0) ndp_stage_bulk(S.B, wimg, NDP_SET128, &S.bar_w);
 
     float hacc[NDP_MAX_HEAD];
 #pragma unroll
@@ -116,9 +116,9 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_fwd_tc_kernel(NdpFwdA
                 float s = S.bin[o0 + j];
 #pragma unroll
                 for (int c = 0; c < 6; ++c) s = fmaf(e[c], w[c], s);
-                v[j] = fmaxf(s, 0.0f);
+                v[j] = ndp_relu_img(s);
             }
-            ndp_store_chunk3(S.A, NDP_IMG128, ndp_img_off(p, o0, NDP_IMG_RS(128)), v);
+            ndp_store_chunk2(S.A, NDP_IMG128, ndp_img_off(p, o0, NDP_IMG_RS(128)), v);
             if (LH == 0) ndp_head_accum(hacc, S.hw, HD, v, o0);
         }
     }
@@ -126,18 +126,18 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_fwd_tc_kernel(NdpFwdA
     __syncthreads();
     NDP_T(2);
 
-    const unsigned idesc = ndp_idesc_bf16(128, 128, 0, 0);
+    const unsigned idesc = ndp_idesc_f16(128, 128, 0, 0);
     for (int l = 0; l < LH; ++l) {
-        // ---- h_{l+1} = relu(W_l h_l + b_l): six bf16 partial products into TMEM, one issuing thread
+        // ---- h_{l+1} = relu(W_l h_l + b_l): three fp16 partial products into TMEM, one issuing thread
         if (tid == 0) {
             if (gact) {      // save h_l for the backward pass straight from the operand image
-                for (int i = 0; i < 3; ++i) ndp_bulk_s2g(gact + (long long)l * NDP_TRI128 + i * NDP_IMG128, S.A + i * NDP_IMG128, NDP_IMG128);
+                for (int i = 0; i < 2; ++i) ndp_bulk_s2g(gact + (long long)l * NDP_SET128 + i * NDP_IMG128, S.A + i * NDP_IMG128, NDP_IMG128);
                 ndp_bulk_commit();
             }
             ndp_mbar_wait(&S.bar_w, (unsigned)(l & 1));
             NDP_T(8 + 4 * l);
             ndp_tc_fence_after();
-            ndp_umma_gemm6(tmem, ndp_umma_desc(S.A, NDP_IMG_CS, NDP_IMG_RS(128)), NDP_IMG128, 2 * NDP_IMG_CS,
+            ndp_umma_gemm3(tmem, ndp_umma_desc(S.A, NDP_IMG_CS, NDP_IMG_RS(128)), NDP_IMG128, 2 * NDP_IMG_CS,
                            ndp_umma_desc(S.B, NDP_IMG_CS, NDP_IMG_RS(128)), NDP_IMG128, 2 * NDP_IMG_CS, 8, idesc, false);
             ndp_umma_commit(&S.bar_mma);
         }
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_fwd_tc_kernel(NdpFwdA
         NDP_T(9 + 4 * l);
         if (tid == 0) {
             if (gact) ndp_bulk_wait_read0();                      // the store has finished reading A
-            if (l + 1 < LH) ndp_stage_bulk(S.B, wimg + (long long)(l + 1) * NDP_TRI128, NDP_TRI128, &S.bar_w);
+            if (l + 1 < LH) ndp_stage_bulk(S.B, wimg + (long long)(l + 1) * NDP_SET128, NDP_SET128, &S.bar_w);
         }
         __syncthreads();
         NDP_T(10 + 4 * l);
@@ -161,11 +161,11 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_fwd_tc_kernel(NdpFwdA
             for (int s8 = 0; s8 < 4; ++s8) {
                 float u[8];
                 const float4 b0 = __ldg((const float4*)(bias + col0 + s8 * 8)), b1 = __ldg((const float4*)(bias + col0 + s8 * 8 + 4));
-                u[0] = fmaxf(v[s8 * 8 + 0] + b0.x, 0.0f); u[1] = fmaxf(v[s8 * 8 + 1] + b0.y, 0.0f);
-                u[2] = fmaxf(v[s8 * 8 + 2] + b0.z, 0.0f); u[3] = fmaxf(v[s8 * 8 + 3] + b0.w, 0.0f);
-                u[4] = fmaxf(v[s8 * 8 + 4] + b1.x, 0.0f); u[5] = fmaxf(v[s8 * 8 + 5] + b1.y, 0.0f);
-                u[6] = fmaxf(v[s8 * 8 + 6] + b1.z, 0.0f); u[7] = fmaxf(v[s8 * 8 + 7] + b1.w, 0.0f);
-                ndp_store_chunk3(S.A, NDP_IMG128, ndp_img_off(p, col0 + s8 * 8, NDP_IMG_RS(128)), u);
+                u[0] = ndp_relu_img(v[s8 * 8 + 0] + b0.x); u[1] = ndp_relu_img(v[s8 * 8 + 1] + b0.y);
+                u[2] = ndp_relu_img(v[s8 * 8 + 2] + b0.z); u[3] = ndp_relu_img(v[s8 * 8 + 3] + b0.w);
+                u[4] = ndp_relu_img(v[s8 * 8 + 4] + b1.x); u[5] = ndp_relu_img(v[s8 * 8 + 5] + b1.y);
+                u[6] = ndp_relu_img(v[s8 * 8 + 6] + b1.z); u[7] = ndp_relu_img(v[s8 * 8 + 7] + b1.w);
+                ndp_store_chunk2(S.A, NDP_IMG128, ndp_img_off(p, col0 + s8 * 8, NDP_IMG_RS(128)), u);
                 if (l == LH - 1) ndp_head_accum(hacc, S.hw, HD, u, col0 + s8 * 8);
             }
         }
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_fwd_tc_kernel(NdpFwdA
         NDP_T(11 + 4 * l);
     }
     if (tid == 0 && gact) {      // top activation
-        for (int i = 0; i < 3; ++i) ndp_bulk_s2g(gact + (long long)LH * NDP_TRI128 + i * NDP_IMG128, S.A + i * NDP_IMG128, NDP_IMG128);
+        for (int i = 0; i < 2; ++i) ndp_bulk_s2g(gact + (long long)LH * NDP_SET128 + i * NDP_IMG128, S.A + i * NDP_IMG128, NDP_IMG128);
         ndp_bulk_commit();
     }
 

@@ -21,7 +21,7 @@ def build(force: bool = False) -> str:
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     os.makedirs(OUT, exist_ok=True)
-    flags = ["-O2", "-g", "-std=c++17", "-fPIC", "-DNDP_EMU", "-ffp-contract=off", "-mfma", "-pthread",
+    flags = ["-O2", "-g", "-std=c++17", "-fPIC", "-DNDP_EMU", "-ffp-contract=off", "-mfma", "-mf16c", "-pthread",
              "-Wno-unknown-pragmas", "-I", HERE, "-I", CSRC]
 
     def cc(src, lang_cuda):
