@@ -92,10 +92,13 @@ static inline void ndp_bulk_g2s(void* dst, const void* src, unsigned bytes, NdpM
     if (left == 0) __atomic_fetch_add((unsigned*)&b->phase, 1u, __ATOMIC_SEQ_CST);
 }
 static inline void ndp_mbar_wait(NdpMbar* b, unsigned parity) {
-    int us = 1;   // sleep instead of spinning: the emulated MMA runs in ONE of ~256 OS threads
+    int us = 1;   // sleep instead of spinning: the emulated MMA runs in ONE of the block's OS threads
+    long long slept = 0;
     while ((__atomic_load_n((unsigned*)&b->phase, __ATOMIC_SEQ_CST) & 1u) == parity) {
         std::this_thread::sleep_for(std::chrono::microseconds(us));
+        slept += us;
         if (us < 2000) us *= 2;
+        if (slept > 120LL * 1000 * 1000) { fprintf(stderr, "[emu] DEADLOCK in mbarrier wait (parity %u, thread %u)\n", parity, threadIdx.x); abort(); }
     }
 }
 static inline void ndp_fence_proxy_async() {}
@@ -126,6 +129,13 @@ __device__ __forceinline__ void ndp_mbar_wait(NdpMbar* b, unsigned parity) {
     __trap();
 }
 __device__ __forceinline__ void ndp_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+
+// Named barrier over `n` threads (a multiple of 32) of the CTA: bar.sync id, n  (id 1..15; 0 is __syncthreads)
+#ifdef NDP_EMU
+static inline void ndp_group_sync(int id, int n) { ndp_emu_named_sync(id, n); }
+#else
+__device__ __forceinline__ void ndp_group_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 #endif
 
 // Stage `bytes` (multiple of 16) with bulk copies of at most 32 KiB each; one thread calls this.

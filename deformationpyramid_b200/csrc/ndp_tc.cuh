@@ -157,6 +157,10 @@ static inline void ndp_tmem_ld32(unsigned taddr, float (&v)[32]) {
     const int col0 = (int)(taddr & 0xffff), lane = (int)(taddr >> 16) + (int)(threadIdx.x & 31);
     for (int j = 0; j < 32; ++j) v[j] = ndp_emu::tmem[lane][col0 + j];
 }
+static inline void ndp_tmem_ld16(unsigned taddr, float (&v)[16]) {
+    const int col0 = (int)(taddr & 0xffff), lane = (int)(taddr >> 16) + (int)(threadIdx.x & 31);
+    for (int j = 0; j < 16; ++j) v[j] = ndp_emu::tmem[lane][col0 + j];
+}
 static inline void ndp_bulk_s2g(void* g, const void* s, unsigned bytes) { memcpy(g, s, bytes); }
 static inline void ndp_bulk_commit() {}
 static inline void ndp_bulk_wait_read0() {}
@@ -206,6 +210,17 @@ __device__ __forceinline__ void ndp_tmem_ld32(unsigned taddr, float (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ void ndp_tmem_ld16(unsigned taddr, float (&v)[16]) {
+    unsigned r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
 }
 // bulk asynchronous copy shared -> global (TMA store, SASS UBLKCP) in the calling thread's bulk group
 __device__ __forceinline__ void ndp_bulk_s2g(void* g, const void* s, unsigned bytes) {

@@ -1,22 +1,26 @@
-// Kernel (1), tensor-core version: one pyramid level of the warp field over a tile of 128 points.
+// Kernel (1), tensor-core version: one pyramid level of the warp field over TWO tiles of 128 points
+// per CTA.
 //
 // Reference: model/nets.py:111-140 (NDPLayer.forward), :164-177 (posenc), :295-304 (MLP),
 //            :144-161 (get_Rotation), model/rigid_body.py.
 //
-// The hidden 128x128 layers (the only GEMM-shaped work: M = 128 points fills one UMMA tile exactly)
-// run on the 5th-generation tensor cores: tcgen05.mma issued by ONE thread, operands in shared
-// memory as fp16 hi/lo image sets (ndp_tc.cuh: 2-way fp16 split, three partial products, fp32
-// accumulation in TMEM => fp32-level accuracy), accumulator [128 lanes x 128 columns] in TMEM, read
-// back with tcgen05.ld by 8 warps (warp w: lanes 32(w%4).., column half w/4) for the
-// bias + ReLU + re-split epilogue that writes the next layer's A operand in place.
-// Weight image sets (64 KB/layer, maintained by the Adam kernel) arrive by TMA bulk copies
-// (cp.async.bulk + mbarrier) issued as soon as the previous layer's MMAs have retired; the saved
-// activations leave by TMA bulk stores straight from the operand images.  Input layer (K = 6), heads
-// (K = 128, N <= 11) and the per-point rotation / warp composition stay on the FP32 pipes.
+// Every contraction of the layer runs on the 5th-generation tensor cores (tcgen05.mma issued by ONE
+// thread per tile, fp32 accumulators in TMEM, operands in shared memory as fp16 hi/lo image sets --
+// ndp_tc.cuh: 2-way split, three partial products => fp32-level accuracy):
+//     input layer   h_0 = relu([e | 0] [W_in | 0]^T + b_in)     M = 128 points, N = 128, K = 16
+//     hidden layers h_l+1 = relu(h_l W_l^T + b_l)               M = 128, N = 128, K = 128
+//     heads         z = h_L W_h^T                               M = 128, N = 16,  K = 128
+// A CTA is two independent groups of 8 warps, one 128-point tile each, that share the weight images
+// (one 64 KB buffer, refilled by TMA bulk copies as soon as BOTH groups' MMAs of the previous layer
+// have retired): while one group's MMAs run, the other group's warps do the TMEM -> bias + ReLU ->
+// re-split epilogue that writes the next layer's A operand in place, so the tensor pipe and the
+// FP32 pipes overlap and the weight traffic per tile halves.  Saved activations leave by TMA bulk
+// stores straight from the operand images.  Only the per-point rotation / warp composition
+// (rigid_body.py) stays scalar.
 #include "ndp_kernels.h"
 #include "ndp_tc.cuh"
 
-// optional phase timestamps of CTA (0,0) (debug aid, read back through ndp_debug_phase_times)
+// optional phase timestamps of CTA (0,0), group 0 (debug aid, read back through ndp_debug_phase_times)
 #ifndef NDP_EMU
 __device__ unsigned long long ndp_dbg_fwd[64];
 #define NDP_T(i) do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ndp_dbg_fwd[i] = t_; } } while (0)
@@ -24,219 +28,222 @@ __device__ unsigned long long ndp_dbg_fwd[64];
 #define NDP_T(i) do {} while (0)
 #endif
 
+#define NDP_FWD_TC_THREADS 512
+#define NDP_GROUP 256                      // threads per tile group
+#define NDP_IMG16 NDP_IMG_BYTES(16)        // [128][16] fp16 image: 4096 bytes
+#define NDP_HWIMG (2 * NDP_IMG_RS(128))    // [16][128] fp16 image: 4096 bytes
+
 struct FwdTcSmem {
-    unsigned char A[NDP_SET128];              // activation hi/lo images (operand A, K-major)
-    unsigned char B[NDP_SET128];              // weight hi/lo images of the current layer (operand B, K-major)
-    float win[NDP_W * 6];
-    float bin[NDP_W];
-    float hw[NDP_MAX_HEAD * NDP_W];
+    unsigned char A[2][NDP_SET128];        // per group: activation hi/lo images (operand A, K-major); first the posenc image
+    unsigned char B[NDP_SET128];           // weight hi/lo images of the current hidden layer (operand B, K-major)
+    unsigned char WIN[2 * NDP_IMG16];      // [128 outputs][16]: cols 0..5 = W_in, rest 0 (operand B of the input layer)
+    unsigned char HW[2 * NDP_HWIMG];       // [16 head rows][128]: head weights, rows >= head_dim 0 (operand B of the heads)
+    float xs[2][NDP_TP * 4];
     float hb[16];
-    float es[NDP_TP * 8];
-    float xs[NDP_TP * 4];
-    float zpart[2 * NDP_TP * NDP_ZPITCH];
-    NdpMbar bar_w, bar_mma;
+    NdpMbar bar_w, bar_mma[2];
+    int bcount[NDP_MAX_HIDDEN];            // groups whose MMAs of hidden layer l have retired
     unsigned tmem_slot, pad[3];
 };
 size_t ndp_fwd_tc_smem_bytes() { return sizeof(FwdTcSmem) + 1024; }
 
-__device__ __forceinline__ void ndp_head_accum(float (&hacc)[NDP_MAX_HEAD], const float* hw, int HD, const float (&v)[8], int col0) {
-#pragma unroll
-    for (int r = 0; r < NDP_MAX_HEAD; ++r) {
-        if (r < HD) {
-            const float4 w0 = *(const float4*)(hw + r * NDP_W + col0), w1 = *(const float4*)(hw + r * NDP_W + col0 + 4);
-            float s = hacc[r];
-            s = fmaf(v[0], w0.x, s); s = fmaf(v[1], w0.y, s); s = fmaf(v[2], w0.z, s); s = fmaf(v[3], w0.w, s);
-            s = fmaf(v[4], w1.x, s); s = fmaf(v[5], w1.y, s); s = fmaf(v[6], w1.z, s); s = fmaf(v[7], w1.w, s);
-            hacc[r] = s;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_fwd_tc_kernel(NdpFwdArgs a) {
+__global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc_kernel(NdpFwdArgs a) {
     NDP_DYN_SMEM(smem_raw);
     FwdTcSmem& S = *(FwdTcSmem*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 
-    const int tid = threadIdx.x, pair = blockIdx.y, tile = blockIdx.x;
+    const int tid = threadIdx.x, pair = blockIdx.y;
+    const int g = tid >> 8, gt = tid & (NDP_GROUP - 1);          // tile group, thread within the group
+    const int tile = blockIdx.x * 2 + g;
     const int n = a.counts ? a.counts[pair] : a.n;
-    if (tile * NDP_TP >= n) return;
+    if (blockIdx.x * 2 * NDP_TP >= n) return;
     if (a.state && a.state[pair].stopped) return;
+    const bool active = tile * NDP_TP < n;
+    const int nactive = ((blockIdx.x * 2 + 1) * NDP_TP < n) ? 2 : 1;
     const NdpLayout& L = a.lay;
     const float* params = a.params + (long long)pair * a.params_stride;
     const unsigned char* wimg = (const unsigned char*)(a.pack + (long long)pair * a.pack_stride + L.pack_img);
     const int LH = L.hidden, HD = L.head_dim;
-    const int warp = tid >> 5, p = tid & (NDP_TP - 1), half = tid >> 7;
+    const int warp = tid >> 5, p = gt & (NDP_TP - 1), half = gt >> 7;
+    const int RS = NDP_IMG_RS(128), CS = NDP_IMG_CS, RS16 = NDP_IMG_RS(16);
     unsigned char* gact = a.act ? (unsigned char*)a.act + ((long long)pair * a.act_stride) * 4 +
                                       (long long)tile * (LH + 1) * NDP_SET128 : nullptr;
+    unsigned char* A = S.A[g];
+    float* xs = S.xs[g];
 
     NDP_T(0);
-    if (warp == 0) ndp_tmem_alloc_warp(&S.tmem_slot, 128);
-    if (tid == 0) { ndp_mbar_init(&S.bar_w, 1); ndp_mbar_init(&S.bar_mma, 1); }
-    // stage the small fp32 operands
-    for (int i = tid; i < NDP_W * 6; i += NDP_THREADS) S.win[i] = __ldg(params + L.off_w_in + i);
-    if (tid < NDP_W) S.bin[tid] = __ldg(params + L.off_b_in + tid);
-    for (int i = tid; i < HD * NDP_W; i += NDP_THREADS) S.hw[i] = __ldg(params + L.head_w[i >> 7] + (i & 127));
-    if (tid < HD) S.hb[tid] = __ldg(params + L.head_b[tid]);
-    if (tid < NDP_TP) {        // points + positional encoding (nets.py:164-177)
-        const int gp = tile * NDP_TP + tid;
+    if (warp == 0) ndp_tmem_alloc_warp(&S.tmem_slot, 256);
+    if (tid == 0) { ndp_mbar_init(&S.bar_w, 1); ndp_mbar_init(&S.bar_mma[0], 1); ndp_mbar_init(&S.bar_mma[1], 1); }
+    if (tid < NDP_MAX_HIDDEN) S.bcount[tid] = 0;
+    if (tid < 16) S.hb[tid] = (tid < HD) ? __ldg(params + L.head_b[tid]) : 0.0f;
+    if (tid < 256) {            // input-layer weight image: row o = tid / 2, 8-column chunk tid & 1
+        const int o = tid >> 1, c8 = tid & 1;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (c8 == 0 && j < 6) ? __ldg(params + L.off_w_in + o * 6 + j) : 0.0f;
+        ndp_store_chunk2(S.WIN, NDP_IMG16, ndp_img_off(o, c8 * 8, RS16), v);
+    } else {                    // head weight image: row r = (tid - 256) / 16, 8-column chunk (tid - 256) & 15
+        const int r = (tid - 256) >> 4, c8 = (tid - 256) & 15;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (r < HD) ? __ldg(params + L.head_w[r] + c8 * 8 + j) : 0.0f;   // head rows are not 16-byte aligned
+        ndp_store_chunk2(S.HW, NDP_HWIMG, ndp_img_off(r, c8 * 8, RS), v);
+    }
+    if (gt < NDP_TP) {          // points + positional encoding image (nets.py:164-177), in the head of A
+        const int gp = tile * NDP_TP + gt;
         float px = 0.0f, py = 0.0f, pz = 0.0f;
         if (gp < n) {
             const float* xp = a.x + (long long)pair * a.x_stride + (long long)gp * 3;
             px = __ldg(xp); py = __ldg(xp + 1); pz = __ldg(xp + 2);
         }
-        S.xs[tid * 4 + 0] = px; S.xs[tid * 4 + 1] = py; S.xs[tid * 4 + 2] = pz;
-        float s, c;
-        float* e = S.es + tid * 8;
-        sincosf(px * L.freq, &s, &c); e[0] = s; e[1] = c;
-        sincosf(py * L.freq, &s, &c); e[2] = s; e[3] = c;
-        sincosf(pz * L.freq, &s, &c); e[4] = s; e[5] = c;
+        xs[gt * 4 + 0] = px; xs[gt * 4 + 1] = py; xs[gt * 4 + 2] = pz;
+        float e0[8], e1[8], s, c;
+        sincosf(px * L.freq, &s, &c); e0[0] = s; e0[1] = c;
+        sincosf(py * L.freq, &s, &c); e0[2] = s; e0[3] = c;
+        sincosf(pz * L.freq, &s, &c); e0[4] = s; e0[5] = c;
+        e0[6] = 0.0f; e0[7] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e1[j] = 0.0f;
+        ndp_store_chunk2(A, NDP_IMG16, ndp_img_off(gt, 0, RS16), e0);
+        ndp_store_chunk2(A, NDP_IMG16, ndp_img_off(gt, 8, RS16), e1);
     }
     ndp_tc_fence_before();
+    ndp_fence_proxy_async();
     __syncthreads();
     ndp_tc_fence_after();
     NDP_T(1);
-    const unsigned tmem = S.tmem_slot;
+    const unsigned tmem = S.tmem_slot + (unsigned)g * 128u;
+    const unsigned tlane = tmem + ((unsigned)((warp & 3) * 32) << 16);
     if (tid == 0 && LH > 0) ndp_stage_bulk(S.B, wimg, NDP_SET128, &S.bar_w);
 
-    float hacc[NDP_MAX_HEAD];
-#pragma unroll
-    for (int r = 0; r < NDP_MAX_HEAD; ++r) hacc[r] = 0.0f;
-
-    // ---- input layer (K = 6) on the FP32 pipes: h0 = relu(W_in e + b_in)  (nets.py:75,114)
-    {
-        float e[6];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) e[c] = S.es[p * 8 + c];
-#pragma unroll 1
-        for (int ch = 0; ch < 8; ++ch) {
-            const int o0 = half * 64 + ch * 8;
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float* w = S.win + (o0 + j) * 6;
-                float s = S.bin[o0 + j];
-#pragma unroll
-                for (int c = 0; c < 6; ++c) s = fmaf(e[c], w[c], s);
-                v[j] = ndp_relu_img(s);
+    if (active) {
+        unsigned mph = 0;
+        // ---- stage s = 0: input layer; s = 1..LH: hidden layer s - 1.  Each stage: MMAs by the group's
+        //      thread 0, then the epilogue h = relu(acc + bias) re-split into the A images (in place).
+        for (int s = 0; s <= LH; ++s) {
+            if (gt == 0) {
+                if (s == 0) {
+                    ndp_umma_gemm3(tmem, ndp_umma_desc(A, CS, RS16), NDP_IMG16, 0, ndp_umma_desc(S.WIN, CS, RS16), NDP_IMG16, 0, 1,
+                                   ndp_idesc_f16(128, 128, 0, 0), false);
+                } else {
+                    if (gact) {      // save h_{s-1} for the backward pass straight from the operand images
+                        ndp_bulk_s2g(gact + (long long)(s - 1) * NDP_SET128, A, NDP_IMG128);
+                        ndp_bulk_s2g(gact + (long long)(s - 1) * NDP_SET128 + NDP_IMG128, A + NDP_IMG128, NDP_IMG128);
+                        ndp_bulk_commit();
+                    }
+                    ndp_mbar_wait(&S.bar_w, (unsigned)((s - 1) & 1));
+                    ndp_tc_fence_after();
+                    ndp_umma_gemm3(tmem, ndp_umma_desc(A, CS, RS), NDP_IMG128, 2 * CS, ndp_umma_desc(S.B, CS, RS), NDP_IMG128, 2 * CS, 8,
+                                   ndp_idesc_f16(128, 128, 0, 0), false);
+                }
+                ndp_umma_commit(&S.bar_mma[g]);
+                NDP_T(8 + 4 * s);
             }
-            ndp_store_chunk2(S.A, NDP_IMG128, ndp_img_off(p, o0, NDP_IMG_RS(128)), v);
-            if (LH == 0) ndp_head_accum(hacc, S.hw, HD, v, o0);
+            ndp_mbar_wait(&S.bar_mma[g], mph); mph ^= 1;
+            ndp_tc_fence_after();
+            NDP_T(9 + 4 * s);
+            if (gt == 0 && s > 0) {
+                if (gact) ndp_bulk_wait_read0();                  // the store has finished reading A
+                // the last group to retire hidden layer s - 1 refills the weight buffer with the next layer
+                if (s < LH && atomicAdd(&S.bcount[s - 1], 1) == nactive - 1)
+                    ndp_stage_bulk(S.B, wimg + (long long)s * NDP_SET128, NDP_SET128, &S.bar_w);
+            }
+            if (gact && s > 0) ndp_group_sync(1 + g, NDP_GROUP);  // A may be overwritten only after wait_read0
+            NDP_T(10 + 4 * s);
+            const float* bias = params + (s == 0 ? L.off_b_in : L.off_b[s - 1]);
+#pragma unroll 1
+            for (int c32 = 0; c32 < 2; ++c32) {
+                float v[32];
+                const int col0 = half * 64 + c32 * 32;
+                ndp_tmem_ld32(tlane + col0, v);
+#pragma unroll
+                for (int s8 = 0; s8 < 4; ++s8) {
+                    float u[8];
+                    const float4 b0 = __ldg((const float4*)(bias + col0 + s8 * 8)), b1 = __ldg((const float4*)(bias + col0 + s8 * 8 + 4));
+                    u[0] = ndp_relu_img(v[s8 * 8 + 0] + b0.x); u[1] = ndp_relu_img(v[s8 * 8 + 1] + b0.y);
+                    u[2] = ndp_relu_img(v[s8 * 8 + 2] + b0.z); u[3] = ndp_relu_img(v[s8 * 8 + 3] + b0.w);
+                    u[4] = ndp_relu_img(v[s8 * 8 + 4] + b1.x); u[5] = ndp_relu_img(v[s8 * 8 + 5] + b1.y);
+                    u[6] = ndp_relu_img(v[s8 * 8 + 6] + b1.z); u[7] = ndp_relu_img(v[s8 * 8 + 7] + b1.w);
+                    ndp_store_chunk2(A, NDP_IMG128, ndp_img_off(p, col0 + s8 * 8, RS), u);
+                }
+            }
+            ndp_tc_fence_before();
+            ndp_fence_proxy_async();
+            ndp_group_sync(1 + g, NDP_GROUP);
+            NDP_T(11 + 4 * s);
         }
-    }
-    ndp_fence_proxy_async();
-    __syncthreads();
-    NDP_T(2);
 
-    const unsigned idesc = ndp_idesc_f16(128, 128, 0, 0);
-    for (int l = 0; l < LH; ++l) {
-        // ---- h_{l+1} = relu(W_l h_l + b_l): three fp16 partial products into TMEM, one issuing thread
-        if (tid == 0) {
-            if (gact) {      // save h_l for the backward pass straight from the operand image
-                for (int i = 0; i < 2; ++i) ndp_bulk_s2g(gact + (long long)l * NDP_SET128 + i * NDP_IMG128, S.A + i * NDP_IMG128, NDP_IMG128);
+        // ---- heads on the tensor core: z_raw[128 points][16] = h_L W_h^T; top activation saved meanwhile
+        if (gt == 0) {
+            ndp_tc_fence_after();
+            if (gact) {
+                ndp_bulk_s2g(gact + (long long)LH * NDP_SET128, A, NDP_IMG128);
+                ndp_bulk_s2g(gact + (long long)LH * NDP_SET128 + NDP_IMG128, A + NDP_IMG128, NDP_IMG128);
                 ndp_bulk_commit();
             }
-            ndp_mbar_wait(&S.bar_w, (unsigned)(l & 1));
-            NDP_T(8 + 4 * l);
-            ndp_tc_fence_after();
-            ndp_umma_gemm3(tmem, ndp_umma_desc(S.A, NDP_IMG_CS, NDP_IMG_RS(128)), NDP_IMG128, 2 * NDP_IMG_CS,
-                           ndp_umma_desc(S.B, NDP_IMG_CS, NDP_IMG_RS(128)), NDP_IMG128, 2 * NDP_IMG_CS, 8, idesc, false);
-            ndp_umma_commit(&S.bar_mma);
+            ndp_umma_gemm3(tmem, ndp_umma_desc(A, CS, RS), NDP_IMG128, 2 * CS, ndp_umma_desc(S.HW, CS, RS), NDP_HWIMG, 2 * CS, 8,
+                           ndp_idesc_f16(128, 16, 0, 0), false);
+            ndp_umma_commit(&S.bar_mma[g]);
         }
-        ndp_mbar_wait(&S.bar_mma, (unsigned)(l & 1));
+        ndp_mbar_wait(&S.bar_mma[g], mph); mph ^= 1;
         ndp_tc_fence_after();
-        NDP_T(9 + 4 * l);
-        if (tid == 0) {
-            if (gact) ndp_bulk_wait_read0();                      // the store has finished reading A
-            if (l + 1 < LH) ndp_stage_bulk(S.B, wimg + (long long)(l + 1) * NDP_SET128, NDP_SET128, &S.bar_w);
-        }
-        __syncthreads();
-        NDP_T(10 + 4 * l);
-        // ---- epilogue: TMEM -> registers, bias + ReLU, re-split into the A images (in place)
-        const float* bias = params + L.off_b[l];
-#pragma unroll 1
-        for (int c32 = 0; c32 < 2; ++c32) {
-            float v[32];
-            const int col0 = half * 64 + c32 * 32;
-            ndp_tmem_ld32(tmem + ((unsigned)((warp & 3) * 32) << 16) + col0, v);
-#pragma unroll
-            for (int s8 = 0; s8 < 4; ++s8) {
-                float u[8];
-                const float4 b0 = __ldg((const float4*)(bias + col0 + s8 * 8)), b1 = __ldg((const float4*)(bias + col0 + s8 * 8 + 4));
-                u[0] = ndp_relu_img(v[s8 * 8 + 0] + b0.x); u[1] = ndp_relu_img(v[s8 * 8 + 1] + b0.y);
-                u[2] = ndp_relu_img(v[s8 * 8 + 2] + b0.z); u[3] = ndp_relu_img(v[s8 * 8 + 3] + b0.w);
-                u[4] = ndp_relu_img(v[s8 * 8 + 4] + b1.x); u[5] = ndp_relu_img(v[s8 * 8 + 5] + b1.y);
-                u[6] = ndp_relu_img(v[s8 * 8 + 6] + b1.z); u[7] = ndp_relu_img(v[s8 * 8 + 7] + b1.w);
-                ndp_store_chunk2(S.A, NDP_IMG128, ndp_img_off(p, col0 + s8 * 8, NDP_IMG_RS(128)), u);
-                if (l == LH - 1) ndp_head_accum(hacc, S.hw, HD, u, col0 + s8 * 8);
-            }
-        }
-        ndp_tc_fence_before();
-        ndp_fence_proxy_async();
-        __syncthreads();
-        NDP_T(11 + 4 * l);
-    }
-    if (tid == 0 && gact) {      // top activation
-        for (int i = 0; i < 2; ++i) ndp_bulk_s2g(gact + (long long)LH * NDP_SET128 + i * NDP_IMG128, S.A + i * NDP_IMG128, NDP_IMG128);
-        ndp_bulk_commit();
-    }
+        NDP_T(60);
 
-    // ---- heads: z = mlp_scale * (W_h h + b_h), the two column halves combined through smem
+        // ---- per-point rotation + warp composition (nets.py:119-137)
+        if (gt < NDP_TP) {
+            const int gp = tile * NDP_TP + gt;
+            const float INF = __int_as_float(0x7f800000);
+            float y[3] = {INF, INF, INF};
+            float zr[16];
+            ndp_tmem_ld16(tlane, zr);
+            if (gp < n) {
+                float z[NDP_MAX_HEAD], nu = 0.0f;
 #pragma unroll
-    for (int r = 0; r < NDP_MAX_HEAD; ++r) S.zpart[(half * NDP_TP + p) * NDP_ZPITCH + r] = hacc[r];
-    __syncthreads();
-
-    // ---- per-point rotation + warp composition (nets.py:119-137)
-    if (tid < NDP_TP) {
-        const int gp = tile * NDP_TP + tid;
-        const float INF = __int_as_float(0x7f800000);
-        float y[3] = {INF, INF, INF};
-        if (gp < n) {
-            float z[NDP_MAX_HEAD], nu = 0.0f;
-#pragma unroll
-            for (int r = 0; r < NDP_MAX_HEAD; ++r)
-                z[r] = (r < HD) ? L.mu * (S.zpart[tid * NDP_ZPITCH + r] + S.zpart[(NDP_TP + tid) * NDP_ZPITCH + r] + S.hb[r]) : 0.0f;
-            ndp_point_forward(L.motion, L.rot, L.nonrigid, z, S.xs + tid * 4, y, &nu);
-            if (a.y_add) {
-                const float* ya = a.y_add + (long long)pair * a.y_add_stride;
-                y[0] += ya[0]; y[1] += ya[1]; y[2] += ya[2];
+                for (int r = 0; r < NDP_MAX_HEAD; ++r) z[r] = (r < HD) ? L.mu * (zr[r] + S.hb[r]) : 0.0f;
+                ndp_point_forward(L.motion, L.rot, L.nonrigid, z, xs + gt * 4, y, &nu);
+                if (a.y_add) {
+                    const float* ya = a.y_add + (long long)pair * a.y_add_stride;
+                    y[0] += ya[0]; y[1] += ya[1]; y[2] += ya[2];
+                }
+                float* yp = a.y + (long long)pair * a.y_stride + (long long)gp * 3;
+                yp[0] = y[0]; yp[1] = y[1]; yp[2] = y[2];
+                if (a.nu && L.nonrigid) a.nu[(long long)pair * a.nu_stride + gp] = nu;
+                if (a.zsave) {
+                    float4* zp = (float4*)(a.zsave + (long long)pair * a.z_stride + (long long)gp * NDP_ZPITCH);
+                    zp[0] = make_float4(z[0], z[1], z[2], z[3]);
+                    zp[1] = make_float4(z[4], z[5], z[6], z[7]);
+                    zp[2] = make_float4(z[8], z[9], z[10], z[11]);
+                }
             }
-            float* yp = a.y + (long long)pair * a.y_stride + (long long)gp * 3;
-            yp[0] = y[0]; yp[1] = y[1]; yp[2] = y[2];
-            if (a.nu && L.nonrigid) a.nu[(long long)pair * a.nu_stride + gp] = nu;
-            if (a.zsave) {
-                float* zp = a.zsave + (long long)pair * a.z_stride + (long long)gp * NDP_ZPITCH;
-#pragma unroll
-                for (int r = 0; r < NDP_ZPITCH; ++r) zp[r] = z[r];
+            if (a.y4) {
+                const int o = (gp < n) ? a.orig[(long long)pair * a.orig_stride + gp] : 0x7fffffff;
+                a.y4[(long long)pair * a.y4_stride + gp] = make_float4(y[0], y[1], y[2], __int_as_float(o));
+                float l0 = y[0], l1 = y[1], l2 = y[2];
+                float h0 = (gp < n) ? y[0] : -INF, h1 = (gp < n) ? y[1] : -INF, h2 = (gp < n) ? y[2] : -INF;
+                for (int s = 16; s > 0; s >>= 1) {
+                    l0 = fminf(l0, __shfl_xor_sync(0xffffffffu, l0, s)); l1 = fminf(l1, __shfl_xor_sync(0xffffffffu, l1, s));
+                    l2 = fminf(l2, __shfl_xor_sync(0xffffffffu, l2, s)); h0 = fmaxf(h0, __shfl_xor_sync(0xffffffffu, h0, s));
+                    h1 = fmaxf(h1, __shfl_xor_sync(0xffffffffu, h1, s)); h2 = fmaxf(h2, __shfl_xor_sync(0xffffffffu, h2, s));
+                }
+                if ((gt & 31) == 0 && gp < n) {
+                    float* bx = a.ybox + ((long long)pair * a.box_stride + (gp >> 5)) * 8;
+                    bx[0] = l0; bx[1] = l1; bx[2] = l2; bx[3] = 0.0f; bx[4] = h0; bx[5] = h1; bx[6] = h2; bx[7] = 0.0f;
+                }
             }
         }
-        if (a.y4) {
-            const int o = (gp < n) ? a.orig[(long long)pair * a.orig_stride + gp] : 0x7fffffff;
-            a.y4[(long long)pair * a.y4_stride + gp] = make_float4(y[0], y[1], y[2], __int_as_float(o));
-            float l0 = y[0], l1 = y[1], l2 = y[2];
-            float h0 = (gp < n) ? y[0] : -INF, h1 = (gp < n) ? y[1] : -INF, h2 = (gp < n) ? y[2] : -INF;
-            for (int s = 16; s > 0; s >>= 1) {
-                l0 = fminf(l0, __shfl_xor_sync(0xffffffffu, l0, s)); l1 = fminf(l1, __shfl_xor_sync(0xffffffffu, l1, s));
-                l2 = fminf(l2, __shfl_xor_sync(0xffffffffu, l2, s)); h0 = fmaxf(h0, __shfl_xor_sync(0xffffffffu, h0, s));
-                h1 = fmaxf(h1, __shfl_xor_sync(0xffffffffu, h1, s)); h2 = fmaxf(h2, __shfl_xor_sync(0xffffffffu, h2, s));
-            }
-            if ((tid & 31) == 0 && gp < n) {
-                float* bx = a.ybox + ((long long)pair * a.box_stride + (gp >> 5)) * 8;
-                bx[0] = l0; bx[1] = l1; bx[2] = l2; bx[3] = 0.0f; bx[4] = h0; bx[5] = h1; bx[6] = h2; bx[7] = 0.0f;
-            }
-        }
+        NDP_T(61);
+        if (gt == 0 && gact) ndp_bulk_wait0();     // smem must outlive the bulk stores
+        NDP_T(62);
     }
-    NDP_T(61);
-    if (tid == 0 && gact) ndp_bulk_wait0();     // smem must outlive the bulk stores
-    NDP_T(62);
     ndp_tc_fence_before();
     __syncthreads();
     NDP_T(63);
-    if (warp == 0) ndp_tmem_dealloc(tmem, 128);
+    if (warp == 0) ndp_tmem_dealloc(S.tmem_slot, 256);
 }
 
 void ndp_launch_fwd_tc(const NdpFwdArgs& a, cudaStream_t s) {
     if (a.npairs <= 0 || a.n <= 0) return;
-    dim3 grid((a.n + NDP_TP - 1) / NDP_TP, a.npairs);
-    NDP_LAUNCH(ndp_warp_fwd_tc_kernel, grid, dim3(NDP_THREADS), ndp_fwd_tc_smem_bytes(), s, a);
+    const int tiles = (a.n + NDP_TP - 1) / NDP_TP;
+    dim3 grid((tiles + 1) / 2, a.npairs);
+    NDP_LAUNCH(ndp_warp_fwd_tc_kernel, grid, dim3(NDP_FWD_TC_THREADS), ndp_fwd_tc_smem_bytes(), s, a);
 }
 
 int ndp_fwd_tc_init() {

@@ -5,6 +5,7 @@ namespace ndp_emu {
 
 thread_local Ctx ctx;
 Barrier block_barrier;
+Barrier named_barriers[16];
 std::vector<Barrier*> warp_barriers;
 std::vector<uint64_t> warp_slots;
 unsigned char* dyn_smem_ptr = nullptr;
@@ -12,9 +13,11 @@ float tmem[128][512];
 static size_t dyn_smem_cap = 0;
 
 void prepare(unsigned nthreads, size_t smem) {
+    block_barrier.name = "__syncthreads / block end";
+    for (int i = 0; i < 16; ++i) named_barriers[i].name = "named barrier";
     block_barrier.reset((int)nthreads);
     unsigned nwarps = (nthreads + 31) / 32;
-    while (warp_barriers.size() < nwarps) warp_barriers.push_back(new Barrier());
+    while (warp_barriers.size() < nwarps) { warp_barriers.push_back(new Barrier()); warp_barriers.back()->name = "warp barrier"; }
     for (unsigned w = 0; w < nwarps; ++w) {
         unsigned lanes = (w + 1) * 32 <= nthreads ? 32 : nthreads - w * 32;
         warp_barriers[w]->reset((int)lanes);

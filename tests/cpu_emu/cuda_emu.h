@@ -58,11 +58,25 @@ struct Barrier {
     int count = 0, waiting = 0;
     uint64_t gen = 0;
     void reset(int n) { count = n; waiting = 0; }
+    const char* name = "barrier";
+    void stuck(int have) {   // watchdog: a protocol error becomes a diagnosable abort instead of a hung test
+        fprintf(stderr, "[emu] DEADLOCK at %s: %d of %d threads arrived (block %u %u %u, thread %u)\n", name, have, count,
+                0u, 0u, 0u, 0u);
+        fflush(stderr);
+        abort();
+    }
     void wait() {
         std::unique_lock<std::mutex> lk(mu);
         uint64_t g = gen;
         if (++waiting == count) { waiting = 0; ++gen; cv.notify_all(); }
-        else cv.wait(lk, [&] { return gen != g; });
+        else if (!cv.wait_for(lk, std::chrono::seconds(120), [&] { return gen != g; })) stuck(waiting);
+    }
+    void wait_n(int n) {      // named barrier: every participant passes the same thread count
+        std::unique_lock<std::mutex> lk(mu);
+        count = n;
+        uint64_t g = gen;
+        if (++waiting == count) { waiting = 0; ++gen; cv.notify_all(); }
+        else if (!cv.wait_for(lk, std::chrono::seconds(120), [&] { return gen != g; })) stuck(waiting);
     }
 };
 
@@ -73,6 +87,7 @@ struct Ctx {
 };
 extern thread_local Ctx ctx;
 extern Barrier block_barrier;
+extern Barrier named_barriers[16];
 extern std::vector<Barrier*> warp_barriers;
 extern std::vector<uint64_t> warp_slots;   // [warp][32]
 extern unsigned char* dyn_smem_ptr;
@@ -85,6 +100,7 @@ template <class K, class... A>
 void launch(K kernel, dim3 grid, dim3 block, size_t smem, A... args) {
     unsigned nthreads = block.x * block.y * block.z;
     prepare(nthreads, smem);
+    if (getenv("NDP_EMU_TRACE")) { fprintf(stderr, "[emu] launch %p grid %u %u %u block %u\n", (void*)kernel, grid.x, grid.y, grid.z, nthreads); fflush(stderr); }
     std::vector<std::thread> pool;
     pool.reserve(nthreads);
     for (unsigned t = 0; t < nthreads; ++t) {
@@ -115,6 +131,7 @@ unsigned warp_ballot(int pred);
 #define gridDim (ndp_emu::ctx.gdim)
 
 static inline void __syncthreads() { ndp_emu::block_barrier.wait(); }
+static inline void ndp_emu_named_sync(int id, int n) { ndp_emu::named_barriers[id & 15].wait_n(n); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { ndp_emu::warp_barriers[ndp_emu::ctx.warp]->wait(); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
