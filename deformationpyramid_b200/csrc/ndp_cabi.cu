@@ -72,7 +72,7 @@ extern "C" int64_t ndp_saved_floats(const ndp_layer_cfg* c, int64_t n) {
 extern "C" int64_t ndp_backward_workspace_bytes(const ndp_layer_cfg* c, int64_t n) {
     if (check_cfg(c)) return -1;
     const long long tiles = n > 0 ? (n + NDP_TP - 1) / NDP_TP : 1;
-    return tiles * pad4(layout_of(c).param_count) * (long long)sizeof(float);
+    return tiles * (pad4(layout_of(c).param_count) + NDP_HGREC) * (long long)sizeof(float);
 }
 
 // ---- nearest-neighbour launch plan -------------------------------------------------------------
@@ -156,6 +156,7 @@ extern "C" int ndp_layer_backward(const ndp_layer_cfg* c, const float* params, c
     b.gnu = grad_nu; b.gnu_stride = 0;
     b.partials = (float*)workspace; b.partials_stride = 0; b.partial_pitch = (int)pad4(L.param_count);
     b.gx = grad_x; b.gx_stride = 0; b.n = (int)n; b.counts = nullptr; b.state = nullptr; b.npairs = 1;
+    b.hgbuf = (float*)workspace + ((n + NDP_TP - 1) / NDP_TP) * (long long)b.partial_pitch; b.hgbuf_stride = 0;
     if (g_mlp_mode == 0) ndp_launch_bwd_tc(b, (cudaStream_t)stream); else ndp_launch_bwd(b, (cudaStream_t)stream);
     NdpAdamArgs r;
     r.lay = L; r.params = nullptr; r.params_stride = 0; r.pack = nullptr; r.pack_stride = 0;
@@ -243,7 +244,7 @@ struct ndp_solver {
     float *means = nullptr, *smp[2] = {nullptr, nullptr}, *tsmp = nullptr;
     int *perm_s = nullptr, *perm_t = nullptr, *ncount = nullptr, *mcount = nullptr, *nscount = nullptr, *ntcount = nullptr;
     float *params = nullptr, *pack = nullptr, *adam_m = nullptr, *adam_v = nullptr;
-    float *act = nullptr, *zsave = nullptr, *gx = nullptr, *partials = nullptr, *loss = nullptr, *loss_hist = nullptr;
+    float *act = nullptr, *zsave = nullptr, *gx = nullptr, *partials = nullptr, *hgbuf = nullptr, *loss = nullptr, *loss_hist = nullptr;
     unsigned long long* gacc = nullptr;
     float2* nnpart = nullptr;
     // culled NN search (nn_mode 0): Morton order, float4 copies, block boxes, previous-NN seeds
@@ -327,7 +328,7 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
     DA(perm_s, B * S); DA(perm_t, B * S); DA(ncount, B); DA(mcount, B); DA(nscount, B); DA(ntcount, B);
     DA(params, B * c->levels * s->Ppad); DA(pack, B * s->packn); DA(adam_m, B * s->Ppad); DA(adam_v, B * s->Ppad);
     DA(act, B * s->act_pair); DA(zsave, B * S * NDP_ZPITCH); DA(gx, B * S * 3); DA(gacc, B * S * 3);
-    DA(partials, B * s->tiles * s->Ppad); DA(loss, B);
+    DA(partials, B * s->tiles * s->Ppad); DA(hgbuf, B * s->tiles * (long long)NDP_HGREC); DA(loss, B);
     DA(nnpart, B * 2 * s->plan.chunks * s->plan.qpitch); DA(blocksums, B * s->plan.blocks * 2); DA(counters, B);
     DA(state, B);
     if (c->nn_mode == 0) {
@@ -445,6 +446,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         b.gacc = s->gacc; b.gacc_stride = S * 3; b.m = s->S; b.mcounts = s->mcount; b.gnu = nullptr; b.gnu_stride = 0;
         b.partials = s->partials; b.partials_stride = (long long)s->tiles * s->Ppad; b.partial_pitch = s->Ppad;
         b.gx = nullptr; b.gx_stride = 0; b.n = s->S; b.counts = s->ncount; b.state = s->state; b.npairs = npairs;
+        b.hgbuf = s->hgbuf; b.hgbuf_stride = (long long)s->tiles * NDP_HGREC;
 
         NdpAdamArgs ad;
         ad.lay = L; ad.params = lvl_params; ad.params_stride = pstride; ad.pack = s->pack; ad.pack_stride = s->packn;
@@ -476,7 +478,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
             if (prof) CK(cudaEventRecord(ev[4], st));
             ndp_launch_adam(ad, st);
             if (prof) CK(cudaEventRecord(ev[5], st));
-            s->launches += 5;
+            s->launches += (s->mlp_mode == 0) ? 6 : 5;
             if ((it + 1) % poll == 0 && it + 1 < c.iters) {
                 CK(cudaMemcpyAsync(s->h_state, s->state, sizeof(NdpPairState) * npairs, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));

@@ -26,14 +26,14 @@ struct NdpFwdArgs {
     int npairs;
 };
 void ndp_launch_fwd(const NdpFwdArgs& a, cudaStream_t s);      // FP32-pipe version (act: fp32 [L+1][n][128])
-// tensor-core version: act = [tile][L+1] bf16 tri-images (98304 bytes each), act_stride in floats per pair
+// tensor-core version: act = [tile][L+1] fp16 hi/lo image sets (65536 bytes each), act_stride in floats per pair
 void ndp_launch_fwd_tc(const NdpFwdArgs& a, cudaStream_t s);
 
 // ---- kernel (3a): backward of kernel (1) -> per-tile parameter-gradient partials -----------------
 struct NdpBwdArgs {
     NdpLayout lay;
     const float* params; long long params_stride;
-    const float* pack;   long long pack_stride;       // tensor-core version only (weight tri-images)
+    const float* pack;   long long pack_stride;       // tensor-core version only (weight image sets)
     const float* x;      long long x_stride;
     const float* act;    long long act_stride; long long act_layer_stride;
     const float* zsave;  long long z_stride;
@@ -43,12 +43,14 @@ struct NdpBwdArgs {
     const float* gnu;    long long gnu_stride;        // dL/dnu [pair][n] or null
     float* partials;     long long partials_stride; int partial_pitch;   // [pair][tile][pitch]
     float* gx;           long long gx_stride;         // dL/dx [pair][n][3] or null
+    float* hgbuf;        long long hgbuf_stride;      // tensor-core version: per-tile head-gradient records [pair][tile][NDP_HGREC]
     int n; const int* counts;
     const NdpPairState* state;
     int npairs;
 };
+#define NDP_HGREC (NDP_TP * 24)    // floats per tile: hg[128][16], e[128][8] (e[0][7] = tile max |hg|)
 void ndp_launch_bwd(const NdpBwdArgs& a, cudaStream_t s);
-void ndp_launch_bwd_tc(const NdpBwdArgs& a, cudaStream_t s);   // needs `pack` (weight tri-images)
+void ndp_launch_bwd_tc(const NdpBwdArgs& a, cudaStream_t s);   // needs `pack` (weight image sets)
 
 // ---- kernel (3b): fixed-order reduction of the partials + Adam + transposed-copy refresh ---------
 struct NdpAdamArgs {

@@ -4,19 +4,24 @@
 // Replaces the autograd backward of NDPLayer.forward (model/nets.py:111-140) that the reference
 // runs in loss.backward() (model/registration.py:236).
 //
-// Every reduction over the tile's 128 points is a tcgen05 GEMM with K = points (operands as fp16
-// hi/lo image sets, fp32 accumulation in TMEM, see ndp_tc.cuh), issued by one thread:
-//     head grads   dW_h  = hg^T h_L          A = hg image   (MN-major)  B = h_L   (MN-major)
-//     weight grads dW_l  = delta^T h_l       A = delta      (MN-major)  B = h_l   (MN-major)
-//     bias grads   db_l  = delta^T 1         A = delta      (MN-major)  B = E[:,6] = 1
-//     input layer  dW_in = delta_0^T e       A = delta_0    (MN-major)  B = E[:,0:6] = posenc
-//     back-prop    delta_l = (delta W_l).relu'   A = delta  (K-major)   B = W_l   (MN-major)
+// Every contraction is a tcgen05 GEMM (operands as fp16 hi/lo image sets, fp32 accumulation in
+// TMEM, see ndp_tc.cuh) issued by one thread; reductions over the tile's points have K = points:
+//     delta at top  delta_L = (hg W_h) . relu'(h_L)     A = hg image   (K-major)   B = W_h   (MN-major)
+//     head grads    dW_h^T = h_L^T hg                   A = h_L        (MN-major)  B = hg    (MN-major)
+//                   db_h   = hg^T 1                     A = hg         (MN-major)  B = E[:,6] = 1
+//     weight grads  dW_l  = delta^T h_l                 A = delta      (MN-major)  B = h_l   (MN-major)
+//     bias grads    db_l  = delta^T 1                   A = delta      (MN-major)  B = E[:,6] = 1
+//     back-prop     delta_l = (delta W_l) . relu'(h_l)  A = delta      (K-major)   B = W_l   (MN-major)
+//     input layer   dW_in = delta_0^T e                 A = delta_0    (MN-major)  B = E[:,0:6] = posenc
 // The SAME delta image is the MN-major operand of the dW products and the K-major operand of the
 // back-propagation product, and the SAME weight image serves forward and backward (the core-matrix
-// layout is both canonical UMMA layouts at once), so nothing is ever transposed.  h_l image sets
-// come back from HBM by TMA bulk copies exactly as the forward kernel's bulk stores wrote them;
-// the weight image of the layer replaces h_l in shared memory as soon as the dW MMAs retire,
-// overlapping with the TMEM -> HBM epilogue of dW.  No atomics: one partial row per tile.
+// layout is both canonical UMMA layouts at once), so nothing is ever transposed.  h_l and W_l image
+// sets arrive by TMA bulk copies (exactly as the forward kernel's bulk stores / the Adam kernel
+// wrote them) into two dedicated buffers, both requested as soon as the previous layer's MMAs have
+// retired, so that per layer ONE batch of MMAs (dW_l, db_l, delta_l) is issued back to back; the
+// dW accumulators are double buffered in TMEM and drained to HBM by all 16 warps while the next
+// layer's MMAs run.  Deltas are carried multiplied by the tile's power-of-two scale (fp16 range).
+// No atomics: one partial row per tile.
 #include "ndp_kernels.h"
 #include "ndp_tc.cuh"
 
@@ -28,61 +33,65 @@ __device__ unsigned long long ndp_dbg_bwd[64];
 #define NDP_T(i) do {} while (0)
 #endif
 
-#define NDP_IMG16 NDP_IMG_BYTES(16)     // [128][16] fp16 image: 4096 bytes
+#define NDP_BWD_TC_THREADS 544              // 16 worker warps + 1 warp whose lane 0 issues every MMA / TMA copy
+#define NDP_IMG16 NDP_IMG_BYTES(16)        // [128][16] fp16 image: 4096 bytes
+#define NDP_HWIMG (2 * NDP_IMG_RS(128))    // [16][128] fp16 image: 4096 bytes
 struct BwdTcSmem {
     unsigned char D[NDP_SET128];        // delta hi/lo images (scaled by the tile's power of two)
-    unsigned char X[NDP_SET128];        // h_l images, then W_l images
-    unsigned char HG[2 * NDP_IMG16];    // [128 points][16]: mlp_scale * dL/dz (head gradients); must precede E:
-    unsigned char E[2 * NDP_IMG16];     // [128 points][16]: cols 0..5 positional encoding, col 6 = 1
-    float hw[NDP_MAX_HEAD * NDP_W];     // head weights (fp32), rows >= head_dim zero
-    float xs[NDP_TP * 4];
-    float gxs[NDP_TP * 4];
-    float red[4];                       // per-warp max |head gradient| of the tile
-    NdpMbar bar_x, bar_mma;
+    unsigned char H[NDP_SET128];        // h_l images
+    unsigned char W[NDP_SET128];        // W_l images
+    unsigned char HG[2 * NDP_IMG16];    // [128 points][16]: scaled mlp_scale * dL/dz (head gradients)
+    unsigned char E[2 * NDP_IMG16];     // [128 points][16]: cols 0..5 positional encoding, rest 0
+    unsigned char HW[2 * NDP_HWIMG];    // [16 head rows][128]: head weights, rows >= head_dim zero
+    float dbred[4][NDP_W];              // per lane-quarter column sums of delta (bias gradients)
+    NdpMbar bar_h, bar_w, bar_mma;
     unsigned tmem_slot, pad[3];
 };
 size_t ndp_bwd_tc_smem_bytes() { return sizeof(BwdTcSmem) + 128; }
 
-#define TM_DW 0u
-#define TM_DH 128u
-#define TM_SM 256u
+// TMEM columns
+#define TM_DH 0u                                 // delta_l accumulator                  [128 points][128]
+#define TM_DW(b) (128u + 128u * (unsigned)(b))   // dW_l^T accumulators, double buffered [128 i][128 o]
+#define TM_HDW 384u                              // dW_h^T                               [128 i][16 head rows]
+#define TM_DIN 400u                              // delta_0^T E: cols 0..5 = dW_in       [128 o][16]
 
-__global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdArgs a) {
-    NDP_DYN_SMEM(smem_raw);
-    BwdTcSmem& S = *(BwdTcSmem*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+// Column sums over the 32 lanes of a warp of v[0..31] (one row per lane): lane c returns the sum of
+// column c.  Halving butterfly: 31 shuffles, fixed order (deterministic).
+__device__ __forceinline__ float ndp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < off; ++j) {
+            const float send = upper ? v[j] : v[j + off];
+            const float keep = upper ? v[j + off] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
 
+// ---- kernel (3a-0): per point dL/dy -> dL/dz (head gradients), positional encoding, tile maximum ----
+// One CTA of 128 threads per tile, full occupancy (the per-point chain of dependent global loads,
+// fp64 fixed-point conversion and rotation backward is latency bound and would otherwise sit at the
+// head of every tensor-core CTA).  Record per tile (NDP_HGREC floats): hg[128][16], e[128][8]
+// (e[0][7] = the tile's max |hg|).  db_h = sum_p hg[p] goes straight to the tile's partial row.
+__global__ void __launch_bounds__(NDP_TP) ndp_head_grad_kernel(NdpBwdArgs a) {
+    __shared__ float red[4];
+    __shared__ float hsum[4][NDP_MAX_HEAD];
     const int tid = threadIdx.x, pair = blockIdx.y, tile = blockIdx.x;
     const int n = a.counts ? a.counts[pair] : a.n;
     if (tile * NDP_TP >= n) return;
     if (a.state && a.state[pair].stopped) return;
     const NdpLayout& L = a.lay;
-    const float* params = a.params + (long long)pair * a.params_stride;
-    const unsigned char* wimg = (const unsigned char*)(a.pack + (long long)pair * a.pack_stride + L.pack_img);
-    const int LH = L.hidden, HD = L.head_dim;
-    const unsigned char* gact = (const unsigned char*)a.act + ((long long)pair * a.act_stride) * 4 +
-                                (long long)tile * (LH + 1) * NDP_SET128;
+    const int HD = L.head_dim;
+    const int warp = tid >> 5, lane = tid & 31;
+    float* rec = a.hgbuf + (long long)pair * a.hgbuf_stride + (long long)tile * NDP_HGREC;
     float* part = a.partials + (long long)pair * a.partials_stride + (long long)tile * a.partial_pitch;
-    const int warp = tid >> 5, lane = tid & 31, p = tid & (NDP_TP - 1), half = tid >> 7;
-    const int RS = NDP_IMG_RS(128), CS = NDP_IMG_CS, RS16 = NDP_IMG_RS(16);
-    unsigned xph = 0, mph = 0;
-    NDP_T(0);
-
-    if (warp == 0) ndp_tmem_alloc_warp(&S.tmem_slot, 512);
-    if (tid == 0) { ndp_mbar_init(&S.bar_x, 1); ndp_mbar_init(&S.bar_mma, 1); }
-    for (int i = tid; i < NDP_MAX_HEAD * NDP_W; i += NDP_THREADS)
-        S.hw[i] = ((i >> 7) < HD) ? __ldg(params + L.head_w[i >> 7] + (i & 127)) : 0.0f;
-    ndp_tc_fence_before();
-    __syncthreads();
-    ndp_tc_fence_after();
-    NDP_T(1);
-    const unsigned tmem = S.tmem_slot;
-    const unsigned tlane = tmem + ((unsigned)((warp & 3) * 32) << 16);
-    if (tid == 0) ndp_stage_bulk(S.X, gact + (long long)LH * NDP_SET128, NDP_SET128, &S.bar_x);      // h_L
-
-    // ---- per point: dL/dy -> dL/dz (heads) and the direct part of dL/dx; E and head-gradient images
     float hgv[16], e0[8];
 #pragma unroll
     for (int r = 0; r < 16; ++r) hgv[r] = 0.0f;
+    {
     if (tid < NDP_TP) {
         const int gp = tile * NDP_TP + tid;
         float gz[NDP_MAX_HEAD];
@@ -117,200 +126,248 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
 #pragma unroll
         for (int r = 0; r < NDP_MAX_HEAD; ++r) { hgv[r] = L.mu * gz[r]; mx = fmaxf(mx, fabsf(hgv[r])); }
         for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
-        if (lane == 0) S.red[warp] = mx;
-        S.xs[tid * 4 + 0] = x[0]; S.xs[tid * 4 + 1] = x[1]; S.xs[tid * 4 + 2] = x[2];
-        S.gxs[tid * 4 + 0] = gxd[0]; S.gxs[tid * 4 + 1] = gxd[1]; S.gxs[tid * 4 + 2] = gxd[2];
+        if (lane == 0) red[warp] = mx;
+        if (a.gx && gp < n) {   // direct part of dL/dx; the tensor-core kernel adds the path through the encoding
+            float* gxp = a.gx + (long long)pair * a.gx_stride + (long long)gp * 3;
+            gxp[0] = gxd[0]; gxp[1] = gxd[1]; gxp[2] = gxd[2];
+        }
         float s, c;
         sincosf(x[0] * L.freq, &s, &c); e0[0] = s; e0[1] = c;
         sincosf(x[1] * L.freq, &s, &c); e0[2] = s; e0[3] = c;
         sincosf(x[2] * L.freq, &s, &c); e0[4] = s; e0[5] = c;
-        e0[6] = 1.0f; e0[7] = 0.0f;
+        e0[6] = 0.0f; e0[7] = 0.0f;
     }
+
+    }
+    // db_h[r] = sum over the tile's points (fixed order: lanes by butterfly, then warps 0..3)
+#pragma unroll
+    for (int r = 0; r < NDP_MAX_HEAD; ++r) {
+        float sv = hgv[r];
+        for (int s = 16; s > 0; s >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, s);
+        if (lane == 0) hsum[warp][r] = sv;
+    }
+    float4* hp = (float4*)(rec + tid * 16);
+    hp[0] = make_float4(hgv[0], hgv[1], hgv[2], hgv[3]);   hp[1] = make_float4(hgv[4], hgv[5], hgv[6], hgv[7]);
+    hp[2] = make_float4(hgv[8], hgv[9], hgv[10], hgv[11]); hp[3] = make_float4(hgv[12], hgv[13], hgv[14], hgv[15]);
     __syncthreads();
+    if (tid == 0) e0[7] = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    float4* ep = (float4*)(rec + NDP_TP * 16 + tid * 8);
+    ep[0] = make_float4(e0[0], e0[1], e0[2], e0[3]); ep[1] = make_float4(e0[4], e0[5], e0[6], e0[7]);
+    if (tid < HD) part[L.head_b[tid]] = (hsum[0][tid] + hsum[1][tid]) + (hsum[2][tid] + hsum[3][tid]);
+}
+
+__global__ void __launch_bounds__(NDP_BWD_TC_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdArgs a) {
+    NDP_DYN_SMEM(smem_raw);
+    BwdTcSmem& S = *(BwdTcSmem*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+
+    const int tid = threadIdx.x, pair = blockIdx.y, tile = blockIdx.x;
+    const int n = a.counts ? a.counts[pair] : a.n;
+    if (tile * NDP_TP >= n) return;
+    if (a.state && a.state[pair].stopped) return;
+    const NdpLayout& L = a.lay;
+    const float* params = a.params + (long long)pair * a.params_stride;
+    const unsigned char* wimg = (const unsigned char*)(a.pack + (long long)pair * a.pack_stride + L.pack_img);
+    const int LH = L.hidden, HD = L.head_dim;
+    const unsigned char* gact = (const unsigned char*)a.act + ((long long)pair * a.act_stride) * 4 +
+                                (long long)tile * (LH + 1) * NDP_SET128;
+    float* part = a.partials + (long long)pair * a.partials_stride + (long long)tile * a.partial_pitch;
+    // thread -> TMEM lane quarter q (hardware: warp % 4), row p = 32 q + lane, column quarter cq
+    const int warp = tid >> 5, lane = tid & 31, q = warp & 3, cq = warp >> 2, p = q * 32 + lane;
+    const bool wk = tid < 512, iss = tid == 512;   // workers (epilogues, drains) / the issuing thread
+    const int RS = NDP_IMG_RS(128), CS = NDP_IMG_CS, RS16 = NDP_IMG_RS(16);
+    unsigned hph = 0, wph = 0, mph = 0;
+    NDP_T(0);
+
+    if (warp == 0) ndp_tmem_alloc_warp(&S.tmem_slot, 512);
+    if (iss) {                  // barriers, and the first operands requested before anything else
+        ndp_mbar_init(&S.bar_h, 1); ndp_mbar_init(&S.bar_w, 1); ndp_mbar_init(&S.bar_mma, 1);
+        ndp_stage_bulk(S.H, gact + (long long)LH * NDP_SET128, NDP_SET128, &S.bar_h);                 // h_L
+        if (LH > 0) ndp_stage_bulk(S.W, wimg + (long long)(LH - 1) * NDP_SET128, NDP_SET128, &S.bar_w);   // W_{L-1}
+    }
     // the tile's delta scale: an exact power of two that brings the largest head gradient into [1, 2)
     // (fp16 operand range, see ndp_tc.cuh); undone when the gradients leave TMEM
+    const float* rec = a.hgbuf + (long long)pair * a.hgbuf_stride + (long long)tile * NDP_HGREC;
     float dscale, dinv;
-    ndp_pow2_scale(fmaxf(fmaxf(S.red[0], S.red[1]), fmaxf(S.red[2], S.red[3])), dscale, dinv);
-    if (tid < NDP_TP) {
-        float v0[8], v1[8], e1[8];
+    ndp_pow2_scale(rec[NDP_TP * 16 + 7], dscale, dinv);
+    if (!wk) {
+    } else if (tid >= 256) {    // head weight image: row r = (tid - 256) / 16, 8-column chunk (tid - 256) & 15
+        const int r = (tid - 256) >> 4, c8 = (tid - 256) & 15;
+        float v[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) { v0[r] = hgv[r] * dscale; v1[r] = hgv[8 + r] * dscale; e1[r] = 0.0f; }
-        ndp_store_chunk2(S.HG, NDP_IMG16, ndp_img_off(tid, 0, RS16), v0);
-        ndp_store_chunk2(S.HG, NDP_IMG16, ndp_img_off(tid, 8, RS16), v1);
-        ndp_store_chunk2(S.E, NDP_IMG16, ndp_img_off(tid, 0, RS16), e0);
-        ndp_store_chunk2(S.E, NDP_IMG16, ndp_img_off(tid, 8, RS16), e1);
-    }
-    ndp_fence_proxy_async();
-    __syncthreads();
-    NDP_T(2);
-
-    const unsigned id_nn = ndp_idesc_f16(128, 128, 1, 1), id_sm = ndp_idesc_f16(128, 16, 1, 1), id_kn = ndp_idesc_f16(128, 128, 0, 1);
-    const NdpUmmaDesc dD_mn = ndp_umma_desc(S.D, RS, CS), dD_k = ndp_umma_desc(S.D, CS, RS), dX_mn = ndp_umma_desc(S.X, RS, CS);
-    const NdpUmmaDesc dE = ndp_umma_desc(S.E, RS16, CS), dHG = ndp_umma_desc(S.HG, RS16, CS);
-    // ---- head gradients: dW_h = hg^T h_L, db_h = hg^T 1.  The [128][16] head-gradient image is read as
-    //      a 128-row MN-major operand: rows >= 16 of the result are other rows' data and are never read.
-    ndp_mbar_wait(&S.bar_x, xph); xph ^= 1;
-    NDP_T(3);
-    if (tid == 0) {
-        ndp_tc_fence_after();
-        ndp_umma_gemm3(tmem + TM_DH, dHG, NDP_IMG16, 2 * RS16, dX_mn, NDP_IMG128, 2 * RS, 8, id_nn, false);
-        ndp_umma_gemm_a2(tmem + TM_SM, dHG, NDP_IMG16, 2 * RS16, dE, 2 * RS16, 8, id_sm);
-        ndp_umma_commit(&S.bar_mma);
-    }
-    // ---- delta at the top activation straight into the delta image while the head GEMMs run:
-    //      (W_h^T hg) . relu'(h_L)
-    {
-        // this row's (scaled) head gradients, re-assembled from the two fp16 parts of the image
-        float g[16];
-        {
-            float t8[8];
-            ndp_load_chunk2(S.HG, NDP_IMG16, ndp_img_off(p, 0, RS16), t8);
+        for (int j = 0; j < 8; ++j) v[j] = (r < HD) ? __ldg(params + L.head_w[r] + c8 * 8 + j) : 0.0f;   // head rows are not 16-byte aligned
+        ndp_store_chunk2(S.HW, NDP_HWIMG, ndp_img_off(r, c8 * 8, RS), v);
+    } else {                    // head-gradient / encoding images from the record of ndp_head_grad_kernel
+        const int pt = tid >> 1, c8 = tid & 1;
+        const float4 h0 = *(const float4*)(rec + pt * 16 + c8 * 8), h1 = *(const float4*)(rec + pt * 16 + c8 * 8 + 4);
+        float v[8] = {h0.x * dscale, h0.y * dscale, h0.z * dscale, h0.w * dscale, h1.x * dscale, h1.y * dscale, h1.z * dscale, h1.w * dscale};
+        ndp_store_chunk2(S.HG, NDP_IMG16, ndp_img_off(pt, c8 * 8, RS16), v);
+        float e[8];
+        if (c8 == 0) {
+            const float4 e0 = *(const float4*)(rec + NDP_TP * 16 + pt * 8), e1 = *(const float4*)(rec + NDP_TP * 16 + pt * 8 + 4);
+            e[0] = e0.x; e[1] = e0.y; e[2] = e0.z; e[3] = e0.w; e[4] = e1.x; e[5] = e1.y; e[6] = 0.0f; e[7] = 0.0f;
+        } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) g[k] = t8[k];
-            ndp_load_chunk2(S.HG, NDP_IMG16, ndp_img_off(p, 8, RS16), t8);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) g[8 + k] = t8[k];
+            for (int j = 0; j < 8; ++j) e[j] = 0.0f;
         }
-#pragma unroll 1
-        for (int ch = 0; ch < 8; ++ch) {
-            const int o0 = half * 64 + ch * 8;
-            const unsigned pm = ndp_pos_mask8(*(const uint4*)(S.X + ndp_img_off(p, o0, RS)));
-            float u[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) u[j] = 0.0f;
-#pragma unroll
-            for (int r = 0; r < NDP_MAX_HEAD; ++r) {     // rows >= head_dim of hw are zero
-                const float4 wa = *(const float4*)(S.hw + r * NDP_W + o0), wb = *(const float4*)(S.hw + r * NDP_W + o0 + 4);
-                u[0] = fmaf(g[r], wa.x, u[0]); u[1] = fmaf(g[r], wa.y, u[1]); u[2] = fmaf(g[r], wa.z, u[2]); u[3] = fmaf(g[r], wa.w, u[3]);
-                u[4] = fmaf(g[r], wb.x, u[4]); u[5] = fmaf(g[r], wb.y, u[5]); u[6] = fmaf(g[r], wb.z, u[6]); u[7] = fmaf(g[r], wb.w, u[7]);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) u[j] = ((pm >> j) & 1u) ? u[j] : 0.0f;
-            ndp_store_chunk2(S.D, NDP_IMG128, ndp_img_off(p, o0, RS), u);
-        }
-    }
-    NDP_T(4);
-    ndp_mbar_wait(&S.bar_mma, mph); mph ^= 1;
-    ndp_tc_fence_after();
-    NDP_T(5);
-    ndp_fence_proxy_async();
-    __syncthreads();            // every thread is done with h_L (relu' masks) and delta_top is complete
-    if (tid == 0 && LH > 0) ndp_stage_bulk(S.X, gact + (long long)(LH - 1) * NDP_SET128, NDP_SET128, &S.bar_x);
-    if ((warp & 3) == 0) {      // TMEM lanes 0..31 hold the head rows
-#pragma unroll 1
-        for (int c32 = 0; c32 < 2; ++c32) {
-            float v[32];
-            const int col0 = half * 64 + c32 * 32;
-            ndp_tmem_ld32(tlane + TM_DH + col0, v);
-            if (lane < HD) {
-                float* dst = part + L.head_w[lane] + col0;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) dst[j] = v[j] * dinv;
-            }
-        }
-        if (half == 0) {
-            float v[32];
-            ndp_tmem_ld32(tlane + TM_SM, v);
-            if (lane < HD) part[L.head_b[lane]] = v[6] * dinv;
-        }
+        ndp_store_chunk2(S.E, NDP_IMG16, ndp_img_off(pt, c8 * 8, RS16), e);
     }
     ndp_tc_fence_before();
+    ndp_fence_proxy_async();
     __syncthreads();
     ndp_tc_fence_after();
-    NDP_T(6);
+    NDP_T(1);
+    const unsigned tmem = S.tmem_slot;
+    const unsigned tlane = tmem + ((unsigned)(q * 32) << 16);
 
-    for (int l = LH - 1; l >= 0; --l) {
-        const int tb = 8 + 8 * (LH - 1 - l);
-        ndp_mbar_wait(&S.bar_x, xph); xph ^= 1;        // h_l (requested before the previous epilogue)
-        NDP_T(tb + 0);
-        if (tid == 0) {
-            ndp_tc_fence_after();
-            // dW_l[o][i] = sum_p delta[p][o] h_l[p][i];  db_l[o] = sum_p delta[p][o] (ones column of E)
-            ndp_umma_gemm3(tmem + TM_DW, dD_mn, NDP_IMG128, 2 * RS, dX_mn, NDP_IMG128, 2 * RS, 8, id_nn, false);
-            ndp_umma_gemm_a2(tmem + TM_SM, dD_mn, NDP_IMG128, 2 * RS, dE, 2 * RS16, 8, id_sm);
-            ndp_umma_commit(&S.bar_mma);
-        }
-        // relu' mask of h_l for this thread's row / column half, before W_l replaces h_l
-        unsigned mask[2] = {0u, 0u};
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch)
-            mask[ch >> 2] |= ndp_pos_mask8(*(const uint4*)(S.X + ndp_img_off(p, half * 64 + ch * 8, RS))) << ((ch & 3) * 8);
-        NDP_T(tb + 1);
-        ndp_mbar_wait(&S.bar_mma, mph); mph ^= 1;
+    const unsigned id_nn = ndp_idesc_f16(128, 128, 1, 1), id_sm = ndp_idesc_f16(128, 16, 1, 1), id_kn = ndp_idesc_f16(128, 128, 0, 1);
+    const NdpUmmaDesc dD_mn = ndp_umma_desc(S.D, RS, CS), dD_k = ndp_umma_desc(S.D, CS, RS);
+    const NdpUmmaDesc dH_mn = ndp_umma_desc(S.H, RS, CS), dW_mn = ndp_umma_desc(S.W, RS, CS);
+    const NdpUmmaDesc dE = ndp_umma_desc(S.E, RS16, CS), dHG_mn = ndp_umma_desc(S.HG, RS16, CS), dHG_k = ndp_umma_desc(S.HG, CS, RS16);
+    const NdpUmmaDesc dHW_mn = ndp_umma_desc(S.HW, RS, CS);
+
+    // The issuing thread launches the MMAs of hidden layer l: delta_l (needs W_l), then dW_l^T (needs h_l)
+    auto issue_layer = [&](int l, int b) {
+        ndp_mbar_wait(&S.bar_w, wph);                        // W_l
         ndp_tc_fence_after();
-        __syncthreads();        // all masks extracted: h_l may be overwritten
-        NDP_T(tb + 2);
-        if (tid == 0) ndp_stage_bulk(S.X, wimg + (long long)l * NDP_SET128, NDP_SET128, &S.bar_x);     // W_l over h_l
-        // dW epilogue: TMEM -> this tile's partial row (thread = output row o, 64 input columns)
-        {
-            const int o = (warp & 3) * 32 + lane;
-#pragma unroll 1
-            for (int c32 = 0; c32 < 2; ++c32) {
-                float v[32];
-                const int col0 = half * 64 + c32 * 32;
-                ndp_tmem_ld32(tlane + TM_DW + col0, v);
-                float* dst = part + L.off_w[l] + o * NDP_W + col0;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) *(float4*)(dst + j) = make_float4(v[j] * dinv, v[j + 1] * dinv, v[j + 2] * dinv, v[j + 3] * dinv);
-            }
-            if (half == 0) {
-                float v[32];
-                ndp_tmem_ld32(tlane + TM_SM, v);
-                part[L.off_b[l] + o] = v[6] * dinv;
-            }
-        }
-        NDP_T(tb + 3);
-        ndp_mbar_wait(&S.bar_x, xph); xph ^= 1;
-        NDP_T(tb + 4);
-        if (tid == 0) {
-            ndp_tc_fence_after();
-            // delta_l[p][i] = sum_o delta[p][o] W_l[o][i]
-            ndp_umma_gemm3(tmem + TM_DH, dD_k, NDP_IMG128, 2 * CS, dX_mn, NDP_IMG128, 2 * RS, 8, id_kn, false);
-            ndp_umma_commit(&S.bar_mma);
-        }
-        ndp_mbar_wait(&S.bar_mma, mph); mph ^= 1;
+        // delta_l[p][i] = sum_o delta[p][o] W_l[o][i]  (runs while h_l is still landing)
+        ndp_umma_gemm3(tmem + TM_DH, dD_k, NDP_IMG128, 2 * CS, dW_mn, NDP_IMG128, 2 * RS, 8, id_kn, false);
+        ndp_mbar_wait(&S.bar_h, hph);                        // h_l
         ndp_tc_fence_after();
-        NDP_T(tb + 5);
-        if (tid == 0 && l > 0) ndp_stage_bulk(S.X, gact + (long long)(l - 1) * NDP_SET128, NDP_SET128, &S.bar_x);   // h_{l-1} over W_l
-        // dH epilogue: relu' mask, re-split, delta image updated in place
-#pragma unroll 1
-        for (int c32 = 0; c32 < 2; ++c32) {
-            float v[32];
-            const int col0 = half * 64 + c32 * 32;
+        // dW_l^T[i][o] = sum_p h_l[p][i] delta[p][o]  (lanes = i: the drain is coalesced)
+        ndp_umma_gemm3(tmem + TM_DW(b), dH_mn, NDP_IMG128, 2 * RS, dD_mn, NDP_IMG128, 2 * RS, 8, id_nn, false);
+        ndp_umma_commit(&S.bar_mma);
+        (void)l;
+    };
+
+    // ---- batch 0: raw delta at the top activation (hg W_h), head weight gradients
+    if (iss) {
+        ndp_umma_gemm3(tmem + TM_DH, dHG_k, NDP_IMG16, 0, dHW_mn, NDP_HWIMG, 0, 1, id_kn, false);
+        ndp_mbar_wait(&S.bar_h, hph);                        // h_L has landed
+        ndp_tc_fence_after();
+        ndp_umma_gemm3(tmem + TM_HDW, dH_mn, NDP_IMG128, 2 * RS, dHG_mn, NDP_IMG16, 2 * RS16, 8, id_sm, false);
+        ndp_umma_commit(&S.bar_mma);
+    }
+    hph ^= 1;
+    __syncthreads();            // the issuer has seen h_L land => visible to everybody
+    NDP_T(2);
+    ndp_mbar_wait(&S.bar_mma, mph); mph ^= 1;
+    ndp_tc_fence_after();
+    NDP_T(3);
+    float v[32];
+    const int col0 = cq * 32;
+    {   // delta_L = raw . relu'(h_L), re-split into the delta images; h_{L-1} replaces h_L meanwhile
+        unsigned mask = 0u;
+        if (wk) {
+#pragma unroll
+            for (int s8 = 0; s8 < 4; ++s8)
+                mask |= ndp_pos_mask8(*(const uint4*)(S.H + ndp_img_off(p, col0 + s8 * 8, RS))) << (s8 * 8);
+        }
+        __syncthreads();        // all masks extracted, head MMAs retired: h_L is free
+        if (iss && LH > 0) ndp_stage_bulk(S.H, gact + (long long)(LH - 1) * NDP_SET128, NDP_SET128, &S.bar_h);
+        if (wk) {
             ndp_tmem_ld32(tlane + TM_DH + col0, v);
-            const unsigned mk = mask[c32];
 #pragma unroll
             for (int s8 = 0; s8 < 4; ++s8) {
                 float u[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) u[j] = ((mk >> (s8 * 8 + j)) & 1u) ? v[s8 * 8 + j] : 0.0f;
+                for (int j = 0; j < 8; ++j) { v[s8 * 8 + j] = ((mask >> (s8 * 8 + j)) & 1u) ? v[s8 * 8 + j] : 0.0f; u[j] = v[s8 * 8 + j]; }
+                ndp_store_chunk2(S.D, NDP_IMG128, ndp_img_off(p, col0 + s8 * 8, RS), u);
+            }
+        }
+    }
+    ndp_tc_fence_before();
+    ndp_fence_proxy_async();
+    __syncthreads();            // delta_L complete
+    ndp_tc_fence_after();
+    NDP_T(4);
+    if (iss && LH > 0) issue_layer(LH - 1, 0);               // the tensor pipe works while the workers drain
+    if (LH > 0) { hph ^= 1; wph ^= 1; }
+    // bias gradient of the layer below = column sums of delta (per lane quarter; combined after the next sync)
+    if (wk) S.dbred[q][col0 + lane] = ndp_colsum32(v, lane);
+    // head weight gradients leave TMEM: dW_h^T[i][r] (lanes = input feature i)
+    if (cq == 0) {
+        float w[16];
+        ndp_tmem_ld16(tlane + TM_HDW, w);
+#pragma unroll
+        for (int r = 0; r < NDP_MAX_HEAD; ++r)
+            if (r < HD) part[L.head_w[r] + p] = w[r] * dinv;
+    }
+
+    for (int l = LH - 1; l >= 0; --l) {
+        const int b = (LH - 1 - l) & 1, tb = 8 + 8 * (LH - 1 - l);
+        NDP_T(tb + 1);
+        __syncthreads();        // (A) the issuer has seen h_l land => visible to everybody; dbred complete
+        if (tid < NDP_W)        // db_l[o] = sum_p delta_{l+1}[p][o], quarters in fixed order
+            part[L.off_b[l] + tid] = ((S.dbred[0][tid] + S.dbred[1][tid]) + (S.dbred[2][tid] + S.dbred[3][tid])) * dinv;
+        // relu' mask of h_l for this thread's row / column quarter, before h_{l-1} replaces h_l
+        unsigned mask = 0u;
+        if (wk) {
+#pragma unroll
+            for (int s8 = 0; s8 < 4; ++s8)
+                mask |= ndp_pos_mask8(*(const uint4*)(S.H + ndp_img_off(p, col0 + s8 * 8, RS))) << (s8 * 8);
+        }
+        ndp_mbar_wait(&S.bar_mma, mph); mph ^= 1;
+        ndp_tc_fence_after();
+        NDP_T(tb + 2);
+        __syncthreads();        // (B) all masks extracted, MMAs retired: h_l, W_l and the delta images are free
+        if (iss && l > 0) {
+            ndp_stage_bulk(S.H, gact + (long long)(l - 1) * NDP_SET128, NDP_SET128, &S.bar_h);
+            ndp_stage_bulk(S.W, wimg + (long long)(l - 1) * NDP_SET128, NDP_SET128, &S.bar_w);
+        }
+        if (wk) {   // delta_l = raw . relu'(h_l), re-split, delta images updated in place
+            ndp_tmem_ld32(tlane + TM_DH + col0, v);
+#pragma unroll
+            for (int s8 = 0; s8 < 4; ++s8) {
+                float u[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { v[s8 * 8 + j] = ((mask >> (s8 * 8 + j)) & 1u) ? v[s8 * 8 + j] : 0.0f; u[j] = v[s8 * 8 + j]; }
                 ndp_store_chunk2(S.D, NDP_IMG128, ndp_img_off(p, col0 + s8 * 8, RS), u);
             }
         }
         ndp_tc_fence_before();
         ndp_fence_proxy_async();
-        __syncthreads();
+        __syncthreads();        // (C) delta_l complete
         ndp_tc_fence_after();
-        NDP_T(tb + 6);
+        NDP_T(tb + 3);
+        if (iss) {
+            if (l > 0) issue_layer(l - 1, b ^ 1);
+            else {
+                // input layer: dW_in[o][0..5] = sum_p delta_0[p][o] E[p][0..5]
+                ndp_umma_gemm3(tmem + TM_DIN, dD_mn, NDP_IMG128, 2 * RS, dE, NDP_IMG16, 2 * RS16, 8, id_sm, false);
+                ndp_umma_commit(&S.bar_mma);
+            }
+        }
+        if (l > 0) { hph ^= 1; wph ^= 1; }
+        if (wk) S.dbred[q][col0 + lane] = ndp_colsum32(v, lane);     // -> db_{l-1} (db_in for l == 0)
+        // dW_l^T leaves TMEM while the next batch of MMAs runs: lane = input feature i, column = output o,
+        // so every store instruction of a warp writes 128 contiguous bytes of the canonical [o][i] block
+        if (wk) {
+            float w[32];
+            ndp_tmem_ld32(tlane + TM_DW(b) + col0, w);
+            float* dst = part + L.off_w[l] + col0 * NDP_W + p;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst[j * NDP_W] = w[j] * dinv;
+        }
+        NDP_T(tb + 4);
     }
 
-    // ---- input layer: [dW_in | db_in][o][0..6] = sum_p delta_0[p][o] E[p][0..6]
-    if (tid == 0) {
-        ndp_umma_gemm3(tmem + TM_SM, dD_mn, NDP_IMG128, 2 * RS, dE, NDP_IMG16, 2 * RS16, 8, id_sm, false);
+    if (LH == 0 && iss) {
+        ndp_umma_gemm3(tmem + TM_DIN, dD_mn, NDP_IMG128, 2 * RS, dE, NDP_IMG16, 2 * RS16, 8, id_sm, false);
         ndp_umma_commit(&S.bar_mma);
     }
+    __syncthreads();            // dbred of delta_0 complete
+    if (tid < NDP_W)
+        part[L.off_b_in + tid] = ((S.dbred[0][tid] + S.dbred[1][tid]) + (S.dbred[2][tid] + S.dbred[3][tid])) * dinv;
     ndp_mbar_wait(&S.bar_mma, mph); mph ^= 1;
     ndp_tc_fence_after();
-    if (half == 0) {
-        float v[32];
-        const int o = (warp & 3) * 32 + lane;
-        ndp_tmem_ld32(tlane + TM_SM, v);
-        float* dst = part + L.off_w_in + o * 6;
+    if (cq == 0) {
+        float w[16];
+        ndp_tmem_ld16(tlane + TM_DIN, w);
+        float* dst = part + L.off_w_in + p * 6;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) dst[c] = v[c] * dinv;
-        part[L.off_b_in + o] = v[6] * dinv;
+        for (int c = 0; c < 6; ++c) dst[c] = w[c] * dinv;
     }
-    if (a.gx && tid < NDP_TP) {     // optional dL/dx: direct part + path through the positional encoding
+    if (a.gx && tid < NDP_TP) {     // optional dL/dx: + the path through the positional encoding
         const int gp = tile * NDP_TP + tid;
         if (gp < n) {
             float de[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
@@ -326,12 +383,13 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
                     for (int c = 0; c < 6; ++c) de[c] = fmaf(d, __ldg(wi + o * 6 + c), de[c]);
                 }
             }
+            const float* xp = a.x + (long long)pair * a.x_stride + (long long)gp * 3;
             float* gxp = a.gx + (long long)pair * a.gx_stride + (long long)gp * 3;
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
-                float s, c;
-                sincosf(S.xs[tid * 4 + d] * L.freq, &s, &c);
-                gxp[d] = S.gxs[tid * 4 + d] + L.freq * (c * de[2 * d] - s * de[2 * d + 1]);
+                float sn, cs;
+                sincosf(__ldg(xp + d) * L.freq, &sn, &cs);
+                gxp[d] += L.freq * (cs * de[2 * d] - sn * de[2 * d + 1]);
             }
         }
     }
@@ -345,7 +403,8 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdA
 void ndp_launch_bwd_tc(const NdpBwdArgs& a, cudaStream_t s) {
     if (a.npairs <= 0 || a.n <= 0) return;
     dim3 grid((a.n + NDP_TP - 1) / NDP_TP, a.npairs);
-    NDP_LAUNCH(ndp_warp_bwd_tc_kernel, grid, dim3(NDP_THREADS), ndp_bwd_tc_smem_bytes(), s, a);
+    NDP_LAUNCH(ndp_head_grad_kernel, grid, dim3(NDP_TP), 0, s, a);
+    NDP_LAUNCH(ndp_warp_bwd_tc_kernel, grid, dim3(NDP_BWD_TC_THREADS), ndp_bwd_tc_smem_bytes(), s, a);
 }
 
 int ndp_bwd_tc_init() {
