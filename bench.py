@@ -241,6 +241,7 @@ def main():
     barrier()
     launches = solver.launch_count - l0
     prof1, ns1 = solver.profile()
+    prof_pairs = solver.profiled_pairs
     clocks = sampler.stop() if rank == 0 else None
     solver.close()
 
@@ -276,7 +277,7 @@ def main():
         t_nn = (prof1["nn_search"] - prof0["nn_search"]) / n_s * 1e-3
         t_ep = (prof1["chamfer_epilogue"] - prof0["chamfer_epilogue"]) / n_s * 1e-3
         shares = {k: (prof1[k] - prof0[k]) / n_s for k in prof1}
-        alg_bytes = B * (20 * (N + N) + 12 * N + 4)           # 425 988 B per pair at 8192^2
+        alg_bytes = prof_pairs * (20 * (N + N) + 12 * N + 4)  # 425 988 B per pair at 8192^2
         achieved = alg_bytes / max(t_nn + t_ep, 1e-12) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "nn_traffic.json")
@@ -284,7 +285,7 @@ def main():
             with open(tp) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
         sm_clock = (clocks or {}).get("sm_mhz") or pk.get("sm_max_mhz", 1965.0)
-        evals = B * 2.0 * N * N
+        evals = prof_pairs * 2.0 * N * N
         fp32_roof_evals = 148 * 128 * sm_clock * 1e6 / 8.0     # 8 FP32-pipe instructions per pair evaluation
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": 1e3 * sec_dev / a.steps, "higher_is_better": True, "scaling": "weak",

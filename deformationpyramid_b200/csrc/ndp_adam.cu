@@ -34,7 +34,7 @@ __device__ __forceinline__ void ndp_pack_store(const NdpLayout& L, float* pack, 
 }
 
 __global__ void __launch_bounds__(256) ndp_reduce_adam_kernel(NdpAdamArgs a) {
-    const int pair = blockIdx.y;
+    const int pair = blockIdx.y + a.pair0;
     if (a.state && a.state[pair].stopped) return;
     const int idx = blockIdx.x * 256 + threadIdx.x;
     const NdpLayout& L = a.lay;

@@ -267,6 +267,11 @@ struct ndp_solver {
     int ev_used = 0;
     double prof_ms[5] = {0, 0, 0, 0, 0};
     long long prof_samples = 0;
+    int prof_pairs = 0;                 // pairs per profiled launch
+    // the batch is split into two halves that run on two streams, so that one half's small kernels
+    // (NN search, Chamfer epilogue, Adam) fill the SM time the other half's tensor-core CTAs leave idle
+    cudaStream_t st2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 static int prof_flush(ndp_solver* s) {   // call after a stream synchronisation
@@ -294,6 +299,9 @@ extern "C" void ndp_solver_destroy(ndp_solver* s) {
     if (!s) return;
     for (void* p : s->allocs) cudaFree(p);
     for (cudaEvent_t e : s->events) cudaEventDestroy(e);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
+    if (s->st2) cudaStreamDestroy(s->st2);
     if (s->h_state) cudaFreeHost(s->h_state);
     if (s->h_counts) cudaFreeHost(s->h_counts);
     delete s;
@@ -341,6 +349,10 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
     if (!e && cudaMallocHost((void**)&s->h_state, sizeof(NdpPairState) * B) != cudaSuccess) e = fail(NDP_E_NOMEM, "cudaMallocHost failed");
     if (!e && cudaMallocHost((void**)&s->h_counts, sizeof(int) * B * 4) != cudaSuccess) e = fail(NDP_E_NOMEM, "cudaMallocHost failed");
     if (!e && cudaMemset(s->counters, 0, sizeof(int) * B) != cudaSuccess) e = fail(NDP_E_CUDA, "cudaMemset failed");
+    if (!e && B >= 2 && (cudaStreamCreateWithFlags(&s->st2, cudaStreamNonBlocking) != cudaSuccess ||
+                         cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                         cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess))
+        e = fail(NDP_E_CUDA, "stream / event creation failed");
     if (!e && cudaMemset(s->gacc, 0, 8 * B * S * 3) != cudaSuccess) e = fail(NDP_E_CUDA, "cudaMemset failed");
     if (e) { ndp_solver_destroy(s); return e; }
     *out = s;
@@ -349,6 +361,7 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
 
 extern "C" int64_t ndp_solver_params_per_pair(const ndp_solver* s) { return s ? (int64_t)s->cfg.levels * s->P : -1; }
 extern "C" int64_t ndp_solver_launch_count(const ndp_solver* s) { return s ? s->launches : -1; }
+extern "C" int32_t ndp_solver_profiled_pairs(const ndp_solver* s) { return s ? s->prof_pairs : -1; }
 extern "C" int ndp_solver_profile(const ndp_solver* s, double* ms, int64_t* samples) {
     if (!s || !ms || !samples) return fail(NDP_E_INVALID, "NULL argument");
     for (int k = 0; k < 5; ++k) ms[k] = s->prof_ms[k];
@@ -455,6 +468,23 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         ad.n = s->S; ad.counts = s->ncount; ad.grads_out = nullptr; ad.grads_stride = 0; ad.state = s->state;
         ad.fixed_step = 0; ad.lr = c.lr; ad.beta1 = 0.9; ad.beta2 = 0.999; ad.eps = 1e-8; ad.do_adam = 1; ad.npairs = npairs;
 
+        // two half-batches on two streams (one when there is a single pair)
+        const int ng = (npairs >= 2 && s->st2) ? 2 : 1;
+        const int gfirst[2] = {0, (npairs + 1) / 2};
+        const int gcount[2] = {ng == 2 ? (npairs + 1) / 2 : npairs, npairs - (npairs + 1) / 2};
+        cudaStream_t gs[2] = {st, s->st2};
+        s->prof_pairs = gcount[0];
+        if (ng == 2) {          // the level's set-up (state reset, moments, pack) precedes both halves
+            CK(cudaEventRecord(s->ev_fork, st));
+            CK(cudaStreamWaitEvent(s->st2, s->ev_fork, 0));
+        }
+        auto join = [&]() -> int {
+            if (ng == 2) {
+                CK(cudaEventRecord(s->ev_join, s->st2));
+                CK(cudaStreamWaitEvent(st, s->ev_join, 0));
+            }
+            return NDP_OK;
+        };
         for (int it = 0; it < c.iters; ++it) {
             const bool prof = c.profile_every > 0 && (it % c.profile_every) == c.profile_every / 2;
             cudaEvent_t* ev = nullptr;
@@ -466,20 +496,27 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
                 }
                 ev = s->events.data() + s->ev_used;
                 s->ev_used += 6;
-                CK(cudaEventRecord(ev[0], st));
             }
-            if (s->mlp_mode == 0) ndp_launch_fwd_tc(f, st); else ndp_launch_fwd(f, st);
-            if (prof) CK(cudaEventRecord(ev[1], st));
-            if (culled) ndp_launch_nn_pruned(pn, st); else ndp_launch_nn(ch.nn, st);
-            if (prof) CK(cudaEventRecord(ev[2], st));
-            ndp_launch_chamfer_reduce(ch, st);
-            if (prof) CK(cudaEventRecord(ev[3], st));
-            if (s->mlp_mode == 0) ndp_launch_bwd_tc(b, st); else ndp_launch_bwd(b, st);
-            if (prof) CK(cudaEventRecord(ev[4], st));
-            ndp_launch_adam(ad, st);
-            if (prof) CK(cudaEventRecord(ev[5], st));
-            s->launches += (s->mlp_mode == 0) ? 6 : 5;
+            for (int g = 0; g < ng; ++g) {
+                cudaStream_t q = gs[g];
+                const bool pg = prof && g == 0;               // sampled timing: the first half's launches, on their stream
+                f.pair0 = pn.pair0 = ch.nn.pair0 = b.pair0 = ad.pair0 = gfirst[g];
+                f.npairs = pn.npairs = ch.nn.npairs = b.npairs = ad.npairs = gcount[g];
+                if (pg) CK(cudaEventRecord(ev[0], q));
+                if (s->mlp_mode == 0) ndp_launch_fwd_tc(f, q); else ndp_launch_fwd(f, q);
+                if (pg) CK(cudaEventRecord(ev[1], q));
+                if (culled) ndp_launch_nn_pruned(pn, q); else ndp_launch_nn(ch.nn, q);
+                if (pg) CK(cudaEventRecord(ev[2], q));
+                ndp_launch_chamfer_reduce(ch, q);
+                if (pg) CK(cudaEventRecord(ev[3], q));
+                if (s->mlp_mode == 0) ndp_launch_bwd_tc(b, q); else ndp_launch_bwd(b, q);
+                if (pg) CK(cudaEventRecord(ev[4], q));
+                ndp_launch_adam(ad, q);
+                if (pg) CK(cudaEventRecord(ev[5], q));
+                s->launches += (s->mlp_mode == 0) ? 6 : 5;
+            }
             if ((it + 1) % poll == 0 && it + 1 < c.iters) {
+                if (int e = join()) return e;
                 CK(cudaMemcpyAsync(s->h_state, s->state, sizeof(NdpPairState) * npairs, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
                 if (int e = prof_flush(s)) return e;
@@ -488,6 +525,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
                 if (all) break;
             }
         }
+        if (int e = join()) return e;
         CK(cudaMemcpyAsync(s->h_state, s->state, sizeof(NdpPairState) * npairs, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(NDP_NN_THREADS) ndp_nn_kernel(NdpNnArgs a) {
     __shared__ __align__(16) float sz[NDP_NN_TS];
 
     const int tid = threadIdx.x;
-    const int dir = blockIdx.z & 1, pair = blockIdx.z >> 1, chunk = blockIdx.y, qt = blockIdx.x;
+    const int dir = blockIdx.z & 1, pair = (blockIdx.z >> 1) + a.pair0, chunk = blockIdx.y, qt = blockIdx.x;
     if (a.state && a.state[pair].stopped) return;
     const int n = a.ncounts ? a.ncounts[pair] : a.n;
     const int m = a.mcounts ? a.mcounts[pair] : a.m;
@@ -126,7 +126,7 @@ __device__ __forceinline__ void ndp_combine(const float2* part, int chunks, int 
 __global__ void __launch_bounds__(NDP_CR_THREADS) ndp_chamfer_reduce_kernel(NdpChamferArgs a) {
     __shared__ double red[2][NDP_CR_THREADS];
     __shared__ int is_last;
-    const int tid = threadIdx.x, pair = blockIdx.y;
+    const int tid = threadIdx.x, pair = blockIdx.y + a.nn.pair0;
     if (a.state && a.state[pair].stopped) return;
     const NdpNnArgs& g = a.nn;
     const int n = g.ncounts ? g.ncounts[pair] : g.n;

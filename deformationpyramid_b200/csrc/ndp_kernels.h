@@ -24,6 +24,7 @@ struct NdpFwdArgs {
     int n; const int* counts;                        // points per pair (counts overrides n when non-null)
     const NdpPairState* state;                       // pairs with state.stopped are skipped, or null
     int npairs;
+    int pair0 = 0;                                   // first pair of this launch (the driver splits a batch over two streams)
 };
 void ndp_launch_fwd(const NdpFwdArgs& a, cudaStream_t s);      // FP32-pipe version (act: fp32 [L+1][n][128])
 // tensor-core version: act = [tile][L+1] fp16 hi/lo image sets (65536 bytes each), act_stride in floats per pair
@@ -47,6 +48,7 @@ struct NdpBwdArgs {
     int n; const int* counts;
     const NdpPairState* state;
     int npairs;
+    int pair0 = 0;
 };
 #define NDP_HGREC (NDP_TP * 24)    // floats per tile: hg[128][16], e[128][8] (e[0][7] = tile max |hg|)
 void ndp_launch_bwd(const NdpBwdArgs& a, cudaStream_t s);
@@ -66,6 +68,7 @@ struct NdpAdamArgs {
     double lr, beta1, beta2, eps;                     // Python floats in torch.optim.Adam => double here
     int do_adam;
     int npairs;
+    int pair0 = 0;
 };
 void ndp_launch_adam(const NdpAdamArgs& a, cudaStream_t s);
 
@@ -89,6 +92,7 @@ struct NdpNnArgs {
     int qpitch; int chunks; int chunk_targets;  // chunk_targets is a multiple of NDP_NN_TS
     const NdpPairState* state;
     int npairs;
+    int pair0 = 0;
 };
 void ndp_launch_nn(const NdpNnArgs& a, cudaStream_t s);
 
@@ -139,6 +143,7 @@ struct NdpPrunedArgs {
     float2* part; long long part_pair_stride; int qpitch;             // [pair][dir][qpitch] (d2, sorted idx bits)
     const NdpPairState* state;
     int npairs;
+    int pair0 = 0;
 };
 void ndp_launch_nn_pruned(const NdpPrunedArgs& a, cudaStream_t s);
 

@@ -158,7 +158,7 @@ int ndp_launch_sort(const NdpSortArgs& a, cudaStream_t s) {
 __global__ void __launch_bounds__(NDP_PN_WARPS * 32) ndp_nn_pruned_kernel(NdpPrunedArgs a) {
     __shared__ __align__(16) float4 stage[NDP_PN_WARPS][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int dir = blockIdx.z & 1, pair = blockIdx.z >> 1;
+    const int dir = blockIdx.z & 1, pair = (blockIdx.z >> 1) + a.pair0;
     if (a.state && a.state[pair].stopped) return;
     const int n = a.ncounts ? a.ncounts[pair] : a.n;
     const int m = a.mcounts ? a.mcounts[pair] : a.m;

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_bwd_kernel(NdpBwdArgs
     float* gxs = xs + NDP_TP * 4;                       // [TP][4] direct part of dL/dx
     NdpMbar* bar = (NdpMbar*)(gxs + NDP_TP * 4);
 
-    const int tid = threadIdx.x, pair = blockIdx.y, tile = blockIdx.x;
+    const int tid = threadIdx.x, pair = blockIdx.y + a.pair0, tile = blockIdx.x;
     const int n = a.counts ? a.counts[pair] : a.n;
     if (tile * NDP_TP >= n) return;
     if (a.state && a.state[pair].stopped) return;

@@ -79,7 +79,7 @@ __device__ __forceinline__ float ndp_colsum32(float (&v)[32], int lane) {
 __global__ void __launch_bounds__(NDP_TP) ndp_head_grad_kernel(NdpBwdArgs a) {
     __shared__ float red[4];
     __shared__ float hsum[4][NDP_MAX_HEAD];
-    const int tid = threadIdx.x, pair = blockIdx.y, tile = blockIdx.x;
+    const int tid = threadIdx.x, pair = blockIdx.y + a.pair0, tile = blockIdx.x;
     const int n = a.counts ? a.counts[pair] : a.n;
     if (tile * NDP_TP >= n) return;
     if (a.state && a.state[pair].stopped) return;
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(NDP_BWD_TC_THREADS, 1) ndp_warp_bwd_tc_kernel(
     NDP_DYN_SMEM(smem_raw);
     BwdTcSmem& S = *(BwdTcSmem*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
 
-    const int tid = threadIdx.x, pair = blockIdx.y, tile = blockIdx.x;
+    const int tid = threadIdx.x, pair = blockIdx.y + a.pair0, tile = blockIdx.x;
     const int n = a.counts ? a.counts[pair] : a.n;
     if (tile * NDP_TP >= n) return;
     if (a.state && a.state[pair].stopped) return;

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(NDP_THREADS, 1) ndp_warp_fwd_kernel(NdpFwdArgs
     float* hb = hw + NDP_MAX_HEAD * NDP_W;              // [head_dim] head biases
     NdpMbar* bar = (NdpMbar*)(hb + 16);                 // 2 barriers
 
-    const int tid = threadIdx.x, pair = blockIdx.y, tile = blockIdx.x;
+    const int tid = threadIdx.x, pair = blockIdx.y + a.pair0, tile = blockIdx.x;
     const int n = a.counts ? a.counts[pair] : a.n;
     if (tile * NDP_TP >= n) return;
     if (a.state && a.state[pair].stopped) return;

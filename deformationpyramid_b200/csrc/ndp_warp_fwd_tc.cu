@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc_kernel(
     NDP_DYN_SMEM(smem_raw);
     FwdTcSmem& S = *(FwdTcSmem*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 
-    const int tid = threadIdx.x, pair = blockIdx.y;
+    const int tid = threadIdx.x, pair = blockIdx.y + a.pair0;
     const int g = tid >> 8, gt = tid & (NDP_GROUP - 1);          // tile group, thread within the group
     const int tile = blockIdx.x * 2 + g;
     const int n = a.counts ? a.counts[pair] : a.n;

@@ -261,6 +261,11 @@ class Solver:
         _lib.check(self.lib, self.lib.ndp_solver_profile(self.handle, ms, ctypes.byref(n)), "ndp_solver_profile")
         return dict(zip(self.KERNELS, [float(v) for v in ms])), int(n.value)
 
+    @property
+    def profiled_pairs(self) -> int:
+        """Pairs per sampled launch (the driver runs two half-batches on two streams)."""
+        return int(self.lib.ndp_solver_profiled_pairs(self.handle))
+
     def losses(self, pair: int) -> torch.Tensor:
         out = torch.full((self.cfg.levels, self.cfg.iters), float("nan"), dtype=torch.float32)
         _lib.check(self.lib, self.lib.ndp_solver_losses(self.handle, int(pair), _ptr(out), ctypes.c_void_p(0)),

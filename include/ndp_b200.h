@@ -155,8 +155,13 @@ int ndp_solver_losses(ndp_solver* s, int32_t pair, float* out, void* stream);
 int64_t ndp_solver_launch_count(const ndp_solver* s);
 /* Sampled device time per kernel since creation (profile_every > 0): ms[5] = accumulated
  * milliseconds of {warp forward, NN search, Chamfer epilogue, warp backward, reduce+Adam} over
- * *samples sampled iterations (each sample is one launch of each kernel over all active pairs). */
+ * *samples sampled iterations (each sample is one launch of each kernel over
+ * ndp_solver_profiled_pairs() pairs).                                                          */
 int ndp_solver_profile(const ndp_solver* s, double* ms, int64_t* samples);
+/* The driver splits a batch into two halves that run on two streams (the second one internal),
+ * so that one half's small kernels fill the SM time the other half's tensor-core CTAs leave
+ * idle.  The sampled launches of ndp_solver_profile are the FIRST half's: this many pairs each. */
+int32_t ndp_solver_profiled_pairs(const ndp_solver* s);
 
 #ifdef __cplusplus
 }

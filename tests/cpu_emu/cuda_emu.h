@@ -193,9 +193,14 @@ static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcp
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)(uintptr_t)1; return cudaSuccess; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 typedef double* cudaEvent_t;   // an event is a wall-clock timestamp in the emulation
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new double(0.0); return cudaSuccess; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new double(0.0); return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = 0) {
     struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); *e = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; return cudaSuccess;

@@ -38,7 +38,7 @@ def test_library_builds_loads_and_exports_every_symbol():
     assert lib.ndp_param_count(ctypes.byref(cfg)) == 34694
     cfg2 = _lib.LayerCfg(128, 3, 1, 1, 0, 2.0 ** -7, 0.001)
     assert lib.ndp_param_count(ctypes.byref(cfg2)) == 34823
-    assert lib.ndp_saved_floats(ctypes.byref(cfg), 256) == 2 * 3 * 24576 + 256 * 12      # tensor-core tri-images
+    assert lib.ndp_saved_floats(ctypes.byref(cfg), 256) == 2 * 3 * 16384 + 256 * 12      # tensor-core fp16 hi/lo image sets (65536 B per tile and layer)
     bad = _lib.LayerCfg(64, 3, 0, 0, 0, 1.0, 0.001)
     assert lib.ndp_param_count(ctypes.byref(bad)) == -1
     assert b"width" in lib.ndp_last_error()
