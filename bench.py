@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ndp", choices=["ndp", "reference"])
-    ap.add_argument("--pairs", type=int, default=8, help="pairs registered concurrently per GPU per step")
+    ap.add_argument("--pairs", type=int, default=32, help="pairs registered concurrently per GPU per step")
     ap.add_argument("--points", type=int, default=8192)
     ap.add_argument("--levels", type=int, default=9)
     ap.add_argument("--iters", type=int, default=500)
@@ -57,9 +57,10 @@ def workload(a):
                         + ("early stop disabled (fixed-iter mode A)" if a.mode == "fixed"
                            else "shipped early-stop thresholds (mode B)"),
             "points": a.points, "levels": a.levels, "iters_per_level": a.iters, "mode": a.mode,
-            "pairs_per_step_per_gpu": a.pairs, "mlp": "tcgen05 bf16x3 (fp32-accurate)" if os.environ.get("NDP_MLP_MODE", "0") == "0" else "fp32 pipes", "nn_search": "exact culled (Morton blocks + boxes + seeds)" if a.nn_mode == 0 else "brute force", "width": 128, "depth": 3, "motion": "SE3", "rotation": "axis_angle",
-            "l2": "flushed (256 MiB write) between timed steps; one step streams ~100 MiB of saved activations "
-                  "and gradient partials per iteration"}
+            "pairs_per_step_per_gpu": a.pairs, "streams": "two half-batches on two streams",
+            "mlp": "tcgen05 fp16 hi/lo split, 3 partial products, fp32 accumulate (fp32-accurate)" if os.environ.get("NDP_MLP_MODE", "0") == "0" else "fp32 pipes", "nn_search": "exact culled (Morton blocks + boxes + seeds)" if a.nn_mode == 0 else "brute force", "width": 128, "depth": 3, "motion": "SE3", "rotation": "axis_angle",
+            "l2": "flushed (256 MiB write) between timed steps; one step streams >= 100 MiB of saved activations "
+                  "and gradient partials per iteration (larger than L2)"}
 
 
 class ClockSampler:
@@ -272,21 +273,34 @@ def main():
         pk, pk_src = peaks()
         P = 34694
         iters_done = int(its.sum()) // B if its is not None else a.levels * a.iters
-        # roofline of the dominant kernel pair (NN search + Chamfer epilogue = one "Chamfer call")
         n_s = max(ns1 - ns0, 1)
-        t_nn = (prof1["nn_search"] - prof0["nn_search"]) / n_s * 1e-3
-        t_ep = (prof1["chamfer_epilogue"] - prof0["chamfer_epilogue"]) / n_s * 1e-3
-        shares = {k: (prof1[k] - prof0[k]) / n_s for k in prof1}
-        alg_bytes = prof_pairs * (20 * (N + N) + 12 * N + 4)  # 425 988 B per pair at 8192^2
-        achieved = alg_bytes / max(t_nn + t_ep, 1e-12) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "nn_traffic.json")
+        shares = {k: (prof1[k] - prof0[k]) / n_s for k in prof1}      # ms per sampled launch (prof_pairs pairs each)
+        t_nn, t_ep, t_bwd = shares["nn_search"] * 1e-3, shares["chamfer_epilogue"] * 1e-3, shares["warp_bwd"] * 1e-3
+        tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+        traffic = {}
         if os.path.exists(tp):
             with open(tp) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                traffic = json.load(f)
         sm_clock = (clocks or {}).get("sm_mhz") or pk.get("sm_max_mhz", 1965.0)
+        # dominant kernel: the tensor-core backward (largest share of the step, profiles/r01_launches_*.csv).
+        # Algorithmic flops per point (kernel (3a)): dW and dH of the two 128x128 layers
+        # 4 * 2*128*128, heads and their back-projection 2 * 2*6*128, input layer 2*128*6 = 135 680.
+        bwd_flops = prof_pairs * N * (4 * 2 * 128 * 128 + 2 * 2 * 6 * 128 + 2 * 128 * 6)
+        tensor_peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1400.0))   # kernel timed inside a long step
+        ach_tf = bwd_flops / max(t_bwd, 1e-12) / 1e12
+        roofline = {"bound": "tensor", "kernel": "ndp_head_grad_kernel + ndp_warp_bwd_tc_kernel (one backward launch)",
+                    "achieved": ach_tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach_tf / tensor_peak,
+                    "traffic": (traffic.get("ndp_warp_bwd_tc_kernel") or {}).get("dram_bytes_per_launch"),
+                    "peak_source": pk_src + " bf16_tflops_sustained", "algorithmic_flops_per_launch": bwd_flops,
+                    "pairs_per_launch": prof_pairs, "launch_ms": 1e3 * t_bwd,
+                    "note": "fp32-accurate products are issued as 3 fp16 MMAs: issued tensor flops = 3x algorithmic"}
+        # the metric's second half: one Chamfer call (NN search + epilogue) against the HBM roof
+        alg_bytes = prof_pairs * (20 * (N + N) + 12 * N + 4)          # 425 988 B per pair at 8192^2
+        achieved = alg_bytes / max(t_nn + t_ep, 1e-12) / 1e9
         evals = prof_pairs * 2.0 * N * N
         fp32_roof_evals = 148 * 128 * sm_clock * 1e6 / 8.0     # 8 FP32-pipe instructions per pair evaluation
+        nn_names = ("ndp_nn_pruned_kernel", "ndp_chamfer_reduce_kernel") if a.nn_mode == 0 else ("ndp_nn_kernel", "ndp_chamfer_reduce_kernel")
+        nn_traffic = [(traffic.get(k) or {}).get("dram_bytes_per_launch") for k in nn_names]
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": 1e3 * sec_dev / a.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload(a),
@@ -296,20 +310,26 @@ def main():
                        "d2h_bytes_per_step": B * (N * 12 + a.levels * P * 4 + a.levels * 8)},
                "gpu_launches": int(launches),
                "iterations_per_pair": iters_done,
-               "roofline": {"bound": "hbm", "kernel": "ndp_nn_kernel + ndp_chamfer_reduce_kernel (one Chamfer call)",
-                            "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                            "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_src,
-                            "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": 1e3 * (t_nn + t_ep),
-                            "note": "brute-force NN is FP32-issue bound (2500 flop/B), not HBM bound: see fp32"},
+               "roofline": roofline,
+               "roofline_chamfer": {"bound": "hbm", "kernel": " + ".join(nn_names) + " (one Chamfer call)",
+                                    "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                    "frac": achieved / pk["hbm_gbs"],
+                                    "traffic": sum(nn_traffic) if all(v is not None for v in nn_traffic) else None,
+                                    "peak_source": pk_src, "algorithmic_bytes_per_launch": alg_bytes,
+                                    "pairs_per_launch": prof_pairs, "launch_ms": 1e3 * (t_nn + t_ep),
+                                    "note": "exact NN search is ALU-issue bound, not HBM bound (SURVEY.md 8d): see fp32"},
                "fp32": {"pair_evals_per_s": evals / max(t_nn, 1e-12), "roof_pair_evals_per_s": fp32_roof_evals,
                         "frac": evals / max(t_nn, 1e-12) / fp32_roof_evals, "sm_mhz_used": sm_clock,
-                        "model": "148 SM x 128 lanes x clock / 8 issue slots per pair evaluation"},
-               "kernel_ms_per_iteration": shares}
+                        "model": "brute-force equivalent pair evaluations (2NM per pair) / time, against 148 SM x 128 lanes x "
+                                 "clock / 8 issue slots; the culled search skips most of them, so > 1 means 'faster than "
+                                 "any brute-force kernel could be'"},
+               "kernel_ms_per_launch": shares, "pairs_per_launch": prof_pairs}
         if not a.no_cpu_baseline:
             from oracle import ndp_oracle as O
             torch.set_num_threads(os.cpu_count() or 1)
             cores = os.cpu_count() or 1
             kt = min(cores, O.max_threads())
+            cpu_sample(a, kt, 1)                              # warm the thread pools / the C library
             par = cpu_sample(a, kt, a.cpu_sample_iters)
             one = cpu_sample(a, 1, 1)
             out["cpu_baseline"] = {

@@ -12,7 +12,7 @@ for P in $PAIRS; do
   python - <<PY
 import json
 try:
-    d=json.load(open("$OUT/bench_${TAG}_p$P.json")); print("pairs=$P value %.3f e2e %.3f"%(d["value"], d["e2e"]["value"]), {k: round(v,4) for k,v in d["kernel_ms_per_iteration"].items()})
+    d=json.load(open("$OUT/bench_${TAG}_p$P.json")); print("pairs=$P value %.3f e2e %.3f"%(d["value"], d["e2e"]["value"]), {k: round(v,4) for k,v in d["kernel_ms_per_launch"].items()})
 except Exception as e: print("pairs=$P failed", e); print(open("$OUT/bench_${TAG}_p$P.err").read()[-1500:])
 PY
 done

@@ -11,7 +11,7 @@ summ() {
 python - <<PY
 import json
 try:
-    d=json.load(open("$1")); print("$1 value %.3f e2e %.3f"%(d["value"], d["e2e"]["value"]), {k: round(v,4) for k,v in d["kernel_ms_per_iteration"].items()})
+    d=json.load(open("$1")); print("$1 value %.3f e2e %.3f"%(d["value"], d["e2e"]["value"]), {k: round(v,4) for k,v in d["kernel_ms_per_launch"].items()})
 except Exception as e: print("$1 failed", e); print(open("$2").read()[-1500:])
 PY
 }
