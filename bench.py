@@ -57,7 +57,7 @@ def workload(a):
                         + ("early stop disabled (fixed-iter mode A)" if a.mode == "fixed"
                            else "shipped early-stop thresholds (mode B)"),
             "points": a.points, "levels": a.levels, "iters_per_level": a.iters, "mode": a.mode,
-            "pairs_per_step_per_gpu": a.pairs, "streams": "two half-batches on two streams",
+            "pairs_per_step_per_gpu": a.pairs, "streams": os.environ.get("NDP_SOLVER_STREAMS", "4") + " stream groups (contiguous pair ranges)",
             "mlp": "tcgen05 fp16 hi/lo split, 3 partial products, fp32 accumulate (fp32-accurate)" if os.environ.get("NDP_MLP_MODE", "0") == "0" else "fp32 pipes", "nn_search": "exact culled (Morton blocks + boxes + seeds)" if a.nn_mode == 0 else "brute force", "width": 128, "depth": 3, "motion": "SE3", "rotation": "axis_angle",
             "l2": "flushed (256 MiB write) between timed steps; one step streams >= 100 MiB of saved activations "
                   "and gradient partials per iteration (larger than L2)"}
@@ -186,6 +186,8 @@ def main():
     ops.set_mlp_mode(mlp_mode)
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 

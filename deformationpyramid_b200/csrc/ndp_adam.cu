@@ -34,27 +34,40 @@ __device__ __forceinline__ void ndp_pack_store(const NdpLayout& L, float* pack, 
 }
 
 __global__ void __launch_bounds__(256) ndp_reduce_adam_kernel(NdpAdamArgs a) {
+    __shared__ float s_fac[2];              // step_size, sqrt(bias_correction2): one fp64 evaluation per CTA
     const int pair = blockIdx.y + a.pair0;
     if (a.state && a.state[pair].stopped) return;
-    const int idx = blockIdx.x * 256 + threadIdx.x;
     const NdpLayout& L = a.lay;
+    if (a.do_adam && threadIdx.x == 0) {
+        // torch evaluates the scalar factors in Python floats (fp64) and rounds them to fp32 once
+        const int step = a.state ? a.state[pair].evals : a.fixed_step;
+        const double bc1 = 1.0 - pow(a.beta1, (double)step);
+        const double bc2 = 1.0 - pow(a.beta2, (double)step);
+        s_fac[0] = (float)(a.lr / bc1);
+        s_fac[1] = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    const int idx = blockIdx.x * 256 + threadIdx.x;
     if (idx >= L.param_count) return;
     const int n = a.counts ? a.counts[pair] : a.n;
     const int tiles = n > 0 ? (n + NDP_TP - 1) / NDP_TP : 1;
     const float* part = a.partials + (long long)pair * a.partials_stride + idx;
     float g = 0.0f;
-    for (int t = 0; t < tiles; ++t) g += part[(long long)t * a.partial_pitch];   // ascending tile order
+    int t = 0;
+    for (; t + 8 <= tiles; t += 8) {        // ascending tile order; the eight loads are issued together
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = part[(long long)(t + k) * a.partial_pitch];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g += v[k];
+    }
+    for (; t < tiles; ++t) g += part[(long long)t * a.partial_pitch];
     if (a.grads_out) a.grads_out[(long long)pair * a.grads_stride + idx] = g;
     if (!a.do_adam) return;
-    const int step = a.state ? a.state[pair].evals : a.fixed_step;
     float* p = a.params + (long long)pair * a.params_stride + idx;
     float* mp = a.m + (long long)pair * a.mv_stride + idx;
     float* vp = a.v + (long long)pair * a.mv_stride + idx;
-    // torch evaluates the scalar factors in Python floats (fp64) and rounds them to fp32 once
-    const double bc1 = 1.0 - pow(a.beta1, (double)step);
-    const double bc2 = 1.0 - pow(a.beta2, (double)step);
-    const float step_size = (float)(a.lr / bc1);
-    const float bc2_sqrt = (float)sqrt(bc2);
+    const float step_size = s_fac[0], bc2_sqrt = s_fac[1];
     const float w1 = (float)(1.0 - a.beta1), b2 = (float)a.beta2, w2 = (float)(1.0 - a.beta2);
     float m = *mp, v = *vp;
     m = m + w1 * (g - m);                 // exp_avg.lerp_(grad, 1 - beta1)

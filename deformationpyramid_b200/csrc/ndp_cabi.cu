@@ -4,6 +4,7 @@
 #include "ndp_kernels.h"
 #include "ndp_tc.cuh"
 
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -234,6 +235,7 @@ extern "C" int ndp_adam_step(const ndp_layer_cfg* c, float* params, const float*
 // =================================================================================================
 // Fused per-pair driver
 // =================================================================================================
+#define NDP_MAX_STREAMS 4
 struct ndp_solver {
     ndp_solver_cfg cfg;
     std::vector<NdpLayout> lay;
@@ -270,8 +272,9 @@ struct ndp_solver {
     int prof_pairs = 0;                 // pairs per profiled launch
     // the batch is split into two halves that run on two streams, so that one half's small kernels
     // (NN search, Chamfer epilogue, Adam) fill the SM time the other half's tensor-core CTAs leave idle
-    cudaStream_t st2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int nstreams = 1;                   // stream groups (1..NDP_MAX_STREAMS), env NDP_SOLVER_STREAMS, default 4
+    cudaStream_t st_extra[NDP_MAX_STREAMS - 1] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[NDP_MAX_STREAMS - 1] = {};
 };
 
 static int prof_flush(ndp_solver* s) {   // call after a stream synchronisation
@@ -300,8 +303,10 @@ extern "C" void ndp_solver_destroy(ndp_solver* s) {
     for (void* p : s->allocs) cudaFree(p);
     for (cudaEvent_t e : s->events) cudaEventDestroy(e);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
-    if (s->ev_join) cudaEventDestroy(s->ev_join);
-    if (s->st2) cudaStreamDestroy(s->st2);
+    for (int i = 0; i < NDP_MAX_STREAMS - 1; ++i) {
+        if (s->ev_join[i]) cudaEventDestroy(s->ev_join[i]);
+        if (s->st_extra[i]) cudaStreamDestroy(s->st_extra[i]);
+    }
     if (s->h_state) cudaFreeHost(s->h_state);
     if (s->h_counts) cudaFreeHost(s->h_counts);
     delete s;
@@ -349,10 +354,18 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
     if (!e && cudaMallocHost((void**)&s->h_state, sizeof(NdpPairState) * B) != cudaSuccess) e = fail(NDP_E_NOMEM, "cudaMallocHost failed");
     if (!e && cudaMallocHost((void**)&s->h_counts, sizeof(int) * B * 4) != cudaSuccess) e = fail(NDP_E_NOMEM, "cudaMallocHost failed");
     if (!e && cudaMemset(s->counters, 0, sizeof(int) * B) != cudaSuccess) e = fail(NDP_E_CUDA, "cudaMemset failed");
-    if (!e && B >= 2 && (cudaStreamCreateWithFlags(&s->st2, cudaStreamNonBlocking) != cudaSuccess ||
-                         cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-                         cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess))
-        e = fail(NDP_E_CUDA, "stream / event creation failed");
+    if (!e) {
+        int want = 4;
+        if (const char* env = getenv("NDP_SOLVER_STREAMS")) want = atoi(env);
+        want = want < 1 ? 1 : (want > NDP_MAX_STREAMS ? NDP_MAX_STREAMS : want);
+        s->nstreams = (int)(B < want ? B : want);
+        if (s->nstreams > 1 && cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess)
+            e = fail(NDP_E_CUDA, "event creation failed");
+        for (int i = 0; !e && i < s->nstreams - 1; ++i)
+            if (cudaStreamCreateWithFlags(&s->st_extra[i], cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&s->ev_join[i], cudaEventDisableTiming) != cudaSuccess)
+                e = fail(NDP_E_CUDA, "stream / event creation failed");
+    }
     if (!e && cudaMemset(s->gacc, 0, 8 * B * S * 3) != cudaSuccess) e = fail(NDP_E_CUDA, "cudaMemset failed");
     if (e) { ndp_solver_destroy(s); return e; }
     *out = s;
@@ -468,20 +481,24 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         ad.n = s->S; ad.counts = s->ncount; ad.grads_out = nullptr; ad.grads_stride = 0; ad.state = s->state;
         ad.fixed_step = 0; ad.lr = c.lr; ad.beta1 = 0.9; ad.beta2 = 0.999; ad.eps = 1e-8; ad.do_adam = 1; ad.npairs = npairs;
 
-        // two half-batches on two streams (one when there is a single pair)
-        const int ng = (npairs >= 2 && s->st2) ? 2 : 1;
-        const int gfirst[2] = {0, (npairs + 1) / 2};
-        const int gcount[2] = {ng == 2 ? (npairs + 1) / 2 : npairs, npairs - (npairs + 1) / 2};
-        cudaStream_t gs[2] = {st, s->st2};
+        // the batch is split into stream groups (contiguous pair ranges, sizes differ by at most one)
+        const int ng = npairs < s->nstreams ? npairs : s->nstreams;
+        int gfirst[NDP_MAX_STREAMS], gcount[NDP_MAX_STREAMS];
+        cudaStream_t gs[NDP_MAX_STREAMS];
+        for (int g = 0, at = 0; g < ng; ++g) {
+            gcount[g] = npairs / ng + (g < npairs % ng ? 1 : 0);
+            gfirst[g] = at; at += gcount[g];
+            gs[g] = g == 0 ? st : s->st_extra[g - 1];
+        }
         s->prof_pairs = gcount[0];
-        if (ng == 2) {          // the level's set-up (state reset, moments, pack) precedes both halves
+        if (ng > 1) {           // the level's set-up (state reset, moments, pack) precedes every group
             CK(cudaEventRecord(s->ev_fork, st));
-            CK(cudaStreamWaitEvent(s->st2, s->ev_fork, 0));
+            for (int g = 1; g < ng; ++g) CK(cudaStreamWaitEvent(gs[g], s->ev_fork, 0));
         }
         auto join = [&]() -> int {
-            if (ng == 2) {
-                CK(cudaEventRecord(s->ev_join, s->st2));
-                CK(cudaStreamWaitEvent(st, s->ev_join, 0));
+            for (int g = 1; g < ng; ++g) {
+                CK(cudaEventRecord(s->ev_join[g - 1], gs[g]));
+                CK(cudaStreamWaitEvent(st, s->ev_join[g - 1], 0));
             }
             return NDP_OK;
         };

@@ -29,6 +29,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __maxnreg__(...)
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
 #define __constant__ static
