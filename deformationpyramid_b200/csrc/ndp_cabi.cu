@@ -253,7 +253,7 @@ struct ndp_solver {
     unsigned long long* keys = nullptr;
     float *sraw = nullptr, *traw = nullptr, *bounds = nullptr, *xbox = nullptr, *tbox = nullptr;
     float4 *x4 = nullptr, *t4 = nullptr;
-    int *orig_s = nullptr, *orig_t = nullptr, *prev_x = nullptr, *prev_y = nullptr;
+    int *orig_s = nullptr, *orig_t = nullptr, *inv_s = nullptr, *inv_t = nullptr, *prev_x = nullptr, *prev_y = nullptr;
     int npad = 0, S128 = 0, nboxes = 0, mlp_mode = 0;
     long long act_pair = 0;
     double* blocksums = nullptr;
@@ -347,7 +347,7 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
     if (c->nn_mode == 0) {
         DA(keys, B * 2 * s->npad); DA(sraw, B * S * 3); DA(traw, B * S * 3); DA(bounds, B * 12);
         DA(xbox, B * s->nboxes * 8); DA(tbox, B * s->nboxes * 8); DA(x4, B * s->S128); DA(t4, B * s->S128);
-        DA(orig_s, B * S); DA(orig_t, B * S); DA(prev_x, B * S); DA(prev_y, B * S);
+        DA(orig_s, B * S); DA(orig_t, B * S); DA(inv_s, B * S); DA(inv_t, B * S); DA(prev_x, B * S); DA(prev_y, B * S);
     }
     if (c->record_loss) DA(loss_hist, B * c->levels * (long long)c->iters);
 #undef DA
@@ -412,7 +412,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         NdpSortArgs so;
         so.src = s->sraw; so.tgt = s->traw; so.cloud_stride = S * 3; so.n = s->S; so.ncounts = s->ncount;
         so.m = s->S; so.mcounts = s->mcount; so.bounds = s->bounds; so.keys = s->keys; so.npad = s->npad;
-        so.src_sorted = s->smp[0]; so.tgt_sorted = s->tsmp; so.src_orig = s->orig_s; so.tgt_orig = s->orig_t;
+        so.src_sorted = s->smp[0]; so.tgt_sorted = s->tsmp; so.src_orig = s->orig_s; so.tgt_orig = s->orig_t; so.src_inv = s->inv_s; so.tgt_inv = s->inv_t;
         so.orig_stride = S; so.tgt4 = s->t4; so.p4_stride = s->S128; so.tgt_box = s->tbox; so.box_stride = s->nboxes;
         so.npairs = npairs;
         s->launches += ndp_launch_sort(so, st);
@@ -453,7 +453,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         ch.nn.state = s->state; ch.nn.npairs = npairs;
         NdpPrunedArgs pn;
         pn.x4 = s->x4; pn.y4 = s->t4; pn.p4_stride = s->S128; pn.xbox = s->xbox; pn.ybox = s->tbox; pn.box_stride = s->nboxes;
-        pn.prev_x = s->prev_x; pn.prev_y = s->prev_y; pn.prev_stride = S; pn.n = s->S; pn.ncounts = s->ncount;
+        pn.prev_x = s->prev_x; pn.prev_y = s->prev_y; pn.prev_stride = S; pn.inv_x = s->inv_s; pn.inv_y = s->inv_t; pn.inv_stride = S; pn.n = s->S; pn.ncounts = s->ncount;
         pn.m = s->S; pn.mcounts = s->mcount; pn.part = s->nnpart; pn.part_pair_stride = ch.nn.part_pair_stride;
         pn.qpitch = s->plan.qpitch; pn.state = s->state; pn.npairs = npairs;
         ch.trunc = c.trunc; ch.gx = s->gx; ch.gx_stride = S * 3; ch.gacc = s->gacc; ch.gacc_stride = S * 3;

@@ -129,6 +129,7 @@ struct NdpSortArgs {
     unsigned long long* keys; int npad;                               // [pair][2][npad], npad = pow2 >= max(n, m)
     float* src_sorted; float* tgt_sorted;                             // [pair][S][3]
     int* src_orig; int* tgt_orig; long long orig_stride;              // sorted position -> sample index
+    int* src_inv; int* tgt_inv;                                       // sample index -> sorted position (same stride)
     float4* tgt4; long long p4_stride;                                // [pair][S_pad32]
     float* tgt_box; long long box_stride;                             // [pair][box_stride][8]
     int npairs;
@@ -139,6 +140,7 @@ struct NdpPrunedArgs {
     const float4* x4; const float4* y4; long long p4_stride;         // warped source / target, sorted, (x,y,z,orig)
     const float* xbox; const float* ybox; long long box_stride;
     int* prev_x; int* prev_y; long long prev_stride;                  // previous NN (sorted index), -1 = none
+    const int* inv_x; const int* inv_y; long long inv_stride;         // sample index -> sorted position of the source / target cloud
     int n; const int* ncounts; int m; const int* mcounts;
     float2* part; long long part_pair_stride; int qpitch;             // [pair][dir][qpitch] (d2, sorted idx bits)
     const NdpPairState* state;

@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(256) ndp_apply_order_kernel(NdpSortArgs a) {
         x = P[(long long)o * 3]; y = P[(long long)o * 3 + 1]; z = P[(long long)o * 3 + 2];
         out[(long long)i * 3] = x; out[(long long)i * 3 + 1] = y; out[(long long)i * 3 + 2] = z;
         (which ? a.tgt_orig : a.src_orig)[(long long)pair * a.orig_stride + i] = o;
+        (which ? a.tgt_inv : a.src_inv)[(long long)pair * a.orig_stride + o] = i;
     }
     if (which) a.tgt4[(long long)pair * a.p4_stride + i] = make_float4(x, y, z, __int_as_float(o));
     // block box of the (static) target; padded slots (+inf) are excluded
@@ -182,8 +183,10 @@ __global__ void __launch_bounds__(NDP_PN_WARPS * 32) ndp_nn_pruned_kernel(NdpPru
     if (js >= nt) js = nt - 1;
     const float4 ts = T4[js];
     float best = ndp_sqdist3(qq.x, qq.y, qq.z, ts.x, ts.y, ts.z);
-    int bo = __float_as_int(ts.w), bj = js;
     if (!(best == best)) best = INF;                           // NaN seed: fall back to a full scan
+    // (distance, original index) packed into one 64-bit key: for non-negative floats the bit pattern
+    // is monotone, so "d < best || (d == best && o < bo)" is ONE unsigned compare (NaN sorts last)
+    unsigned long long bestk = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)__float_as_int(ts.w);
     float wmax = live ? best : 0.0f;                           // dead lanes never widen the search
     for (int s = 16; s > 0; s >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, s));
     const float4 qlo = *(const float4*)qbox, qhi = *(const float4*)(qbox + 4);
@@ -213,13 +216,16 @@ __global__ void __launch_bounds__(NDP_PN_WARPS * 32) ndp_nn_pruned_kernel(NdpPru
             for (int j = 0; j < 32; ++j) {
                 const float4 t = stage[w][j];
                 const float d = ndp_sqdist3(qq.x, qq.y, qq.z, t.x, t.y, t.z);
-                const int o = __float_as_int(t.w);
-                if (d < best || (d == best && o < bo)) { best = d; bo = o; bj = tb * 32 + j; }
+                const unsigned long long k = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(t.w);
+                bestk = k < bestk ? k : bestk;
             }
+            best = __uint_as_float((unsigned)(bestk >> 32));
             __syncwarp();
         }
     }
     if (live) {
+        const int bo = (int)(unsigned)(bestk & 0xffffffffull);
+        const int bj = (dir ? a.inv_x : a.inv_y)[(long long)pair * a.inv_stride + bo];   // sorted position of the winner
         // NaN query: reference semantics are (NaN, index 0)
         if (!(qq.x == qq.x) || !(qq.y == qq.y) || !(qq.z == qq.z)) best = __int_as_float(0x7fc00000);
         a.part[(long long)pair * a.part_pair_stride + (long long)dir * a.qpitch + q] = make_float2(best, __int_as_float(bj));
