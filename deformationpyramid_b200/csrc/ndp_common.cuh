@@ -131,6 +131,22 @@ __device__ __forceinline__ void ndp_mbar_wait(NdpMbar* b, unsigned parity) {
 __device__ __forceinline__ void ndp_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
 
+// Warp-uniform helpers.  tcgen05.mma takes its operands from UNIFORM registers: issued from a branch the
+// compiler cannot prove single-threaded (e.g. `tid == 0`) every MMA is wrapped in a per-thread
+// "waterfall" loop (VOTEU / ELECT / 7 x R2UR / UTCHMMA / BRA, ~100 cycles).  Branching on elect.sync
+// of a warp whose index came through a shuffle broadcast lets ptxas keep everything in uniform registers.
+#ifdef NDP_EMU
+static inline bool ndp_elect_one() { return (threadIdx.x & 31) == 0; }
+static inline int ndp_warp_uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+#else
+__device__ __forceinline__ bool ndp_elect_one() {      // exactly one lane of the (converged) warp; always the same lane
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ int ndp_warp_uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+#endif
+
 // Named barrier over `n` threads (a multiple of 32) of the CTA: bar.sync id, n  (id 1..15; 0 is __syncthreads)
 #ifdef NDP_EMU
 static inline void ndp_group_sync(int id, int n) { ndp_emu_named_sync(id, n); }

@@ -236,13 +236,13 @@ static inline void ndp_tmem_alloc_warp(unsigned* slot, int n) { ndp_tmem_alloc(s
 #endif
 
 // One fp32-accurate product D[128 x N] (+)= A . B over K = 16 * ksteps from hi/lo image sets:
-// the three fp16 partial products, issued by ONE thread.  a_step / b_step: descriptor byte advance
+// the three fp16 partial products, issued by ONE thread (call from a branch on ndp_elect_one(), see ndp_common.cuh).  a_step / b_step: descriptor byte advance
 // per 16-deep k-step; a_img / b_img: byte distance between the hi and lo images.
 // ndp_umma_gemm_a2: only the hi image of B (for operands that are exact in fp16, e.g. a column of ones).
 #ifdef NDP_EMU
 static inline
 #else
-static __device__ __noinline__
+static __device__ __forceinline__
 #endif
 void ndp_umma_gemm_a2(unsigned tmem_d, NdpUmmaDesc a0, unsigned a_img, unsigned a_step, NdpUmmaDesc b0, unsigned b_step,
                       int ksteps, unsigned idesc) {
@@ -263,7 +263,7 @@ void ndp_umma_gemm_a2(unsigned tmem_d, NdpUmmaDesc a0, unsigned a_img, unsigned 
 #ifdef NDP_EMU
 static inline
 #else
-static __device__ __noinline__
+static __device__ __forceinline__
 #endif
 void ndp_umma_gemm3(unsigned tmem_d, NdpUmmaDesc a0, unsigned a_img, unsigned a_step,
                     NdpUmmaDesc b0, unsigned b_img, unsigned b_step, int ksteps,

@@ -173,7 +173,9 @@ __global__ void __launch_bounds__(NDP_BWD_TC_THREADS, 1) ndp_warp_bwd_tc_kernel(
     float* part = a.partials + (long long)pair * a.partials_stride + (long long)tile * a.partial_pitch;
     // thread -> TMEM lane quarter q (hardware: warp % 4), row p = 32 q + lane, column quarter cq
     const int warp = tid >> 5, lane = tid & 31, q = warp & 3, cq = warp >> 2, p = q * 32 + lane;
-    const bool wk = tid < 512, iss = tid == 512;   // workers (epilogues, drains) / the issuing thread
+    const bool wk = tid < 512;                     // workers (epilogues, drains)
+    const bool issw = ndp_warp_uniform(warp) == 16; // the issuing warp: one elected lane launches every MMA / TMA copy
+#define iss (issw && ndp_elect_one())
     const int RS = NDP_IMG_RS(128), CS = NDP_IMG_CS, RS16 = NDP_IMG_RS(16);
     unsigned hph = 0, wph = 0, mph = 0;
     NDP_T(0);
@@ -398,6 +400,7 @@ __global__ void __launch_bounds__(NDP_BWD_TC_THREADS, 1) ndp_warp_bwd_tc_kernel(
     __syncthreads();
     NDP_T(63);
     if (warp == 0) ndp_tmem_dealloc(tmem, 512);
+#undef iss
 }
 
 void ndp_launch_bwd_tc(const NdpBwdArgs& a, cudaStream_t s) {

@@ -63,6 +63,8 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc_kernel(
     const unsigned char* wimg = (const unsigned char*)(a.pack + (long long)pair * a.pack_stride + L.pack_img);
     const int LH = L.hidden, HD = L.head_dim;
     const int warp = tid >> 5, p = gt & (NDP_TP - 1), half = gt >> 7;
+    const bool ldw = (ndp_warp_uniform(warp) & 7) == 0;   // the group's issuing warp: one elected lane launches MMAs / bulk copies
+#define NDP_LEADER (ldw && ndp_elect_one())
     const int RS = NDP_IMG_RS(128), CS = NDP_IMG_CS, RS16 = NDP_IMG_RS(16);
     unsigned char* gact = a.act ? (unsigned char*)a.act + ((long long)pair * a.act_stride) * 4 +
                                       (long long)tile * (LH + 1) * NDP_SET128 : nullptr;
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc_kernel(
         // ---- stage s = 0: input layer; s = 1..LH: hidden layer s - 1.  Each stage: MMAs by the group's
         //      thread 0, then the epilogue h = relu(acc + bias) re-split into the A images (in place).
         for (int s = 0; s <= LH; ++s) {
-            if (gt == 0) {
+            if (NDP_LEADER) {
                 if (s == 0) {
                     ndp_umma_gemm3(tmem, ndp_umma_desc(A, CS, RS16), NDP_IMG16, 0, ndp_umma_desc(S.WIN, CS, RS16), NDP_IMG16, 0, 1,
                                    ndp_idesc_f16(128, 128, 0, 0), false);
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc_kernel(
             ndp_mbar_wait(&S.bar_mma[g], mph); mph ^= 1;
             ndp_tc_fence_after();
             NDP_T(9 + 4 * s);
-            if (gt == 0 && s > 0) {
+            if (s > 0 && NDP_LEADER) {
                 if (gact) ndp_bulk_wait_read0();                  // the store has finished reading A
                 // the last group to retire hidden layer s - 1 refills the weight buffer with the next layer
                 if (s < LH && atomicAdd(&S.bcount[s - 1], 1) == nactive - 1)
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc_kernel(
         }
 
         // ---- heads on the tensor core: z_raw[128 points][16] = h_L W_h^T; top activation saved meanwhile
-        if (gt == 0) {
+        if (NDP_LEADER) {
             ndp_tc_fence_after();
             if (gact) {
                 ndp_bulk_s2g(gact + (long long)LH * NDP_SET128, A, NDP_IMG128);
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc_kernel(
             }
         }
         NDP_T(61);
-        if (gt == 0 && gact) ndp_bulk_wait0();     // smem must outlive the bulk stores
+        if (gact && NDP_LEADER) ndp_bulk_wait0();     // smem must outlive the bulk stores
         NDP_T(62);
     }
     ndp_tc_fence_before();
