@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) ndp_reduce_adam_kernel(NdpAdamArgs a) {
     const int idx = blockIdx.x * 256 + threadIdx.x;
     if (idx >= L.param_count) return;
     const int n = a.counts ? a.counts[pair] : a.n;
-    const int tiles = n > 0 ? (n + NDP_TP - 1) / NDP_TP : 1;
+    const int tiles = n > 0 ? ((n + NDP_TP - 1) / NDP_TP + a.tiles_per_row - 1) / a.tiles_per_row : 1;   // partial rows
     const float* part = a.partials + (long long)pair * a.partials_stride + idx;
     float g = 0.0f;
     int t = 0;

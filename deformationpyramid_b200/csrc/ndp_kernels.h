@@ -49,7 +49,9 @@ struct NdpBwdArgs {
     const NdpPairState* state;
     int npairs;
     int pair0 = 0;
+    int tpc = 1;                                       // tensor-core version: tiles per CTA = tiles per partial row (set by the launcher)
 };
+int ndp_bwd_tc_tiles_per_cta(int hidden);
 #define NDP_HGREC (NDP_TP * 24)    // floats per tile: hg[128][16], e[128][8] (e[0][7] = tile max |hg|)
 void ndp_launch_bwd(const NdpBwdArgs& a, cudaStream_t s);
 void ndp_launch_bwd_tc(const NdpBwdArgs& a, cudaStream_t s);   // needs `pack` (weight image sets)
@@ -61,7 +63,8 @@ struct NdpAdamArgs {
     float* pack;    long long pack_stride;           // may be null
     float* m; float* v; long long mv_stride;         // Adam moments (null when do_adam == 0)
     const float* partials; long long partials_stride; int partial_pitch;
-    int n; const int* counts;                         // tiles per pair = ceil(n / NDP_TP); n == 0 -> 1 partial row
+    int n; const int* counts;                         // partial rows per pair = ceil(ceil(n / NDP_TP) / tiles_per_row); n == 0 -> 1 row
+    int tiles_per_row = 1;
     float* grads_out; long long grads_stride;         // reduced gradient, or null
     const NdpPairState* state;                        // step = state.evals; stopped pairs skipped
     int fixed_step;                                   // used when state == null

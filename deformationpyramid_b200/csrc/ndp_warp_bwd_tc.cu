@@ -24,6 +24,7 @@
 // No atomics: one partial row per tile.
 #include "ndp_kernels.h"
 #include "ndp_tc.cuh"
+#include <stdlib.h>
 
 // optional phase timestamps of CTA (0,0) (debug aid, read back through ndp_debug_phase_times)
 #ifndef NDP_EMU
@@ -44,6 +45,7 @@ struct BwdTcSmem {
     unsigned char E[2 * NDP_IMG16];     // [128 points][16]: cols 0..5 positional encoding, rest 0
     unsigned char HW[2 * NDP_HWIMG];    // [16 head rows][128]: head weights, rows >= head_dim zero
     float dbred[4][NDP_W];              // per lane-quarter column sums of delta (bias gradients)
+    float dbacc[NDP_MAX_HIDDEN + 1][NDP_W];   // bias gradients accumulated over the CTA's tiles (slot LH = input layer)
     NdpMbar bar_h, bar_w, bar_mma;
     unsigned tmem_slot, pad[3];
 };
@@ -75,7 +77,7 @@ __device__ __forceinline__ float ndp_colsum32(float (&v)[32], int lane) {
 // One CTA of 128 threads per tile, full occupancy (the per-point chain of dependent global loads,
 // fp64 fixed-point conversion and rotation backward is latency bound and would otherwise sit at the
 // head of every tensor-core CTA).  Record per tile (NDP_HGREC floats): hg[128][16], e[128][8]
-// (e[0][7] = the tile's max |hg|).  db_h = sum_p hg[p] goes straight to the tile's partial row.
+// (column 7 of e: row 0 = the tile's max |hg|, rows 1.. = db_h = sum_p hg[p]).
 __global__ void __launch_bounds__(NDP_TP) ndp_head_grad_kernel(NdpBwdArgs a) {
     __shared__ float red[4];
     __shared__ float hsum[4][NDP_MAX_HEAD];
@@ -87,7 +89,6 @@ __global__ void __launch_bounds__(NDP_TP) ndp_head_grad_kernel(NdpBwdArgs a) {
     const int HD = L.head_dim;
     const int warp = tid >> 5, lane = tid & 31;
     float* rec = a.hgbuf + (long long)pair * a.hgbuf_stride + (long long)tile * NDP_HGREC;
-    float* part = a.partials + (long long)pair * a.partials_stride + (long long)tile * a.partial_pitch;
     float hgv[16], e0[8];
 #pragma unroll
     for (int r = 0; r < 16; ++r) hgv[r] = 0.0f;
@@ -150,27 +151,33 @@ __global__ void __launch_bounds__(NDP_TP) ndp_head_grad_kernel(NdpBwdArgs a) {
     hp[0] = make_float4(hgv[0], hgv[1], hgv[2], hgv[3]);   hp[1] = make_float4(hgv[4], hgv[5], hgv[6], hgv[7]);
     hp[2] = make_float4(hgv[8], hgv[9], hgv[10], hgv[11]); hp[3] = make_float4(hgv[12], hgv[13], hgv[14], hgv[15]);
     __syncthreads();
+    // column 7 of the e rows carries the tile's scalars: row 0 = max |hg|, row 1 + r = db_h[r]
     if (tid == 0) e0[7] = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    else if (tid <= HD) e0[7] = (hsum[0][tid - 1] + hsum[1][tid - 1]) + (hsum[2][tid - 1] + hsum[3][tid - 1]);
     float4* ep = (float4*)(rec + NDP_TP * 16 + tid * 8);
     ep[0] = make_float4(e0[0], e0[1], e0[2], e0[3]); ep[1] = make_float4(e0[4], e0[5], e0[6], e0[7]);
-    if (tid < HD) part[L.head_b[tid]] = (hsum[0][tid] + hsum[1][tid]) + (hsum[2][tid] + hsum[3][tid]);
 }
 
 __global__ void __launch_bounds__(NDP_BWD_TC_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdArgs a) {
     NDP_DYN_SMEM(smem_raw);
     BwdTcSmem& S = *(BwdTcSmem*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
 
-    const int tid = threadIdx.x, pair = blockIdx.y + a.pair0, tile = blockIdx.x;
+    // A CTA owns a.tpc consecutive tiles of one pair and accumulates their gradients in TMEM / smem:
+    // one partial row per CTA (fixed grouping => deterministic), drained once.
+    const int tid = threadIdx.x, pair = blockIdx.y + a.pair0, tile0 = blockIdx.x * a.tpc;
     const int n = a.counts ? a.counts[pair] : a.n;
-    if (tile * NDP_TP >= n) return;
+    if (tile0 * NDP_TP >= n) return;
     if (a.state && a.state[pair].stopped) return;
+    const int tiles_all = (n + NDP_TP - 1) / NDP_TP;
+    const int ntl = tiles_all - tile0 < a.tpc ? tiles_all - tile0 : a.tpc;     // tiles of this CTA
     const NdpLayout& L = a.lay;
     const float* params = a.params + (long long)pair * a.params_stride;
     const unsigned char* wimg = (const unsigned char*)(a.pack + (long long)pair * a.pack_stride + L.pack_img);
     const int LH = L.hidden, HD = L.head_dim;
-    const unsigned char* gact = (const unsigned char*)a.act + ((long long)pair * a.act_stride) * 4 +
-                                (long long)tile * (LH + 1) * NDP_SET128;
-    float* part = a.partials + (long long)pair * a.partials_stride + (long long)tile * a.partial_pitch;
+    const unsigned char* gact0 = (const unsigned char*)a.act + ((long long)pair * a.act_stride) * 4 +
+                                 (long long)tile0 * (LH + 1) * NDP_SET128;
+    const long long gact_tile = (long long)(LH + 1) * NDP_SET128;
+    float* part = a.partials + (long long)pair * a.partials_stride + (long long)blockIdx.x * a.partial_pitch;
     // thread -> TMEM lane quarter q (hardware: warp % 4), row p = 32 q + lane, column quarter cq
     const int warp = tid >> 5, lane = tid & 31, q = warp & 3, cq = warp >> 2, p = q * 32 + lane;
     const bool wk = tid < 512;                     // workers (epilogues, drains)
@@ -183,21 +190,33 @@ __global__ void __launch_bounds__(NDP_BWD_TC_THREADS, 1) ndp_warp_bwd_tc_kernel(
     if (warp == 0) ndp_tmem_alloc_warp(&S.tmem_slot, 512);
     if (iss) {                  // barriers, and the first operands requested before anything else
         ndp_mbar_init(&S.bar_h, 1); ndp_mbar_init(&S.bar_w, 1); ndp_mbar_init(&S.bar_mma, 1);
-        ndp_stage_bulk(S.H, gact + (long long)LH * NDP_SET128, NDP_SET128, &S.bar_h);                 // h_L
+        ndp_stage_bulk(S.H, gact0 + (long long)LH * NDP_SET128, NDP_SET128, &S.bar_h);                // h_L of the first tile
         if (LH > 0) ndp_stage_bulk(S.W, wimg + (long long)(LH - 1) * NDP_SET128, NDP_SET128, &S.bar_w);   // W_{L-1}
     }
-    // the tile's delta scale: an exact power of two that brings the largest head gradient into [1, 2)
-    // (fp16 operand range, see ndp_tc.cuh); undone when the gradients leave TMEM
-    const float* rec = a.hgbuf + (long long)pair * a.hgbuf_stride + (long long)tile * NDP_HGREC;
+    // the CTA's delta scale: an exact power of two that brings the largest head gradient of its tiles
+    // into [1, 2) (fp16 operand range, see ndp_tc.cuh); undone when the gradients leave TMEM
+    const float* rec0 = a.hgbuf + (long long)pair * a.hgbuf_stride + (long long)tile0 * NDP_HGREC;
     float dscale, dinv;
-    ndp_pow2_scale(rec[NDP_TP * 16 + 7], dscale, dinv);
+    {
+        float mx = 0.0f;
+        for (int t = 0; t < ntl; ++t) mx = fmaxf(mx, rec0[(long long)t * NDP_HGREC + NDP_TP * 16 + 7]);
+        ndp_pow2_scale(mx, dscale, dinv);
+    }
+
+  for (int t = 0; t < ntl; ++t) {
+    const int tile = tile0 + t;
+    const bool last = t == ntl - 1, acc = t > 0;
+    const unsigned char* gact = gact0 + (long long)t * gact_tile;
+    const float* rec = rec0 + (long long)t * NDP_HGREC;
     if (!wk) {
-    } else if (tid >= 256) {    // head weight image: row r = (tid - 256) / 16, 8-column chunk (tid - 256) & 15
+    } else if (tid >= 256) {    // head weight image (first tile only; the guard is warp uniform):
+      if (t == 0) {             // row r = (tid - 256) / 16, 8-column chunk (tid - 256) & 15
         const int r = (tid - 256) >> 4, c8 = (tid - 256) & 15;
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = (r < HD) ? __ldg(params + L.head_w[r] + c8 * 8 + j) : 0.0f;   // head rows are not 16-byte aligned
         ndp_store_chunk2(S.HW, NDP_HWIMG, ndp_img_off(r, c8 * 8, RS), v);
+      }
     } else {                    // head-gradient / encoding images from the record of ndp_head_grad_kernel
         const int pt = tid >> 1, c8 = tid & 1;
         const float4 h0 = *(const float4*)(rec + pt * 16 + c8 * 8), h1 = *(const float4*)(rec + pt * 16 + c8 * 8 + 4);
@@ -236,7 +255,7 @@ __global__ void __launch_bounds__(NDP_BWD_TC_THREADS, 1) ndp_warp_bwd_tc_kernel(
         ndp_mbar_wait(&S.bar_h, hph);                        // h_l
         ndp_tc_fence_after();
         // dW_l^T[i][o] = sum_p h_l[p][i] delta[p][o]  (lanes = i: the drain is coalesced)
-        ndp_umma_gemm3(tmem + TM_DW(b), dH_mn, NDP_IMG128, 2 * RS, dD_mn, NDP_IMG128, 2 * RS, 8, id_nn, false);
+        ndp_umma_gemm3(tmem + TM_DW(b), dH_mn, NDP_IMG128, 2 * RS, dD_mn, NDP_IMG128, 2 * RS, 8, id_nn, acc);
         ndp_umma_commit(&S.bar_mma);
         (void)l;
     };
@@ -246,7 +265,7 @@ __global__ void __launch_bounds__(NDP_BWD_TC_THREADS, 1) ndp_warp_bwd_tc_kernel(
         ndp_umma_gemm3(tmem + TM_DH, dHG_k, NDP_IMG16, 0, dHW_mn, NDP_HWIMG, 0, 1, id_kn, false);
         ndp_mbar_wait(&S.bar_h, hph);                        // h_L has landed
         ndp_tc_fence_after();
-        ndp_umma_gemm3(tmem + TM_HDW, dH_mn, NDP_IMG128, 2 * RS, dHG_mn, NDP_IMG16, 2 * RS16, 8, id_sm, false);
+        ndp_umma_gemm3(tmem + TM_HDW, dH_mn, NDP_IMG128, 2 * RS, dHG_mn, NDP_IMG16, 2 * RS16, 8, id_sm, acc);
         ndp_umma_commit(&S.bar_mma);
     }
     hph ^= 1;
@@ -266,6 +285,7 @@ __global__ void __launch_bounds__(NDP_BWD_TC_THREADS, 1) ndp_warp_bwd_tc_kernel(
         }
         __syncthreads();        // all masks extracted, head MMAs retired: h_L is free
         if (iss && LH > 0) ndp_stage_bulk(S.H, gact + (long long)(LH - 1) * NDP_SET128, NDP_SET128, &S.bar_h);
+        if (iss && LH == 0 && !last) ndp_stage_bulk(S.H, gact + gact_tile, NDP_SET128, &S.bar_h);   // next tile's h_L
         if (wk) {
             ndp_tmem_ld32(tlane + TM_DH + col0, v);
 #pragma unroll
@@ -287,7 +307,7 @@ __global__ void __launch_bounds__(NDP_BWD_TC_THREADS, 1) ndp_warp_bwd_tc_kernel(
     // bias gradient of the layer below = column sums of delta (per lane quarter; combined after the next sync)
     if (wk) S.dbred[q][col0 + lane] = ndp_colsum32(v, lane);
     // head weight gradients leave TMEM: dW_h^T[i][r] (lanes = input feature i)
-    if (cq == 0) {
+    if (cq == 0 && last) {
         float w[16];
         ndp_tmem_ld16(tlane + TM_HDW, w);
 #pragma unroll
@@ -299,8 +319,12 @@ __global__ void __launch_bounds__(NDP_BWD_TC_THREADS, 1) ndp_warp_bwd_tc_kernel(
         const int b = (LH - 1 - l) & 1, tb = 8 + 8 * (LH - 1 - l);
         NDP_T(tb + 1);
         __syncthreads();        // (A) the issuer has seen h_l land => visible to everybody; dbred complete
-        if (tid < NDP_W)        // db_l[o] = sum_p delta_{l+1}[p][o], quarters in fixed order
-            part[L.off_b[l] + tid] = ((S.dbred[0][tid] + S.dbred[1][tid]) + (S.dbred[2][tid] + S.dbred[3][tid])) * dinv;
+        if (tid < NDP_W) {      // db_l[o] = sum_p delta_{l+1}[p][o], quarters in fixed order, tiles in order
+            const float val = (S.dbred[0][tid] + S.dbred[1][tid]) + (S.dbred[2][tid] + S.dbred[3][tid]);
+            const float tot = acc ? S.dbacc[l][tid] + val : val;
+            S.dbacc[l][tid] = tot;
+            if (last) part[L.off_b[l] + tid] = tot * dinv;
+        }
         // relu' mask of h_l for this thread's row / column quarter, before h_{l-1} replaces h_l
         unsigned mask = 0u;
         if (wk) {
@@ -315,6 +339,10 @@ __global__ void __launch_bounds__(NDP_BWD_TC_THREADS, 1) ndp_warp_bwd_tc_kernel(
         if (iss && l > 0) {
             ndp_stage_bulk(S.H, gact + (long long)(l - 1) * NDP_SET128, NDP_SET128, &S.bar_h);
             ndp_stage_bulk(S.W, wimg + (long long)(l - 1) * NDP_SET128, NDP_SET128, &S.bar_w);
+        }
+        if (iss && l == 0 && !last) {       // both buffers are free for the rest of this tile: prefetch the next one
+            ndp_stage_bulk(S.H, gact + gact_tile + (long long)LH * NDP_SET128, NDP_SET128, &S.bar_h);
+            ndp_stage_bulk(S.W, wimg + (long long)(LH - 1) * NDP_SET128, NDP_SET128, &S.bar_w);
         }
         if (wk) {   // delta_l = raw . relu'(h_l), re-split, delta images updated in place
             ndp_tmem_ld32(tlane + TM_DH + col0, v);
@@ -335,7 +363,7 @@ __global__ void __launch_bounds__(NDP_BWD_TC_THREADS, 1) ndp_warp_bwd_tc_kernel(
             if (l > 0) issue_layer(l - 1, b ^ 1);
             else {
                 // input layer: dW_in[o][0..5] = sum_p delta_0[p][o] E[p][0..5]
-                ndp_umma_gemm3(tmem + TM_DIN, dD_mn, NDP_IMG128, 2 * RS, dE, NDP_IMG16, 2 * RS16, 8, id_sm, false);
+                ndp_umma_gemm3(tmem + TM_DIN, dD_mn, NDP_IMG128, 2 * RS, dE, NDP_IMG16, 2 * RS16, 8, id_sm, acc);
                 ndp_umma_commit(&S.bar_mma);
             }
         }
@@ -343,7 +371,7 @@ __global__ void __launch_bounds__(NDP_BWD_TC_THREADS, 1) ndp_warp_bwd_tc_kernel(
         if (wk) S.dbred[q][col0 + lane] = ndp_colsum32(v, lane);     // -> db_{l-1} (db_in for l == 0)
         // dW_l^T leaves TMEM while the next batch of MMAs runs: lane = input feature i, column = output o,
         // so every store instruction of a warp writes 128 contiguous bytes of the canonical [o][i] block
-        if (wk) {
+        if (wk && last) {
             float w[32];
             ndp_tmem_ld32(tlane + TM_DW(b) + col0, w);
             float* dst = part + L.off_w[l] + col0 * NDP_W + p;
@@ -354,15 +382,19 @@ __global__ void __launch_bounds__(NDP_BWD_TC_THREADS, 1) ndp_warp_bwd_tc_kernel(
     }
 
     if (LH == 0 && iss) {
-        ndp_umma_gemm3(tmem + TM_DIN, dD_mn, NDP_IMG128, 2 * RS, dE, NDP_IMG16, 2 * RS16, 8, id_sm, false);
+        ndp_umma_gemm3(tmem + TM_DIN, dD_mn, NDP_IMG128, 2 * RS, dE, NDP_IMG16, 2 * RS16, 8, id_sm, acc);
         ndp_umma_commit(&S.bar_mma);
     }
     __syncthreads();            // dbred of delta_0 complete
-    if (tid < NDP_W)
-        part[L.off_b_in + tid] = ((S.dbred[0][tid] + S.dbred[1][tid]) + (S.dbred[2][tid] + S.dbred[3][tid])) * dinv;
+    if (tid < NDP_W) {
+        const float val = (S.dbred[0][tid] + S.dbred[1][tid]) + (S.dbred[2][tid] + S.dbred[3][tid]);
+        const float tot = acc ? S.dbacc[LH][tid] + val : val;
+        S.dbacc[LH][tid] = tot;
+        if (last) part[L.off_b_in + tid] = tot * dinv;
+    }
     ndp_mbar_wait(&S.bar_mma, mph); mph ^= 1;
     ndp_tc_fence_after();
-    if (cq == 0) {
+    if (cq == 0 && last) {
         float w[16];
         ndp_tmem_ld16(tlane + TM_DIN, w);
         float* dst = part + L.off_w_in + p * 6;
@@ -397,17 +429,36 @@ __global__ void __launch_bounds__(NDP_BWD_TC_THREADS, 1) ndp_warp_bwd_tc_kernel(
     }
     NDP_T(62);
     ndp_tc_fence_before();
-    __syncthreads();
+    __syncthreads();            // end of the tile: images, dbred and the DH / DIN accumulators are free again
+    ndp_tc_fence_after();
+  }
+    if (tid < HD) {             // db_h: per-tile sums of the pre-kernel, tiles in order
+        float sv = 0.0f;
+        for (int t = 0; t < ntl; ++t) sv += rec0[(long long)t * NDP_HGREC + NDP_TP * 16 + (1 + tid) * 8 + 7];
+        part[L.head_b[tid]] = sv;
+    }
     NDP_T(63);
-    if (warp == 0) ndp_tmem_dealloc(tmem, 512);
+    if (warp == 0) ndp_tmem_dealloc(S.tmem_slot, 512);
 #undef iss
 }
 
+// Tiles whose gradients one CTA accumulates (= tiles per partial row).  The dW accumulators are per
+// layer parity, so accumulation over tiles needs at most two hidden layers.
+int ndp_bwd_tc_tiles_per_cta(int hidden) {
+    static int tpc = 0;
+    if (tpc == 0) {
+        tpc = 4;    // fixed (not a function of the batch): the summation grouping must not depend on what a pair is batched with
+        if (const char* env = getenv("NDP_BWD_TPC")) { const int v = atoi(env); if (v >= 1 && v <= 16) tpc = v; }
+    }
+    return hidden <= 2 ? tpc : 1;
+}
 void ndp_launch_bwd_tc(const NdpBwdArgs& a, cudaStream_t s) {
     if (a.npairs <= 0 || a.n <= 0) return;
-    dim3 grid((a.n + NDP_TP - 1) / NDP_TP, a.npairs);
-    NDP_LAUNCH(ndp_head_grad_kernel, grid, dim3(NDP_TP), 0, s, a);
-    NDP_LAUNCH(ndp_warp_bwd_tc_kernel, grid, dim3(NDP_BWD_TC_THREADS), ndp_bwd_tc_smem_bytes(), s, a);
+    const int tiles = (a.n + NDP_TP - 1) / NDP_TP;
+    NDP_LAUNCH(ndp_head_grad_kernel, dim3(tiles, a.npairs), dim3(NDP_TP), 0, s, a);
+    NdpBwdArgs b = a;
+    b.tpc = ndp_bwd_tc_tiles_per_cta(a.lay.hidden);
+    NDP_LAUNCH(ndp_warp_bwd_tc_kernel, dim3((tiles + b.tpc - 1) / b.tpc, a.npairs), dim3(NDP_BWD_TC_THREADS), ndp_bwd_tc_smem_bytes(), s, b);
 }
 
 int ndp_bwd_tc_init() {
