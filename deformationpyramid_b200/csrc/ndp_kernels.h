@@ -24,7 +24,8 @@ struct NdpFwdArgs {
     int n; const int* counts;                        // points per pair (counts overrides n when non-null)
     const NdpPairState* state;                       // pairs with state.stopped are skipped, or null
     int npairs;
-    int pair0 = 0;                                   // first pair of this launch (the driver splits a batch over two streams)
+    int pair0 = 0;                                   // first pair of this launch (the driver splits a batch over stream groups)
+    int rounds = 1;                                  // tensor-core version: tile pairs per CTA (set by the launcher)
 };
 void ndp_launch_fwd(const NdpFwdArgs& a, cudaStream_t s);      // FP32-pipe version (act: fp32 [L+1][n][128])
 // tensor-core version: act = [tile][L+1] fp16 hi/lo image sets (65536 bytes each), act_stride in floats per pair

@@ -19,6 +19,7 @@
 // (rigid_body.py) stays scalar.
 #include "ndp_kernels.h"
 #include "ndp_tc.cuh"
+#include <stdlib.h>
 
 // optional phase timestamps of CTA (0,0), group 0 (debug aid, read back through ndp_debug_phase_times)
 #ifndef NDP_EMU
@@ -29,6 +30,7 @@ __device__ unsigned long long ndp_dbg_fwd[64];
 #endif
 
 #define NDP_FWD_TC_THREADS 512
+#define NDP_FWD_MAX_ROUNDS 4               // tile pairs a CTA processes one after the other (amortises the set-up)
 #define NDP_GROUP 256                      // threads per tile group
 #define NDP_IMG16 NDP_IMG_BYTES(16)        // [128][16] fp16 image: 4096 bytes
 #define NDP_HWIMG (2 * NDP_IMG_RS(128))    // [16][128] fp16 image: 4096 bytes
@@ -41,7 +43,7 @@ struct FwdTcSmem {
     float xs[2][NDP_TP * 4];
     float hb[16];
     NdpMbar bar_w, bar_mma[2];
-    int bcount[NDP_MAX_HIDDEN];            // groups whose MMAs of hidden layer l have retired
+    int bcount[NDP_FWD_MAX_ROUNDS * NDP_MAX_HIDDEN];   // per (round, hidden layer): groups whose MMAs have retired
     unsigned tmem_slot, pad[3];
 };
 size_t ndp_fwd_tc_smem_bytes() { return sizeof(FwdTcSmem) + 1024; }
@@ -52,12 +54,13 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc_kernel(
 
     const int tid = threadIdx.x, pair = blockIdx.y + a.pair0;
     const int g = tid >> 8, gt = tid & (NDP_GROUP - 1);          // tile group, thread within the group
-    const int tile = blockIdx.x * 2 + g;
+    const int rounds = a.rounds;                                 // CTA = tiles [2 rounds bx, 2 rounds (bx + 1)): round r, group g -> tile
+    const int tile_first = blockIdx.x * 2 * rounds;
     const int n = a.counts ? a.counts[pair] : a.n;
-    if (blockIdx.x * 2 * NDP_TP >= n) return;
+    if (tile_first * NDP_TP >= n) return;
     if (a.state && a.state[pair].stopped) return;
-    const bool active = tile * NDP_TP < n;
-    const int nactive = ((blockIdx.x * 2 + 1) * NDP_TP < n) ? 2 : 1;
+    int tile = tile_first + g;
+    bool active = tile * NDP_TP < n;
     const NdpLayout& L = a.lay;
     const float* params = a.params + (long long)pair * a.params_stride;
     const unsigned char* wimg = (const unsigned char*)(a.pack + (long long)pair * a.pack_stride + L.pack_img);
@@ -66,15 +69,14 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc_kernel(
     const bool ldw = (ndp_warp_uniform(warp) & 7) == 0;   // the group's issuing warp: one elected lane launches MMAs / bulk copies
 #define NDP_LEADER (ldw && ndp_elect_one())
     const int RS = NDP_IMG_RS(128), CS = NDP_IMG_CS, RS16 = NDP_IMG_RS(16);
-    unsigned char* gact = a.act ? (unsigned char*)a.act + ((long long)pair * a.act_stride) * 4 +
-                                      (long long)tile * (LH + 1) * NDP_SET128 : nullptr;
+    unsigned char* const gact_pair = a.act ? (unsigned char*)a.act + ((long long)pair * a.act_stride) * 4 : nullptr;
     unsigned char* A = S.A[g];
     float* xs = S.xs[g];
 
     NDP_T(0);
     if (warp == 0) ndp_tmem_alloc_warp(&S.tmem_slot, 256);
     if (tid == 0) { ndp_mbar_init(&S.bar_w, 1); ndp_mbar_init(&S.bar_mma[0], 1); ndp_mbar_init(&S.bar_mma[1], 1); }
-    if (tid < NDP_MAX_HIDDEN) S.bcount[tid] = 0;
+    if (tid < NDP_FWD_MAX_ROUNDS * NDP_MAX_HIDDEN) S.bcount[tid] = 0;
     if (tid < 16) S.hb[tid] = (tid < HD) ? __ldg(params + L.head_b[tid]) : 0.0f;
     if (tid < 256) {            // input-layer weight image: row o = tid / 2, 8-column chunk tid & 1
         const int o = tid >> 1, c8 = tid & 1;
@@ -89,7 +91,8 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc_kernel(
         for (int j = 0; j < 8; ++j) v[j] = (r < HD) ? __ldg(params + L.head_w[r] + c8 * 8 + j) : 0.0f;   // head rows are not 16-byte aligned
         ndp_store_chunk2(S.HW, NDP_HWIMG, ndp_img_off(r, c8 * 8, RS), v);
     }
-    if (gt < NDP_TP) {          // points + positional encoding image (nets.py:164-177), in the head of A
+    auto build_posenc = [&](int tile) {   // points + positional encoding image (nets.py:164-177), in the head of A
+      if (gt < NDP_TP) {
         const int gp = tile * NDP_TP + gt;
         float px = 0.0f, py = 0.0f, pz = 0.0f;
         if (gp < n) {
@@ -106,7 +109,9 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc_kernel(
         for (int j = 0; j < 8; ++j) e1[j] = 0.0f;
         ndp_store_chunk2(A, NDP_IMG16, ndp_img_off(gt, 0, RS16), e0);
         ndp_store_chunk2(A, NDP_IMG16, ndp_img_off(gt, 8, RS16), e1);
-    }
+      }
+    };
+    build_posenc(tile);
     ndp_tc_fence_before();
     ndp_fence_proxy_async();
     __syncthreads();
@@ -116,8 +121,16 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc_kernel(
     const unsigned tlane = tmem + ((unsigned)((warp & 3) * 32) << 16);
     if (tid == 0 && LH > 0) ndp_stage_bulk(S.B, wimg, NDP_SET128, &S.bar_w);
 
-    if (active) {
-        unsigned mph = 0;
+    unsigned mph = 0;
+    for (int r = 0; r < rounds && active; ++r) {
+        const int nactive = ((tile_first + 2 * r + 1) * NDP_TP < n) ? 2 : 1;                 // groups with a tile in this round
+        const bool more = r + 1 < rounds && (tile_first + 2 * (r + 1)) * NDP_TP < n;         // the CTA has another round
+        unsigned char* gact = gact_pair ? gact_pair + (long long)tile * (LH + 1) * NDP_SET128 : nullptr;
+        if (r > 0) {            // this group's next tile: A is free (top-activation store drained by the leader below)
+            build_posenc(tile);
+            ndp_fence_proxy_async();
+            ndp_group_sync(1 + g, NDP_GROUP);
+        }
         // ---- stage s = 0: input layer; s = 1..LH: hidden layer s - 1.  Each stage: MMAs by the group's
         //      thread 0, then the epilogue h = relu(acc + bias) re-split into the A images (in place).
         for (int s = 0; s <= LH; ++s) {
@@ -131,7 +144,7 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc_kernel(
                         ndp_bulk_s2g(gact + (long long)(s - 1) * NDP_SET128 + NDP_IMG128, A + NDP_IMG128, NDP_IMG128);
                         ndp_bulk_commit();
                     }
-                    ndp_mbar_wait(&S.bar_w, (unsigned)((s - 1) & 1));
+                    ndp_mbar_wait(&S.bar_w, (unsigned)((r * LH + s - 1) & 1));
                     ndp_tc_fence_after();
                     ndp_umma_gemm3(tmem, ndp_umma_desc(A, CS, RS), NDP_IMG128, 2 * CS, ndp_umma_desc(S.B, CS, RS), NDP_IMG128, 2 * CS, 8,
                                    ndp_idesc_f16(128, 128, 0, 0), false);
@@ -145,8 +158,9 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc_kernel(
             if (s > 0 && NDP_LEADER) {
                 if (gact) ndp_bulk_wait_read0();                  // the store has finished reading A
                 // the last group to retire hidden layer s - 1 refills the weight buffer with the next layer
-                if (s < LH && atomicAdd(&S.bcount[s - 1], 1) == nactive - 1)
-                    ndp_stage_bulk(S.B, wimg + (long long)s * NDP_SET128, NDP_SET128, &S.bar_w);
+                // (the first layer again when the CTA has another round)
+                if ((s < LH || more) && atomicAdd(&S.bcount[r * LH + s - 1], 1) == nactive - 1)
+                    ndp_stage_bulk(S.B, wimg + (long long)(s < LH ? s : 0) * NDP_SET128, NDP_SET128, &S.bar_w);
             }
             if (gact && s > 0) ndp_group_sync(1 + g, NDP_GROUP);  // A may be overwritten only after wait_read0
             NDP_T(10 + 4 * s);
@@ -232,8 +246,11 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc_kernel(
             }
         }
         NDP_T(61);
-        if (gact && NDP_LEADER) ndp_bulk_wait0();     // smem must outlive the bulk stores
+        if (gact && NDP_LEADER) ndp_bulk_wait0();     // smem must outlive the bulk stores (and A is rebuilt next round)
         NDP_T(62);
+        tile += 2;
+        active = more && tile * NDP_TP < n;
+        if (active) { ndp_tc_fence_before(); ndp_group_sync(1 + g, NDP_GROUP); ndp_tc_fence_after(); }   // head results read, stores drained
     }
     ndp_tc_fence_before();
     __syncthreads();
@@ -244,8 +261,15 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc_kernel(
 void ndp_launch_fwd_tc(const NdpFwdArgs& a, cudaStream_t s) {
     if (a.npairs <= 0 || a.n <= 0) return;
     const int tiles = (a.n + NDP_TP - 1) / NDP_TP;
-    dim3 grid((tiles + 1) / 2, a.npairs);
-    NDP_LAUNCH(ndp_warp_fwd_tc_kernel, grid, dim3(NDP_FWD_TC_THREADS), ndp_fwd_tc_smem_bytes(), s, a);
+    static int rounds = 0;
+    if (rounds == 0) {
+        rounds = 1;     // measured: more rounds only help at large batches (+1 %) and cost at small ones
+        if (const char* env = getenv("NDP_FWD_ROUNDS")) { const int v = atoi(env); if (v >= 1 && v <= NDP_FWD_MAX_ROUNDS) rounds = v; }
+    }
+    NdpFwdArgs b = a;
+    b.rounds = rounds;
+    dim3 grid((tiles + 2 * rounds - 1) / (2 * rounds), a.npairs);
+    NDP_LAUNCH(ndp_warp_fwd_tc_kernel, grid, dim3(NDP_FWD_TC_THREADS), ndp_fwd_tc_smem_bytes(), s, b);
 }
 
 int ndp_fwd_tc_init() {
