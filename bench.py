@@ -290,11 +290,19 @@ def main():
         bwd_flops = prof_pairs * N * (4 * 2 * 128 * 128 + 2 * 2 * 6 * 128 + 2 * 128 * 6)
         tensor_peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1400.0))   # kernel timed inside a long step
         ach_tf = bwd_flops / max(t_bwd, 1e-12) / 1e12
+        iso_ms = None
+        if traffic.get("pairs_per_launch") == prof_pairs:
+            ku = [(traffic.get(k) or {}).get("gpu__time_duration.sum") for k in ("ndp_warp_bwd_tc_kernel", "ndp_head_grad_kernel")]
+            if all(v is not None for v in ku):
+                iso_ms = sum(ku) * 1e-3
         roofline = {"bound": "tensor", "kernel": "ndp_head_grad_kernel + ndp_warp_bwd_tc_kernel (one backward launch)",
                     "achieved": ach_tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach_tf / tensor_peak,
                     "traffic": (traffic.get("ndp_warp_bwd_tc_kernel") or {}).get("dram_bytes_per_launch"),
                     "peak_source": pk_src + " bf16_tflops_sustained", "algorithmic_flops_per_launch": bwd_flops,
                     "pairs_per_launch": prof_pairs, "launch_ms": 1e3 * t_bwd,
+                    "launch_ms_note": "sampled inside the step with the other stream groups' kernels interleaved on the same SMs; "
+                                      "isolated = the ncu launch (profiles/kernel_traffic.json), same pairs per launch",
+                    "isolated_launch_ms": iso_ms, "isolated_frac": (bwd_flops / (iso_ms * 1e-3) / 1e12 / tensor_peak) if iso_ms else None,
                     "note": "fp32-accurate products are issued as 3 fp16 MMAs: issued tensor flops = 3x algorithmic"}
         # the metric's second half: one Chamfer call (NN search + epilogue) against the HBM roof
         alg_bytes = prof_pairs * (20 * (N + N) + 12 * N + 4)          # 425 988 B per pair at 8192^2

@@ -236,7 +236,7 @@ extern "C" int ndp_adam_step(const ndp_layer_cfg* c, float* params, const float*
 // =================================================================================================
 // Fused per-pair driver
 // =================================================================================================
-#define NDP_MAX_STREAMS 4
+#define NDP_MAX_STREAMS 8
 struct ndp_solver {
     ndp_solver_cfg cfg;
     std::vector<NdpLayout> lay;

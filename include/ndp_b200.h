@@ -49,9 +49,9 @@ int64_t ndp_param_count(const ndp_layer_cfg* cfg);
 int64_t ndp_pack_count(const ndp_layer_cfg* cfg);
 /* Floats the forward pass saves for the backward pass of n points (activations + head vectors). */
 int64_t ndp_saved_floats(const ndp_layer_cfg* cfg, int64_t n);
-/* Where the hidden 128x128 layers run: 0 = tensor cores (tcgen05 / TMEM, operands split exactly into
- * three bf16 terms, six partial products, fp32 accumulation: fp32-level accuracy) -- the default;
- * 1 = FP32 pipes.  Process-wide; a solver captures the mode at creation. */
+/* Where the layer's contractions run: 0 = tensor cores (tcgen05 / TMEM, every fp32 operand split into
+ * an fp16 hi and an fp16 lo term, three partial products, fp32 accumulation: fp32-level accuracy) --
+ * the default; 1 = FP32 pipes.  Process-wide; a solver captures the mode at creation. */
 int ndp_set_mlp_mode(int32_t mode);
 int32_t ndp_get_mlp_mode(void);
 /* Bytes of scratch ndp_layer_backward needs for n points. */
@@ -158,9 +158,10 @@ int64_t ndp_solver_launch_count(const ndp_solver* s);
  * *samples sampled iterations (each sample is one launch of each kernel over
  * ndp_solver_profiled_pairs() pairs).                                                          */
 int ndp_solver_profile(const ndp_solver* s, double* ms, int64_t* samples);
-/* The driver splits a batch into two halves that run on two streams (the second one internal),
- * so that one half's small kernels fill the SM time the other half's tensor-core CTAs leave
- * idle.  The sampled launches of ndp_solver_profile are the FIRST half's: this many pairs each. */
+/* The driver splits a batch into up to four contiguous stream groups (env NDP_SOLVER_STREAMS,
+ * default 4) that run on `stream` and on internal streams, so that one group's small kernels fill
+ * the SM time the other groups' tensor-core CTAs leave idle.  The sampled launches of
+ * ndp_solver_profile are the FIRST group's: this many pairs each.                            */
 int32_t ndp_solver_profiled_pairs(const ndp_solver* s);
 
 #ifdef __cplusplus

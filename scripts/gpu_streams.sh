@@ -1,6 +1,6 @@
 OUT=gpurun_out; mkdir -p $OUT
-for S in 1 2 3 4; do for P in 32; do
-NDP_SOLVER_STREAMS=$S timeout 600 python bench.py --steps 1 --warmup 3 --pairs $P --no-cpu-baseline > $OUT/bench_s${S}_p$P.json 2> $OUT/bench_s${S}_p$P.err
+for S in 4 6 8; do for P in 32 64; do
+NDP_SOLVER_STREAMS=$S timeout 600 python bench.py --steps 1 --warmup 2 --pairs $P --no-cpu-baseline > $OUT/bench_s${S}_p$P.json 2> $OUT/bench_s${S}_p$P.err
 python - <<PY
 import json
 try:
@@ -8,5 +8,3 @@ try:
 except Exception as e: print("failed", e); print(open("$OUT/bench_s${S}_p$P.err").read()[-800:])
 PY
 done; done
-NDP_SOLVER_STREAMS=4 timeout 600 python bench.py --steps 1 --warmup 3 --pairs 16 --no-cpu-baseline | python -c "import json,sys; d=json.loads(sys.stdin.readlines()[-1]); print('streams=4 pairs=16', d['value'])"
-NDP_SOLVER_STREAMS=4 timeout 600 python bench.py --steps 1 --warmup 3 --pairs 64 --no-cpu-baseline | python -c "import json,sys; d=json.loads(sys.stdin.readlines()[-1]); print('streams=4 pairs=64', d['value'])"

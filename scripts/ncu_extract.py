@@ -3,7 +3,7 @@
   profiles/<tag>_stalls_<kernel>.txt      hottest SASS lines / stall reasons (scripts/ncu_stalls.py)
   profiles/<tag>_launches_*.csv           the launch list (gpu__time_duration per launch) + per-kernel shares
   profiles/kernel_traffic.json            dram bytes / duration per launch per kernel (bench.py reads it)
-Usage: python scripts/ncu_extract.py r01 [pairs_per_step]"""
+Usage: python scripts/ncu_extract.py r01 [pairs_per_step] [stream_groups]"""
 import collections
 import csv
 import glob
@@ -16,6 +16,7 @@ import sys
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 pairs = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+groups = int(sys.argv[3]) if len(sys.argv) > 3 else 4          # stream groups of the solver (NDP_SOLVER_STREAMS)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 os.makedirs(PROF, exist_ok=True)
@@ -27,8 +28,8 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__block_size", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
         "smsp__inst_executed.sum"]
 traffic = {"source": f"ncu --set full --clock-control none, bench.py --pairs {pairs} --iters 6 ({tag}): one launch per kernel "
-                     f"= one half-batch of {pairs // 2} pairs of 8192x8192 (cold-cache, serialised)",
-           "pairs_per_launch": pairs // 2}
+                     f"= one stream group of {pairs // groups} pairs of 8192x8192 (cold-cache, serialised)",
+           "pairs_per_launch": pairs // groups}
 for rep in sorted(glob.glob(os.path.join(OUT, "prof_*.ncu-rep"))):
     k = os.path.basename(rep)[5:-8]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -80,7 +81,7 @@ if os.path.exists(ll):
     tot = sum(sum(x) for x in agg.values())
     with open(os.path.join(PROF, f"{tag}_launch_shares_pairs{pairs}.txt"), "w") as f:
         f.write(f"# ncu launch list of `bench.py --steps 1 --warmup 1 --pairs {pairs} --iters 6` (per-launch times are cold-cache and serialised;\n"
-                f"# each launch covers one half-batch of {pairs // 2} pairs); shares of the summed kernel time\n")
+                f"# each launch covers one stream group of {pairs // groups} pairs); shares of the summed kernel time\n")
         for n, x in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
             line = f"{n[:60]:60s} n={len(x):5d} mean={sum(x) / len(x):9.2f} us  share={100 * sum(x) / tot:5.1f}%"
             print(line)
