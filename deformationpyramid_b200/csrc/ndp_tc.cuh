@@ -161,6 +161,35 @@ static inline void ndp_tmem_ld16(unsigned taddr, float (&v)[16]) {
     const int col0 = (int)(taddr & 0xffff), lane = (int)(taddr >> 16) + (int)(threadIdx.x & 31);
     for (int j = 0; j < 16; ++j) v[j] = ndp_emu::tmem[lane][col0 + j];
 }
+template <int N> static inline void ndp_tmem_st(unsigned taddr, const unsigned (&r)[N]) {
+    const int col0 = (int)(taddr & 0xffff), lane = (int)(taddr >> 16) + (int)(threadIdx.x & 31);
+    for (int j = 0; j < N; ++j) memcpy(&ndp_emu::tmem[lane][col0 + j], &r[j], 4);
+}
+static inline void ndp_tmem_wait_st() {}
+// A operand in TMEM: element (m, k) of the 16-deep step = half (k & 1) of the 32-bit cell [lane m][column k / 2]
+static inline void ndp_umma_f16_ta(unsigned tmem_d, unsigned tmem_a, NdpUmmaDesc db, unsigned idesc, unsigned acc) {
+    const int N = (int)((idesc >> 17) & 0x3f) << 3, M = (int)((idesc >> 24) & 0x1f) << 4;
+    const int b_mn = (idesc >> 16) & 1;
+    const int col0 = (int)(tmem_d & 0xffff), lane0 = (int)(tmem_d >> 16), acol0 = (int)(tmem_a & 0xffff), alane0 = (int)(tmem_a >> 16);
+    auto ldb = [](NdpUmmaDesc d, int mn, int k, int is_mn) -> float {
+        const unsigned off = is_mn ? (unsigned)((mn >> 3) * d.sbo + (mn & 7) * 2 + (k >> 3) * d.lbo + (k & 7) * 16)
+                                   : (unsigned)((mn >> 3) * d.sbo + (mn & 7) * 16 + (k >> 3) * d.lbo + (k & 7) * 2);
+        unsigned short h; memcpy(&h, d.p + off, 2);
+        return ndp_f16_to_f32(h);
+    };
+    for (int m = 0; m < M; ++m) {
+        float av[16];
+        for (int k = 0; k < 16; ++k) {
+            unsigned cell; memcpy(&cell, &ndp_emu::tmem[alane0 + m][acol0 + (k >> 1)], 4);
+            av[k] = ndp_f16_to_f32((k & 1) ? (cell >> 16) : (cell & 0xffffu));
+        }
+        for (int n = 0; n < N; ++n) {
+            float sacc = acc ? ndp_emu::tmem[lane0 + m][col0 + n] : 0.0f;
+            for (int k = 0; k < 16; ++k) sacc += av[k] * ldb(db, n, k, b_mn);
+            ndp_emu::tmem[lane0 + m][col0 + n] = sacc;
+        }
+    }
+}
 static inline void ndp_bulk_s2g(void* g, const void* s, unsigned bytes) { memcpy(g, s, bytes); }
 static inline void ndp_bulk_commit() {}
 static inline void ndp_bulk_wait_read0() {}
@@ -222,6 +251,25 @@ __device__ __forceinline__ void ndp_tmem_ld16(unsigned taddr, float (&v)[16]) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
 }
+// this warp's 32 TMEM lanes x N consecutive columns <- N registers per thread (N = 8 or 16)
+template <int N> __device__ __forceinline__ void ndp_tmem_st(unsigned taddr, const unsigned (&r)[N]);
+template <> __device__ __forceinline__ void ndp_tmem_st<8>(unsigned taddr, const unsigned (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+template <> __device__ __forceinline__ void ndp_tmem_st<16>(unsigned taddr, const unsigned (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                   "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void ndp_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// A operand in TMEM (M = 128 lanes, 16-bit elements packed two per 32-bit column, K along the columns)
+__device__ __forceinline__ void ndp_umma_f16_ta(unsigned tmem_d, unsigned tmem_a, NdpUmmaDesc db, unsigned idesc, unsigned acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
 // bulk asynchronous copy shared -> global (TMA store, SASS UBLKCP) in the calling thread's bulk group
 __device__ __forceinline__ void ndp_bulk_s2g(void* g, const void* s, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(ndp_smem_u32(s)), "r"(bytes) : "memory");
@@ -279,6 +327,31 @@ void ndp_umma_gemm3(unsigned tmem_d, NdpUmmaDesc a0, unsigned a_img, unsigned a_
             ndp_umma_f16(tmem_d, da, db, idesc, acc);
             acc = 1u;
             da = ndp_umma_desc_adv(da, a_step);
+            db = ndp_umma_desc_adv(db, b_step);
+        }
+    }
+}
+
+// Same with the A operand in TMEM: ta0 = TMEM address of the hi image (8 columns per 16-deep k-step),
+// ta_img = column distance to the lo image.
+#ifdef NDP_EMU
+static inline
+#else
+static __device__ __forceinline__
+#endif
+void ndp_umma_gemm3_ta(unsigned tmem_d, unsigned ta0, unsigned ta_img, NdpUmmaDesc b0, unsigned b_img, unsigned b_step,
+                       int ksteps, unsigned idesc) {
+    unsigned acc = 0u;
+#pragma unroll 1
+    for (int t = 0; t < 3; ++t) {
+        const int i = (t == 0) ? 1 : 0, j = (t == 1) ? 1 : 0;
+        unsigned ta = ta0 + (unsigned)i * ta_img;
+        NdpUmmaDesc db = ndp_umma_desc_adv(b0, j * b_img);
+#pragma unroll 1
+        for (int ks = 0; ks < ksteps; ++ks) {
+            ndp_umma_f16_ta(tmem_d, ta, db, idesc, acc);
+            acc = 1u;
+            ta += 8u;
             db = ndp_umma_desc_adv(db, b_step);
         }
     }

@@ -50,6 +50,7 @@ static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float3 make_float3(float x, float y, float z) { return float3{x, y, z}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 
 namespace ndp_emu {
 
@@ -159,6 +160,7 @@ static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long 
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+static inline int atomicCAS(int* p, int cmp, int v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
 
 // --- warp collectives
 static inline float __shfl_xor_sync(unsigned, float v, int m) {
