@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc2_kernel
         // the first hidden weight set now; the second one after the input layer's MMAs (every CTA of the wave
         // starts at the same time: asking for 128 KB at once doubles the burst the first layer waits behind)
         if (LH > 0) ndp_stage_bulk(S.W[0], wimg, NDP_SET128, &S.bar_w[0]);
+        NDP_T(2);
     }
     if (tid < 16) S.hb[tid] = (tid < HD) ? __ldg(params + L.head_b[tid]) : 0.0f;
     if (tid < 256) {            // input-layer weight image: row o = tid / 2, 8-column chunk tid & 1
@@ -379,7 +380,9 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc2_kernel
         for (int s = 0; s <= LH; ++s) {
             if (ldw && ndp_elect_one()) {
                 if (s > 0) ndp_mbar_wait(&S.bar_w[s - 1], 0u);            // this layer's weights have landed (once per CTA)
+                NDP_T(40 + 2 * s);
                 ndp_pipe_acquire(&S.pipe_lock);
+                NDP_T(41 + 2 * s);
                 ndp_tc_fence_after();
                 if (s == 0) {
                     ndp_umma_gemm3_ta(tmem + TM2_ACC, tmem + TM2_AOP, TM2_LO, ndp_umma_desc(S.WIN, CS, RS16), NDP_IMG16, 0, 1,

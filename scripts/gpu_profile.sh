@@ -16,7 +16,7 @@ NDP_MLP_MODE=1 timeout 900 python bench.py --steps 1 --warmup 3 --pairs 16 --no-
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python __graft_entry__.py --smoke > $OUT/sanitizer_memcheck.log 2>&1; echo "memcheck exit $?"; tail -2 $OUT/sanitizer_memcheck.log
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 1 --warmup 1 --pairs $P --iters 6 --no-cpu-baseline > $OUT/ncu_launches.log 2>&1; echo "ncu launches exit $?"
-for K in ndp_warp_bwd_tc_kernel ndp_warp_fwd_tc_kernel ndp_nn_pruned_kernel ndp_chamfer_reduce_kernel ndp_reduce_adam_kernel ndp_head_grad_kernel; do
+for K in ndp_warp_bwd_tc_kernel ndp_warp_fwd_tc2_kernel ndp_nn_pruned_kernel ndp_chamfer_reduce_kernel ndp_reduce_adam_kernel ndp_head_grad_kernel; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s 30 -c 1 -f -o $OUT/prof_$K \
       python bench.py --steps 1 --warmup 1 --pairs $P --iters 6 --no-cpu-baseline > $OUT/ncu_$K.log 2>&1
   echo "ncu $K exit $?"
