@@ -87,7 +87,7 @@ if os.path.exists(ll):
             print(line)
             f.write(line + "\n")
 for name in ("bench_default.json", "bench_reference.json", "bench_pairs8.json", "bench_pairs16.json", "bench_fp32pipes_pairs16.json",
-             "smoke.log", "pytest_gpu.log", "sanitizer_memcheck.log", "host.txt", "nvidia-smi.txt"):
+             "smoke.log", "pytest_gpu.log", "sanitizer_memcheck.log", "sanitizer_racecheck.log", "sanitizer_synccheck.log", "host.txt", "nvidia-smi.txt"):
     src = os.path.join(OUT, name)
     if os.path.exists(src):
         shutil.copy(src, os.path.join(PROF, f"{tag}_{name}" if not name.startswith(("host", "nvidia")) else name))
