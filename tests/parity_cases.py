@@ -52,6 +52,34 @@ def check_layers_against_golden(lib, golden_dir, device):
         assert torch.equal(y, y2)
 
 
+def check_layers_vs_oracle_depths(lib, device, cases=((1, 130), (2, 257), (3, 700), (5, 385))):
+    """Layer forward / backward against the oracle (= model/nets.py:111-140 + autograd) for MLP depths the
+    golden set does not hold, at point counts with several tiles, a ragged last tile and an odd tile
+    count: depth 1 has no hidden layer, depth > 3 takes the tensor-core kernels' generic paths (weight
+    buffer refilled per layer, one partial row per tile)."""
+    for depth, n in cases:
+        torch.manual_seed(40 + depth)
+        spec = O.LayerSpec(depth, 128, -8, 3, "axis_angle", False, "SE3")
+        P = O.init_params(spec)
+        for v in P.values():
+            v.add_(0.05 * torch.randn_like(v))
+        P = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+        x = torch.rand(n, 3) - 0.5
+        xo = x.clone().requires_grad_(True)
+        yo, _ = O.layer_forward(spec, P, xo)
+        w = torch.randn(n, 3) / n
+        go = torch.autograd.grad((yo * w).sum(), [xo] + [P[k] for k, _ in O.param_layout(spec)])
+        gflat = torch.cat([g.reshape(-1) for g in go[1:]])
+        cfg = ops.make_layer_cfg(depth, 128, -8, 3, "axis_angle", False, "SE3")
+        params = dev(O.flatten_params(spec, {k: v.detach() for k, v in P.items()}), device)
+        pack = ops.pack_params(cfg, params, lib=lib)
+        y, _, saved = ops.layer_forward(cfg, params, pack, dev(x, device), lib=lib)
+        assert rel(y.cpu().numpy(), yo.detach().numpy()) < REL_TOL, (depth, n)
+        gp, gx = ops.layer_backward(cfg, params, pack, dev(x, device), saved, dev(w, device), None, need_grad_x=True, lib=lib)
+        assert rel(gp.cpu().numpy(), gflat.numpy()) < 5 * REL_TOL, (depth, n)
+        assert rel(gx.cpu().numpy(), go[0].numpy()) < 5 * REL_TOL, (depth, n)
+
+
 def check_chamfer_against_golden(lib, golden_dir, device):
     G = np.load(os.path.join(golden_dir, "chamfer.npz"))
     for name in G["meta"]:

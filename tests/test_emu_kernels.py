@@ -14,7 +14,7 @@ from deformationpyramid_b200.synthetic import make_pair
 from oracle import ndp_oracle as O
 from emu_util import emu_lib
 
-from parity_cases import (check_layers_against_golden, check_chamfer_against_golden, check_adam,
+from parity_cases import (check_layers_against_golden, check_layers_vs_oracle_depths, check_chamfer_against_golden, check_adam,
                           check_trajectory_teacher_forced, check_solver_against_oracle,
                           check_chamfer_vs_oracle_random, check_culled_search_equals_brute_force,
                           check_solver_repeatable, check_fp32_pipe_mode)
@@ -27,6 +27,10 @@ def lib():
 
 def test_layers_golden(lib, golden_dir):
     check_layers_against_golden(lib, golden_dir, device="cpu")
+
+
+def test_layers_other_depths_vs_oracle(lib):
+    check_layers_vs_oracle_depths(lib, "cpu", cases=((1, 130), (2, 257), (5, 385)))
 
 
 def test_chamfer_golden(lib, golden_dir):

@@ -8,7 +8,8 @@ import torch
 from deformationpyramid_b200 import ops
 from deformationpyramid_b200.synthetic import make_pair
 from oracle import ndp_oracle as O
-from parity_cases import (REL_TOL, rel, check_layers_against_golden, check_chamfer_against_golden, check_adam,
+from parity_cases import (REL_TOL, rel, check_layers_against_golden, check_layers_vs_oracle_depths,
+                          check_chamfer_against_golden, check_adam,
                           check_trajectory_teacher_forced, check_solver_against_oracle,
                           check_chamfer_vs_oracle_random, check_culled_search_equals_brute_force,
                           check_solver_repeatable, check_fp32_pipe_mode)
@@ -32,6 +33,10 @@ def test_library_is_the_cuda_build(lib):
 
 def test_layers_golden(lib, golden_dir):
     check_layers_against_golden(lib, golden_dir, DEV)
+
+
+def test_layers_other_depths_vs_oracle(lib):
+    check_layers_vs_oracle_depths(lib, DEV)
 
 
 def test_chamfer_golden(lib, golden_dir):
