@@ -165,7 +165,7 @@ extern "C" int ndp_layer_backward(const ndp_layer_cfg* c, const float* params, c
     r.partials = (const float*)workspace; r.partials_stride = 0; r.partial_pitch = b.partial_pitch;
     r.n = (int)n; r.counts = nullptr; r.grads_out = grad_params; r.grads_stride = 0; r.state = nullptr;
     r.fixed_step = 0; r.lr = r.beta1 = r.beta2 = r.eps = 0.0; r.do_adam = 0; r.npairs = 1;
-    r.tiles_per_row = g_mlp_mode == 0 ? ndp_bwd_tc_tiles_per_cta(L.hidden) : 1;
+    r.tiles_per_row = g_mlp_mode == 0 ? ndp_bwd_tc_tiles_per_cta(L.hidden, (int)n) : 1;
     ndp_launch_adam(r, (cudaStream_t)stream);
     CK(cudaGetLastError());
     return NDP_OK;
@@ -481,7 +481,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         ad.partials = s->partials; ad.partials_stride = b.partials_stride; ad.partial_pitch = s->Ppad;
         ad.n = s->S; ad.counts = s->ncount; ad.grads_out = nullptr; ad.grads_stride = 0; ad.state = s->state;
         ad.fixed_step = 0; ad.lr = c.lr; ad.beta1 = 0.9; ad.beta2 = 0.999; ad.eps = 1e-8; ad.do_adam = 1; ad.npairs = npairs;
-        ad.tiles_per_row = s->mlp_mode == 0 ? ndp_bwd_tc_tiles_per_cta(L.hidden) : 1;
+        ad.tiles_per_row = s->mlp_mode == 0 ? ndp_bwd_tc_tiles_per_cta(L.hidden, s->S) : 1;
 
         // the batch is split into stream groups (contiguous pair ranges, sizes differ by at most one)
         const int ng = npairs < s->nstreams ? npairs : s->nstreams;

@@ -52,7 +52,7 @@ struct NdpBwdArgs {
     int pair0 = 0;
     int tpc = 1;                                       // tensor-core version: tiles per CTA = tiles per partial row (set by the launcher)
 };
-int ndp_bwd_tc_tiles_per_cta(int hidden);
+int ndp_bwd_tc_tiles_per_cta(int hidden, int n);
 #define NDP_HGREC (NDP_TP * 24)    // floats per tile: hg[128][16], e[128][8] (e[0][7] = tile max |hg|)
 void ndp_launch_bwd(const NdpBwdArgs& a, cudaStream_t s);
 void ndp_launch_bwd_tc(const NdpBwdArgs& a, cudaStream_t s);   // needs `pack` (weight image sets)

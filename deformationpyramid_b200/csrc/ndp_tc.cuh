@@ -322,7 +322,7 @@ void ndp_umma_gemm3(unsigned tmem_d, NdpUmmaDesc a0, unsigned a_img, unsigned a_
     for (int t = 0; t < 3; ++t) {
         const int i = (t == 0) ? 1 : 0, j = (t == 1) ? 1 : 0;
         NdpUmmaDesc da = ndp_umma_desc_adv(a0, i * a_img), db = ndp_umma_desc_adv(b0, j * b_img);
-#pragma unroll 1
+#pragma unroll 4
         for (int ks = 0; ks < ksteps; ++ks) {
             ndp_umma_f16(tmem_d, da, db, idesc, acc);
             acc = 1u;
@@ -347,7 +347,7 @@ void ndp_umma_gemm3_ta(unsigned tmem_d, unsigned ta0, unsigned ta_img, NdpUmmaDe
         const int i = (t == 0) ? 1 : 0, j = (t == 1) ? 1 : 0;
         unsigned ta = ta0 + (unsigned)i * ta_img;
         NdpUmmaDesc db = ndp_umma_desc_adv(b0, j * b_img);
-#pragma unroll 1
+#pragma unroll 4
         for (int ks = 0; ks < ksteps; ++ks) {
             ndp_umma_f16_ta(tmem_d, ta, db, idesc, acc);
             acc = 1u;

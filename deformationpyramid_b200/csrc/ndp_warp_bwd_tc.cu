@@ -444,20 +444,24 @@ __global__ void __launch_bounds__(NDP_BWD_TC_THREADS, 1) ndp_warp_bwd_tc_kernel(
 
 // Tiles whose gradients one CTA accumulates (= tiles per partial row).  The dW accumulators are per
 // layer parity, so accumulation over tiles needs at most two hidden layers.
-int ndp_bwd_tc_tiles_per_cta(int hidden) {
-    static int tpc = 0;
-    if (tpc == 0) {
-        tpc = 4;    // fixed (not a function of the batch): the summation grouping must not depend on what a pair is batched with
-        if (const char* env = getenv("NDP_BWD_TPC")) { const int v = atoi(env); if (v >= 1 && v <= 16) tpc = v; }
-    }
-    return hidden <= 2 ? tpc : 1;
+int ndp_bwd_tc_tiles_per_cta(int hidden, int n) {
+    int forced = 0;             // read on every call so that tests can switch it
+    if (const char* env = getenv("NDP_BWD_TPC")) { const int v = atoi(env); if (v >= 1 && v <= 16) forced = v; }
+    if (hidden > 2) return 1;
+    if (forced > 0) return forced;
+    // A function of the cloud size only (never of the batch: the summation grouping must not depend on what
+    // a pair is batched with): at least 16 CTAs per pair, at most 8 tiles per CTA.  8192 points -> 4.
+    const int tiles = (n + NDP_TP - 1) / NDP_TP;
+    int tpc = 1;
+    while (tpc < 8 && tiles / (2 * tpc) >= 16) tpc *= 2;
+    return tpc;
 }
 void ndp_launch_bwd_tc(const NdpBwdArgs& a, cudaStream_t s) {
     if (a.npairs <= 0 || a.n <= 0) return;
     const int tiles = (a.n + NDP_TP - 1) / NDP_TP;
     NDP_LAUNCH(ndp_head_grad_kernel, dim3(tiles, a.npairs), dim3(NDP_TP), 0, s, a);
     NdpBwdArgs b = a;
-    b.tpc = ndp_bwd_tc_tiles_per_cta(a.lay.hidden);
+    b.tpc = ndp_bwd_tc_tiles_per_cta(a.lay.hidden, a.n);
     NDP_LAUNCH(ndp_warp_bwd_tc_kernel, dim3((tiles + b.tpc - 1) / b.tpc, a.npairs), dim3(NDP_BWD_TC_THREADS), ndp_bwd_tc_smem_bytes(), s, b);
 }
 

@@ -29,6 +29,14 @@ def test_layers_golden(lib, golden_dir):
     check_layers_against_golden(lib, golden_dir, device="cpu")
 
 
+def test_backward_accumulates_over_tiles(lib, monkeypatch):
+    """Gradients of several tiles accumulated in TMEM by one CTA (what 8192-point clouds use) on small inputs."""
+    monkeypatch.setenv("NDP_BWD_TPC", "4")
+    check_layers_vs_oracle_depths(lib, "cpu", cases=((3, 700), (2, 257)))
+    monkeypatch.setenv("NDP_BWD_TPC", "2")
+    check_layers_vs_oracle_depths(lib, "cpu", cases=((3, 385),))
+
+
 def test_layers_other_depths_vs_oracle(lib):
     check_layers_vs_oracle_depths(lib, "cpu", cases=((1, 130), (2, 257), (5, 385)))
 
