@@ -8,9 +8,10 @@ A "step" registers `--pairs` independent synthetic pairs per GPU (fixed-iteratio
 stop disabled, exactly levels x iters Adam iterations per pair).  One JSON line on stdout (rank 0).
   value : pairs/s with the clouds, weights and permutations already resident in HBM
           (ndp_solver_register_device), device time from CUDA events, max over ranks.
-  e2e   : pairs/s through Registration.register_batch(host=True): weight construction on the host,
+  e2e   : pairs/s through Registration.register_batches(host=True): weight construction on the host,
           pinned-host -> device copies, the optimisation, device -> host read-back of the warped
-          clouds, all inside the timed region (wall clock bracketed by synchronize, max over ranks).
+          clouds, all inside the timed region (wall clock bracketed by synchronize, max over ranks);
+          the host preparation of the next batch overlaps the GPU work of the current one.
 --impl reference times the CPU oracle port of the same path (oracle/ndp_oracle.py + the C kNN loop)
 on the host cores over a bounded sample of the same workload (see cpu_baseline.sample).
 """
@@ -255,8 +256,10 @@ def main():
         reg.register_batch(h_pairs, seeds=gids, host=True)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(a.steps):
-        warped, _, last_e2e = reg.register_batch(h_pairs, seeds=gids, host=True)
+    # every step = one batch through the public API: weights + permutations built on the host, pinned host ->
+    # device copies, optimisation, device -> host read-back; the host preparation of step k + 1 overlaps the
+    # GPU work of step k (Registration.register_batches), all of it inside the timed region
+    for warped, _, last_e2e in reg.register_batches([h_pairs] * a.steps, seeds=[gids] * a.steps, host=True):
         if dist is not None:                              # the path's only collective: final metric gather
             g = [torch.empty_like(last_e2e[:, -1].to(dev)) for _ in range(world)]
             dist.all_gather(g, last_e2e[:, -1].contiguous().to(dev))

@@ -131,6 +131,11 @@ class Registration():
         which makes every pair's result independent of batching and of the rank it runs on.
         host=True: clouds are CPU tensors; host<->device copies happen inside the native call.
         Returns (list of warped clouds, iters [npairs, m], last loss [npairs, m])."""
+        return self._run_prepared(self._prepare_batch(pairs, seeds, host), host)
+
+    def _prepare_batch(self, pairs, seeds, host):
+        """Host-side part of register_batch: per pair the pyramid's fresh weights (reference RNG order,
+        nets.py:20-30,180-183) and the two sampling permutations (registration.py:156-157)."""
         config = self.config
         if config.w_reg > 0:
             raise NotImplementedError("register_batch covers the Chamfer-only NDP objective")
@@ -148,11 +153,35 @@ class Registration():
             else:
                 srcs.append(src.to(dev).contiguous()); tgts.append(tgt.to(dev).contiguous())
                 flats.append(layers_cpu.to(dev)); sps.append(sp.to(dev)); tps.append(tp.to(dev))
+        return srcs, tgts, flats, sps, tps
+
+    def _run_prepared(self, prepared, host):
+        srcs, tgts, flats, sps, tps = prepared
+        dev = torch.device("cuda", self.device) if isinstance(self.device, int) else torch.device(self.device)
         self.src_pcd = srcs[0] if not host else srcs[0].to(dev)   # keeps _get_solver's device key valid
-        solver = self._get_solver(len(pairs), max(s.shape[0] for s in srcs), max(t.shape[0] for t in tgts))
+        solver = self._get_solver(len(srcs), max(s.shape[0] for s in srcs), max(t.shape[0] for t in tgts))
         warped, iters, losses = solver.register(srcs, tgts, flats, sps, tps, host=host)
         self.last_iters, self.last_losses = iters, losses
         return warped, iters, losses
+
+    def register_batches(self, batches, seeds=None, host: bool = True):
+        """Generator over a sequence of batches (each a list of (src, tgt) pairs): yields register_batch's
+        result per batch.  The host-side preparation of batch k + 1 (weight construction in the reference's
+        RNG order, permutations) runs in a worker thread while batch k is being optimised on the GPU -- the
+        native call releases the GIL.  Same results as calling register_batch per batch; `seeds` is a
+        sequence of per-batch seed lists (or None).  The preparation uses torch's global CPU generator
+        (like the reference): do not draw from it in the consuming thread while the generator is active."""
+        from concurrent.futures import ThreadPoolExecutor
+        batches = list(batches)
+        if not batches:
+            return
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            nxt = pool.submit(self._prepare_batch, batches[0], None if seeds is None else seeds[0], host)
+            for k in range(len(batches)):
+                prepared = nxt.result()
+                if k + 1 < len(batches):
+                    nxt = pool.submit(self._prepare_batch, batches[k + 1], None if seeds is None else seeds[k + 1], host)
+                yield self._run_prepared(prepared, host)
 
     # ------------------------------------------------------------------------------------------
     def _optimize_stepwise(self, timer=None):

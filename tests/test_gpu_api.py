@@ -154,8 +154,13 @@ def test_register_batch_seeded_is_batch_independent():
     w_all, it_all, _ = reg.register_batch(pairs, seeds=[5, 6, 7])
     w_one, it_one, _ = reg.register_batch([pairs[2]], seeds=[7])
     assert torch.equal(w_all[2], w_one[0]) and torch.equal(it_all[2], it_one[0])
-    w_host, _, _ = reg.register_batch([(s.pin_memory(), t.pin_memory()) for s, t in pairs], seeds=[5, 6, 7], host=True)
+    hp = [(s.pin_memory(), t.pin_memory()) for s, t in pairs]
+    w_host, _, _ = reg.register_batch(hp, seeds=[5, 6, 7], host=True)
     assert torch.equal(w_host[1], w_all[1].cpu())
+    # pipelined generator (host preparation of batch k + 1 under the GPU work of batch k): same results
+    outs = list(reg.register_batches([hp, hp[:2], hp], seeds=[[5, 6, 7], [5, 6], [5, 6, 7]], host=True))
+    assert len(outs) == 3 and torch.equal(outs[0][0][2], w_host[2]) and torch.equal(outs[2][0][0], w_host[0])
+    assert torch.equal(outs[1][0][1], w_host[1])
 
 
 def test_errors_are_loud():
