@@ -274,7 +274,41 @@ class Registration():
 
 def _init_flat_cpu(config) -> torch.Tensor:
     """Fresh weights of a whole pyramid drawn on the CPU in the reference's RNG order, flattened
-    (level 0 first).  Building the nn.Modules on the CPU never touches the CUDA library."""
+    (level 0 first), without building nn.Modules: per level the nn.Linear default initialisation of every
+    sub-module in construction order (weight U(+-1/sqrt(fan_in)) = kaiming_uniform(a=sqrt(5)), then bias
+    U(+-1/sqrt(fan_in)); nets.py:75-101), then Xavier uniform over every weight in parameters() order
+    (nets.py:180-183).  Consumes torch's global CPU generator exactly like
+    `Deformation_Pyramid(...)` does (tests/test_cabi_and_host.py compares the two bit for bit)."""
+    import math
+    W = config.width
+    linears = [(W, 6)] + [(W, W)] * (config.depth - 1)
+    if config.motion_type in ("Sim3", "SE3"):
+        rdim = {"axis_angle": 3, "euler": 3, "quaternion": 4, "6D": 6}.get(config.rotation_format)
+        if rdim is not None:
+            linears.append((rdim, W))
+        if config.motion_type == "Sim3":
+            linears.append((1, W))
+    linears.append((3, W))
+    per_level = sum(o * i + o for o, i in linears)
+    flat = torch.empty(config.m * per_level, dtype=torch.float32)
+    off = 0
+    for _ in range(config.m):
+        views = []
+        for o, i in linears:
+            b = 1.0 / math.sqrt(i)
+            w = flat[off:off + o * i].view(o, i); off += o * i
+            bias = flat[off:off + o]; off += o
+            w.uniform_(-b, b)
+            bias.uniform_(-b, b)
+            views.append(w)
+        for w in views:
+            a = math.sqrt(3.0) * math.sqrt(2.0 / float(w.shape[0] + w.shape[1]))     # xavier_uniform_, gain 1
+            w.uniform_(-a, a)
+    return flat
+
+
+def _init_flat_modules(config) -> torch.Tensor:
+    """The same through the nn.Module constructors (the reference's own path); kept as the cross-check."""
     from .nets import NDPLayer
     chunks = []
     for i in range(config.m):

@@ -88,6 +88,19 @@ def test_constructor_matches_reference_rng_stream(golden_dir):
         assert [n for n, _ in layer.named_parameters()] == list(G[f"v{vi}_names"])
 
 
+def test_fast_weight_init_equals_module_constructors_bit_for_bit():
+    """register_batch draws a pyramid's weights without building nn.Modules; values AND the generator state
+    afterwards must equal the Deformation_Pyramid constructor path (= the reference's RNG order)."""
+    from deformationpyramid_b200.config import ndp_config
+    from deformationpyramid_b200.model.registration import _init_flat_cpu, _init_flat_modules
+    for kw in (dict(), dict(motion_type="Sim3", rotation_format="euler"), dict(rotation_format="6D"),
+               dict(motion_type="sflow"), dict(depth=4, m=3), dict(rotation_format="quaternion", m=2)):
+        cfg = ndp_config(samples=100, device=0, **kw)
+        torch.manual_seed(11); a = _init_flat_cpu(cfg); ra = torch.rand(4)
+        torch.manual_seed(11); b = _init_flat_modules(cfg); rb = torch.rand(4)
+        assert torch.equal(a, b) and torch.equal(ra, rb), kw
+
+
 def test_flatten_parameters_keeps_values_and_optimizer_semantics():
     from deformationpyramid_b200.model.nets import NDPLayer
     torch.manual_seed(0)
