@@ -302,11 +302,11 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc2_kernel
 
     const int tid = threadIdx.x, pair = blockIdx.y + a.pair0;
     const int g = tid >> 8, gt = tid & (NDP_GROUP - 1);          // tile group, thread within the group
-    const int tile = blockIdx.x * 2 + g;
+    const int rounds = a.rounds;                                 // CTA = tiles [2 rounds bx, 2 rounds (bx + 1)): round r, group g -> tile
+    const int tile_first = blockIdx.x * 2 * rounds;
     const int n = a.counts ? a.counts[pair] : a.n;
-    if (blockIdx.x * 2 * NDP_TP >= n) return;
+    if (tile_first * NDP_TP >= n) return;
     if (a.state && a.state[pair].stopped) return;
-    const bool active = tile * NDP_TP < n;
     const NdpLayout& L = a.lay;
     const float* params = a.params + (long long)pair * a.params_stride;
     const unsigned char* wimg = (const unsigned char*)(a.pack + (long long)pair * a.pack_stride + L.pack_img);
@@ -314,8 +314,7 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc2_kernel
     const int warp = tid >> 5, p = gt & (NDP_TP - 1), half = gt >> 7;
     const bool ldw = (ndp_warp_uniform(warp) & 7) == 0;   // the group's issuing warp: one elected lane launches the MMAs
     const int RS = NDP_IMG_RS(128), CS = NDP_IMG_CS, RS16 = NDP_IMG_RS(16);
-    unsigned char* gact = a.act ? (unsigned char*)a.act + ((long long)pair * a.act_stride) * 4 +
-                                      (long long)tile * (LH + 1) * NDP_SET128 : nullptr;
+    unsigned char* const gact_pair = a.act ? (unsigned char*)a.act + ((long long)pair * a.act_stride) * 4 : nullptr;
     float* xs = S.xs[g];
 
     NDP_T(0);
@@ -342,22 +341,29 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc2_kernel
         for (int j = 0; j < 8; ++j) v[j] = (r < HD) ? __ldg(params + L.head_w[r] + c8 * 8 + j) : 0.0f;   // head rows are not 16-byte aligned
         ndp_store_chunk2(S.HW, NDP_HWIMG, ndp_img_off(r, c8 * 8, RS), v);
     }
-    unsigned ehi[8], elo[8];    // this point's positional encoding (nets.py:164-177) as packed fp16 hi / lo pairs
+    // this point's positional encoding (nets.py:164-177) as packed fp16 hi / lo pairs -> the first 8 columns
+    // (K = 16) of the group's TMEM operand images; also the point itself for the warp composition
+    auto stage_points = [&](int tile, unsigned tl) {
+        if (gt < NDP_TP) {
+            unsigned ehi[8], elo[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { ehi[j] = 0u; elo[j] = 0u; }
-    if (gt < NDP_TP) {
-        const int gp = tile * NDP_TP + gt;
-        float px = 0.0f, py = 0.0f, pz = 0.0f;
-        if (gp < n) {
-            const float* xp = a.x + (long long)pair * a.x_stride + (long long)gp * 3;
-            px = __ldg(xp); py = __ldg(xp + 1); pz = __ldg(xp + 2);
+            for (int j = 0; j < 8; ++j) { ehi[j] = 0u; elo[j] = 0u; }
+            const int gp = tile * NDP_TP + gt;
+            float px = 0.0f, py = 0.0f, pz = 0.0f;
+            if (gp < n) {
+                const float* xp = a.x + (long long)pair * a.x_stride + (long long)gp * 3;
+                px = __ldg(xp); py = __ldg(xp + 1); pz = __ldg(xp + 2);
+            }
+            xs[gt * 4 + 0] = px; xs[gt * 4 + 1] = py; xs[gt * 4 + 2] = pz;
+            float sn, cs;
+            sincosf(px * L.freq, &sn, &cs); ndp_split2_pair(sn, cs, ehi[0], elo[0]);
+            sincosf(py * L.freq, &sn, &cs); ndp_split2_pair(sn, cs, ehi[1], elo[1]);
+            sincosf(pz * L.freq, &sn, &cs); ndp_split2_pair(sn, cs, ehi[2], elo[2]);
+            ndp_tmem_st<8>(tl + TM2_AOP, ehi);
+            ndp_tmem_st<8>(tl + TM2_AOP + TM2_LO, elo);
+            ndp_tmem_wait_st();
         }
-        xs[gt * 4 + 0] = px; xs[gt * 4 + 1] = py; xs[gt * 4 + 2] = pz;
-        float sn, cs;
-        sincosf(px * L.freq, &sn, &cs); ndp_split2_pair(sn, cs, ehi[0], elo[0]);
-        sincosf(py * L.freq, &sn, &cs); ndp_split2_pair(sn, cs, ehi[1], elo[1]);
-        sincosf(pz * L.freq, &sn, &cs); ndp_split2_pair(sn, cs, ehi[2], elo[2]);
-    }
+    };
     ndp_tc_fence_before();
     ndp_fence_proxy_async();
     __syncthreads();
@@ -366,20 +372,19 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc2_kernel
     const unsigned tmem = S.tmem_slot + (unsigned)g * 256u;
     const unsigned tlane = tmem + ((unsigned)((warp & 3) * 32) << 16);
 
-    if (active) {
-        unsigned mph = 0;
-        if (gt < NDP_TP) {      // [e | 0] -> the first 8 columns (K = 16) of the operand images
-            ndp_tmem_st<8>(tlane + TM2_AOP, ehi);
-            ndp_tmem_st<8>(tlane + TM2_AOP + TM2_LO, elo);
-            ndp_tmem_wait_st();
-        }
+    unsigned mph = 0;
+    for (int r = 0; r < rounds; ++r) {
+        const int tile = tile_first + 2 * r + g;
+        if (tile * NDP_TP >= n) break;                  // group-uniform: this group has no further tile
+        unsigned char* gact = gact_pair ? gact_pair + (long long)tile * (LH + 1) * NDP_SET128 : nullptr;
+        stage_points(tile, tlane);
         ndp_tc_fence_before();
         ndp_group_sync(1 + g, NDP_GROUP);
         // ---- stage s = 0: input layer; s = 1..LH: hidden layer s - 1.  MMAs by the group's elected thread,
         //      then the epilogue h = relu(acc + bias) re-split into the TMEM operand images (and saved to HBM).
         for (int s = 0; s <= LH; ++s) {
             if (ldw && ndp_elect_one()) {
-                if (s > 0) ndp_mbar_wait(&S.bar_w[s - 1], 0u);            // this layer's weights have landed (once per CTA)
+                if (s > 0 && r == 0) ndp_mbar_wait(&S.bar_w[s - 1], 0u);  // this layer's weights have landed (once per CTA)
                 NDP_T(40 + 2 * s);
                 ndp_pipe_acquire(&S.pipe_lock);
                 NDP_T(41 + 2 * s);
@@ -393,7 +398,7 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc2_kernel
                 }
                 ndp_umma_commit(&S.bar_mma[g]);
                 ndp_pipe_release(&S.pipe_lock);
-                if (s == 0 && g == 0 && LH > 1) ndp_stage_bulk(S.W[1], wimg + NDP_SET128, NDP_SET128, &S.bar_w[1]);
+                if (s == 0 && r == 0 && g == 0 && LH > 1) ndp_stage_bulk(S.W[1], wimg + NDP_SET128, NDP_SET128, &S.bar_w[1]);
                 NDP_T(8 + 4 * s);
             }
             ndp_mbar_wait(&S.bar_mma[g], mph); mph ^= 1;
@@ -441,6 +446,9 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc2_kernel
         NDP_T(60);
         ndp_fwd_point_tail(a, L, pair, tile, n, gt, HD, tlane + TM2_ACC, xs, S.hb);
         NDP_T(61);
+        ndp_tc_fence_before();
+        ndp_group_sync(1 + g, NDP_GROUP);               // head results read, xs consumed: the next round may overwrite them
+        ndp_tc_fence_after();
     }
     if (tid == 0) for (int l = 0; l < LH; ++l) ndp_mbar_wait(&S.bar_w[l], 0u);   // the weight copies must not outlive the CTA's shared memory
     ndp_tc_fence_before();
@@ -463,7 +471,15 @@ void ndp_launch_fwd_tc(const NdpFwdArgs& a, cudaStream_t s) {
         if (const char* env = getenv("NDP_FWD_TC_VERSION")) { const int v = atoi(env); if (v == 1 || v == 2) version = v; }
     }
     if (version == 2 && a.lay.hidden <= 2) {      // A operand in TMEM, both hidden weight sets resident
-        NDP_LAUNCH(ndp_warp_fwd_tc2_kernel, dim3((tiles + 1) / 2, a.npairs), dim3(NDP_FWD_TC_THREADS), ndp_fwd_tc2_smem_bytes(), s, a);
+        static int rounds2 = 0;
+        if (rounds2 == 0) {
+            rounds2 = 1;
+            if (const char* env = getenv("NDP_FWD_ROUNDS2")) { const int v = atoi(env); if (v >= 1 && v <= 8) rounds2 = v; }
+        }
+        NdpFwdArgs b2 = a;
+        b2.rounds = rounds2;
+        NDP_LAUNCH(ndp_warp_fwd_tc2_kernel, dim3((tiles + 2 * rounds2 - 1) / (2 * rounds2), a.npairs), dim3(NDP_FWD_TC_THREADS),
+                   ndp_fwd_tc2_smem_bytes(), s, b2);
         return;
     }
     NdpFwdArgs b = a;
