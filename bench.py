@@ -58,7 +58,11 @@ def workload(a):
                         + ("early stop disabled (fixed-iter mode A)" if a.mode == "fixed"
                            else "shipped early-stop thresholds (mode B)"),
             "points": a.points, "levels": a.levels, "iters_per_level": a.iters, "mode": a.mode,
-            "pairs_per_step_per_gpu": a.pairs, "streams": os.environ.get("NDP_SOLVER_STREAMS", "4") + " stream groups (contiguous pair ranges)",
+            "pairs_per_step_per_gpu": a.pairs,
+            "tuning": "NDP_BWD_TPC=%s tiles per backward CTA, NDP_FWD_ROUNDS2=%s tile-pair rounds per forward CTA "
+                      "(throughput profile 8 / 2 from 16 pairs per step, library defaults below)"
+                      % (os.environ.get("NDP_BWD_TPC", "default"), os.environ.get("NDP_FWD_ROUNDS2", "default")),
+            "streams": os.environ.get("NDP_SOLVER_STREAMS", "4") + " stream groups (contiguous pair ranges)",
             "mlp": "tcgen05 fp16 hi/lo split, 3 partial products, fp32 accumulate (fp32-accurate)" if os.environ.get("NDP_MLP_MODE", "0") == "0" else "fp32 pipes", "nn_search": "exact culled (Morton blocks + boxes + seeds)" if a.nn_mode == 0 else "brute force", "width": 128, "depth": 3, "motion": "SE3", "rotation": "axis_angle",
             "l2": "flushed (256 MiB write) between timed steps; one step streams >= 100 MiB of saved activations "
                   "and gradient partials per iteration (larger than L2)"}
@@ -176,6 +180,12 @@ def main():
         run_reference(a, rank)
         return
 
+    # Throughput profile of the library for large batches (documented in INTEGRATION.md): 8 instead of 4 tiles
+    # per backward CTA and two tile-pair rounds per forward CTA.  Both only regroup work (fewer, longer CTAs);
+    # the latency-oriented defaults are better below ~16 pairs per step.
+    if a.pairs >= 16:
+        os.environ.setdefault("NDP_BWD_TPC", "8")
+        os.environ.setdefault("NDP_FWD_ROUNDS2", "2")
     from deformationpyramid_b200 import ops
     from deformationpyramid_b200.config import ndp_config
     from deformationpyramid_b200.model.registration import Registration, _init_flat_cpu

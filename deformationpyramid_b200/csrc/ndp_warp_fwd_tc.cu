@@ -471,11 +471,8 @@ void ndp_launch_fwd_tc(const NdpFwdArgs& a, cudaStream_t s) {
         if (const char* env = getenv("NDP_FWD_TC_VERSION")) { const int v = atoi(env); if (v == 1 || v == 2) version = v; }
     }
     if (version == 2 && a.lay.hidden <= 2) {      // A operand in TMEM, both hidden weight sets resident
-        static int rounds2 = 0;
-        if (rounds2 == 0) {
-            rounds2 = 1;
-            if (const char* env = getenv("NDP_FWD_ROUNDS2")) { const int v = atoi(env); if (v >= 1 && v <= 8) rounds2 = v; }
-        }
+        int rounds2 = 1;          // read on every call so that tests / the throughput profile can switch it
+        if (const char* env = getenv("NDP_FWD_ROUNDS2")) { const int v = atoi(env); if (v >= 1 && v <= 8) rounds2 = v; }
         NdpFwdArgs b2 = a;
         b2.rounds = rounds2;
         NDP_LAUNCH(ndp_warp_fwd_tc2_kernel, dim3((tiles + 2 * rounds2 - 1) / (2 * rounds2), a.npairs), dim3(NDP_FWD_TC_THREADS),

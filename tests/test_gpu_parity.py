@@ -41,6 +41,10 @@ def test_backward_accumulates_over_tiles(lib, monkeypatch):
     check_layers_vs_oracle_depths(lib, DEV, cases=((3, 700), (2, 257)))
     monkeypatch.setenv("NDP_BWD_TPC", "2")
     check_layers_vs_oracle_depths(lib, DEV, cases=((3, 385),))
+    # the throughput profile bench.py uses: 8 tiles per backward CTA, 2 tile-pair rounds per forward CTA
+    monkeypatch.setenv("NDP_BWD_TPC", "8")
+    monkeypatch.setenv("NDP_FWD_ROUNDS2", "2")
+    check_layers_vs_oracle_depths(lib, DEV, cases=((3, 1300),) if DEV != "cpu" else ((3, 700),))
 
 
 def test_layers_other_depths_vs_oracle(lib):
