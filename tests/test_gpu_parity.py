@@ -154,6 +154,41 @@ def test_solver_brute_force_mode(lib):
 def test_culled_search_equals_brute_force(lib):
     check_culled_search_equals_brute_force(lib, DEV)
     check_culled_search_equals_brute_force(lib, DEV, n=4200, m=4100, samples=4096, levels=2, iters=12)
+    check_culled_search_equals_brute_force(lib, DEV, n=8300, m=8250, samples=8192, levels=1, iters=6)   # BASELINE size
+
+
+def test_full_size_regrouping_invariance(lib, monkeypatch):
+    """BASELINE.json size (8192 samples): the tensor-core path's work grouping (tiles per backward CTA,
+    tile-pair rounds per forward CTA, stream groups) only regroups fp32 sums -- loss curves of a short
+    run agree to rounding across groupings, and each grouping is bit-reproducible."""
+    from deformationpyramid_b200 import ops
+    from deformationpyramid_b200.synthetic import make_pair
+    from oracle import ndp_oracle as O
+    levels, iters, S = 2, 5, 8192
+    specs = O.make_specs(3, 128, -8, levels, "axis_angle")
+    pairs = [make_pair(90 + p, S, S) for p in range(3)]
+    torch.manual_seed(1)
+    flats0 = [torch.cat([O.flatten_params(s, O.init_params(s)) for s in specs]) for _ in pairs]
+
+    def run():
+        solver = ops.Solver(max_pairs=3, max_src_points=S, max_tgt_points=S, samples=S, levels=levels, k0=-8, depth=3,
+                            width=128, motion="SE3", rotation_format="axis_angle", iters=iters, max_break_count=10 ** 9,
+                            break_threshold_ratio=0.001, lr=0.01, record_loss=True, lib=lib)
+        warped, _, _ = solver.register([a.to(DEV) for a, _ in pairs], [b.to(DEV) for _, b in pairs],
+                                       [f.clone().to(DEV) for f in flats0])
+        out = torch.stack([solver.losses(p) for p in range(3)]), [w.cpu() for w in warped]
+        solver.close()
+        return out
+    base, wbase = run()
+    again, wagain = run()
+    assert torch.equal(base, again) and all(torch.equal(a, b) for a, b in zip(wbase, wagain))
+    for tpc, rounds, streams in (("1", "1", "1"), ("8", "2", "3"), ("2", "4", "2")):
+        monkeypatch.setenv("NDP_BWD_TPC", tpc); monkeypatch.setenv("NDP_FWD_ROUNDS2", rounds)
+        monkeypatch.setenv("NDP_SOLVER_STREAMS", streams)
+        other, wother = run()
+        assert torch.allclose(base, other, rtol=2e-5, atol=0), (tpc, rounds, streams)
+        for a, b in zip(wbase, wother):
+            assert rel(a.numpy(), b.numpy()) < REL_TOL
 
 
 def test_solver_repeatable_with_early_stop(lib):
