@@ -18,10 +18,10 @@ ROT_FORMAT = {"axis_angle": 0, "euler": 1, "quaternion": 2, "6D": 3}
 
 EXPORTS = [
     "ndp_last_error", "ndp_version", "ndp_param_count", "ndp_pack_count",
-    "ndp_saved_floats", "ndp_set_mlp_mode", "ndp_get_mlp_mode", "ndp_backward_workspace_bytes", "ndp_chamfer_workspace_bytes",
+    "ndp_saved_floats", "ndp_set_mlp_mode", "ndp_get_mlp_mode", "ndp_set_layer_tuning", "ndp_backward_workspace_bytes", "ndp_chamfer_workspace_bytes",
     "ndp_pack_params", "ndp_layer_forward", "ndp_layer_backward", "ndp_chamfer", "ndp_adam_step",
     "ndp_solver_create", "ndp_solver_destroy", "ndp_solver_params_per_pair",
-    "ndp_solver_register_host", "ndp_solver_register_device", "ndp_solver_losses",
+    "ndp_solver_register_host", "ndp_solver_register_device", "ndp_solver_last_nn", "ndp_solver_losses",
     "ndp_solver_launch_count", "ndp_solver_profile", "ndp_solver_profiled_pairs",
 ]
 
@@ -36,7 +36,8 @@ class SolverCfg(ctypes.Structure):
                 ("samples", c_int32), ("levels", c_int32), ("k0", c_int32), ("depth", c_int32),
                 ("width", c_int32), ("motion", c_int32), ("rot_format", c_int32), ("iters", c_int32),
                 ("max_break_count", c_int32), ("break_threshold_ratio", c_float), ("lr", c_double),
-                ("trunc", c_float), ("record_loss", c_int32), ("profile_every", c_int32), ("nn_mode", c_int32)]
+                ("trunc", c_float), ("record_loss", c_int32), ("profile_every", c_int32), ("nn_mode", c_int32),
+                ("mlp_mode", c_int32), ("tiles_per_bwd_cta", c_int32), ("fwd_rounds", c_int32), ("streams", c_int32)]
 
 
 def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
@@ -52,6 +53,8 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.ndp_set_mlp_mode.argtypes = [c_int32]
     lib.ndp_set_mlp_mode.restype = ctypes.c_int
     lib.ndp_get_mlp_mode.restype = c_int32
+    lib.ndp_set_layer_tuning.argtypes = [c_int32, c_int32]
+    lib.ndp_set_layer_tuning.restype = ctypes.c_int
     lib.ndp_backward_workspace_bytes.restype = c_int64
     lib.ndp_backward_workspace_bytes.argtypes = [P(LayerCfg), c_int64]
     lib.ndp_chamfer_workspace_bytes.restype = c_int64
@@ -74,9 +77,10 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.ndp_solver_launch_count.restype = c_int64
     pp = P(c_void_p)
     lib.ndp_solver_register_host.argtypes = [c_void_p, c_int32, pp, P(c_int32), pp, P(c_int32), pp, pp,
-                                             c_void_p, c_int32, pp, c_void_p, c_void_p, c_void_p]
+                                             P(c_int32), P(c_int32), c_void_p, c_int32, pp, c_void_p, c_void_p, c_void_p]
     lib.ndp_solver_register_device.argtypes = [c_void_p, c_int32, pp, P(c_int32), pp, P(c_int32), pp, pp,
-                                               pp, pp, c_void_p, c_void_p, c_void_p]
+                                               P(c_int32), P(c_int32), pp, pp, c_void_p, c_void_p, c_void_p]
+    lib.ndp_solver_last_nn.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.ndp_solver_losses.argtypes = [c_void_p, c_int32, c_void_p, c_void_p]
     lib.ndp_solver_profile.argtypes = [c_void_p, P(c_double), P(c_int64)]
     lib.ndp_solver_profile.restype = ctypes.c_int
@@ -84,7 +88,7 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.ndp_solver_profiled_pairs.restype = c_int32
     for name in ("ndp_pack_params", "ndp_layer_forward", "ndp_layer_backward", "ndp_chamfer",
                  "ndp_adam_step", "ndp_solver_create", "ndp_solver_register_host",
-                 "ndp_solver_register_device", "ndp_solver_losses"):
+                 "ndp_solver_register_device", "ndp_solver_losses", "ndp_solver_last_nn"):
         getattr(lib, name).restype = ctypes.c_int
     return lib
 

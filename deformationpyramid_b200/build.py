@@ -17,7 +17,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libndp_b200.so")
 OBJ_DIR = os.path.join(LIB_DIR, "obj")
-SOURCES = ["ndp_warp_fwd.cu", "ndp_warp_bwd.cu", "ndp_warp_fwd_tc.cu", "ndp_warp_bwd_tc.cu", "ndp_chamfer.cu", "ndp_spatial.cu", "ndp_adam.cu", "ndp_cabi.cu"]
+SOURCES = ["ndp_warp_fwd.cu", "ndp_warp_bwd.cu", "ndp_warp_fwd_tc.cu", "ndp_warp_bwd_tc.cu", "ndp_warp_bwd_rc.cu", "ndp_chamfer.cu", "ndp_spatial.cu", "ndp_adam.cu", "ndp_cabi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v"]

@@ -4,7 +4,6 @@
 #include "ndp_kernels.h"
 #include "ndp_tc.cuh"
 
-#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -30,6 +29,15 @@ extern "C" int ndp_set_mlp_mode(int32_t mode) {
     return NDP_OK;
 }
 extern "C" int32_t ndp_get_mlp_mode(void) { return g_mlp_mode; }
+// Work grouping of the standalone layer calls (ndp_layer_forward / ndp_layer_backward); solvers take theirs
+// from ndp_solver_cfg.  0 = automatic.
+static int g_layer_tpc = 0, g_layer_rounds = 0;
+extern "C" int ndp_set_layer_tuning(int32_t tiles_per_bwd_cta, int32_t fwd_rounds) {
+    if (tiles_per_bwd_cta < 0 || tiles_per_bwd_cta > 16 || fwd_rounds < 0 || fwd_rounds > 8)
+        return fail(NDP_E_INVALID, "tiles_per_bwd_cta must be in [0, 16] and fwd_rounds in [0, 8]");
+    g_layer_tpc = tiles_per_bwd_cta; g_layer_rounds = fwd_rounds;
+    return NDP_OK;
+}
 
 static int init_once() {
     static std::once_flag once;
@@ -39,6 +47,7 @@ static int init_once() {
         if (e == 0) e = ndp_bwd_init();
         if (e == 0) e = ndp_fwd_tc_init();
         if (e == 0) e = ndp_bwd_tc_init();
+        if (e == 0) e = ndp_bwd_rc_init();
         rc = e;
     });
     if (rc != 0) return fail(NDP_E_CUDA, std::string("kernel init: ") + cudaGetErrorString((cudaError_t)rc));
@@ -64,6 +73,7 @@ extern "C" int64_t ndp_param_count(const ndp_layer_cfg* c) { return check_cfg(c)
 extern "C" int64_t ndp_pack_count(const ndp_layer_cfg* c) { return check_cfg(c) ? -1 : layout_of(c).pack_count; }
 static long long act_floats(int depth, long long n, int mode) {   // saved activations of one pair
     const long long tiles = (n + NDP_TP - 1) / NDP_TP;
+    if (mode == 0 && ndp_tc_recompute(depth - 1)) return 0;    // the backward kernel rebuilds them from x
     return mode == 0 ? tiles * depth * (long long)(NDP_SET128 / 4) : (long long)depth * n * NDP_W;
 }
 extern "C" int64_t ndp_saved_floats(const ndp_layer_cfg* c, int64_t n) {
@@ -130,8 +140,10 @@ extern "C" int ndp_layer_forward(const ndp_layer_cfg* c, const float* params, co
     a.lay = layout_of(c);
     a.params = params; a.params_stride = 0; a.pack = pack; a.pack_stride = 0;
     a.x = x; a.x_stride = 0; a.y = y; a.y_stride = 0; a.nu = nu; a.nu_stride = 0;
-    a.act = saved; a.act_stride = 0; a.act_layer_stride = n * NDP_W;
-    a.zsave = saved ? saved + act_floats(c->depth, n, g_mlp_mode) : nullptr; a.z_stride = 0;
+    const long long actf = act_floats(c->depth, n, g_mlp_mode);
+    a.act = (saved && actf > 0) ? saved : nullptr; a.act_stride = 0; a.act_layer_stride = n * NDP_W;
+    a.zsave = saved ? saved + actf : nullptr; a.z_stride = 0;
+    a.rounds = g_layer_rounds;
     a.y_add = nullptr; a.y_add_stride = 0; a.y4 = nullptr; a.y4_stride = 0; a.orig = nullptr; a.orig_stride = 0;
     a.ybox = nullptr; a.box_stride = 0; a.n = (int)n; a.counts = nullptr; a.state = nullptr; a.npairs = 1;
     if (g_mlp_mode == 0) ndp_launch_fwd_tc(a, (cudaStream_t)stream); else ndp_launch_fwd(a, (cudaStream_t)stream);
@@ -158,6 +170,7 @@ extern "C" int ndp_layer_backward(const ndp_layer_cfg* c, const float* params, c
     b.partials = (float*)workspace; b.partials_stride = 0; b.partial_pitch = (int)pad4(L.param_count);
     b.gx = grad_x; b.gx_stride = 0; b.n = (int)n; b.counts = nullptr; b.state = nullptr; b.npairs = 1;
     b.hgbuf = (float*)workspace + ((n + NDP_TP - 1) / NDP_TP) * (long long)b.partial_pitch; b.hgbuf_stride = 0;
+    b.tpc = g_layer_tpc;
     if (g_mlp_mode == 0) ndp_launch_bwd_tc(b, (cudaStream_t)stream); else ndp_launch_bwd(b, (cudaStream_t)stream);
     NdpAdamArgs r;
     r.lay = L; r.params = nullptr; r.params_stride = 0; r.pack = nullptr; r.pack_stride = 0;
@@ -165,7 +178,7 @@ extern "C" int ndp_layer_backward(const ndp_layer_cfg* c, const float* params, c
     r.partials = (const float*)workspace; r.partials_stride = 0; r.partial_pitch = b.partial_pitch;
     r.n = (int)n; r.counts = nullptr; r.grads_out = grad_params; r.grads_stride = 0; r.state = nullptr;
     r.fixed_step = 0; r.lr = r.beta1 = r.beta2 = r.eps = 0.0; r.do_adam = 0; r.npairs = 1;
-    r.tiles_per_row = g_mlp_mode == 0 ? ndp_bwd_tc_tiles_per_cta(L.hidden, (int)n) : 1;
+    r.tiles_per_row = g_mlp_mode == 0 ? ndp_bwd_tc_tiles_per_cta(L.hidden, (int)n, g_layer_tpc) : 1;
     ndp_launch_adam(r, (cudaStream_t)stream);
     CK(cudaGetLastError());
     return NDP_OK;
@@ -256,6 +269,9 @@ struct ndp_solver {
     float4 *x4 = nullptr, *t4 = nullptr;
     int *orig_s = nullptr, *orig_t = nullptr, *inv_s = nullptr, *inv_t = nullptr, *prev_x = nullptr, *prev_y = nullptr;
     int npad = 0, S128 = 0, nboxes = 0, mlp_mode = 0;
+    int device = 0;                     // the CUDA device the solver's buffers, streams and events live on
+    int tpc = 0, fwd_rounds = 0;        // work grouping of the tensor-core kernels (0 = automatic)
+    int last_npairs = 0, last_cur = 0;  // the last register call: pairs, and which sample buffer holds the last warped samples
     long long act_pair = 0;
     double* blocksums = nullptr;
     int* counters = nullptr;
@@ -327,7 +343,14 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
     s->P = s->lay[0].param_count; s->Ppad = (int)pad4(s->P); s->packn = s->lay[0].pack_count;
     s->B = c->max_pairs; s->S = c->samples; s->NS = c->max_src_points; s->NT = c->max_tgt_points;
     s->tiles = (s->S + NDP_TP - 1) / NDP_TP;
-    s->mlp_mode = g_mlp_mode;
+    if (c->mlp_mode < 0 || c->mlp_mode > 2 || c->tiles_per_bwd_cta < 0 || c->tiles_per_bwd_cta > 16 || c->fwd_rounds < 0 ||
+        c->fwd_rounds > 8 || c->streams < 0 || c->streams > NDP_MAX_STREAMS) {
+        delete s;
+        return fail(NDP_E_INVALID, "mlp_mode must be 0..2, tiles_per_bwd_cta 0..16, fwd_rounds 0..8, streams 0..8");
+    }
+    s->mlp_mode = c->mlp_mode == 0 ? g_mlp_mode : c->mlp_mode - 1;
+    s->tpc = c->tiles_per_bwd_cta; s->fwd_rounds = c->fwd_rounds;
+    if (cudaGetDevice(&s->device) != cudaSuccess) { delete s; return fail(NDP_E_CUDA, "cudaGetDevice failed"); }
     s->act_pair = act_floats(c->depth, s->S, s->mlp_mode);
     s->plan = nn_plan(s->S, s->S);
     if (c->nn_mode == 0) { s->plan.chunks = 1; s->plan.chunk_targets = 1 << 30; }
@@ -356,9 +379,7 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
     if (!e && cudaMallocHost((void**)&s->h_counts, sizeof(int) * B * 4) != cudaSuccess) e = fail(NDP_E_NOMEM, "cudaMallocHost failed");
     if (!e && cudaMemset(s->counters, 0, sizeof(int) * B) != cudaSuccess) e = fail(NDP_E_CUDA, "cudaMemset failed");
     if (!e) {
-        int want = 4;
-        if (const char* env = getenv("NDP_SOLVER_STREAMS")) want = atoi(env);
-        want = want < 1 ? 1 : (want > NDP_MAX_STREAMS ? NDP_MAX_STREAMS : want);
+        const int want = c->streams > 0 ? c->streams : 4;
         s->nstreams = (int)(B < want ? B : want);
         if (s->nstreams > 1 && cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess)
             e = fail(NDP_E_CUDA, "event creation failed");
@@ -445,6 +466,8 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         f.y4 = culled ? s->x4 : nullptr; f.y4_stride = s->S128; f.orig = s->orig_s; f.orig_stride = S;
         f.ybox = culled ? s->xbox : nullptr; f.box_stride = s->nboxes;
         f.n = s->S; f.counts = s->ncount; f.state = s->state; f.npairs = npairs;
+        f.rounds = s->fwd_rounds;
+        if (s->act_pair == 0) { f.act = nullptr; f.act_stride = 0; }     // nothing is saved: the backward kernel recomputes
 
         NdpChamferArgs ch;
         ch.nn.x = s->smp[cur ^ 1]; ch.nn.x_stride = S * 3; ch.nn.n = s->S; ch.nn.ncounts = s->ncount;
@@ -474,6 +497,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         b.partials = s->partials; b.partials_stride = (long long)s->tiles * s->Ppad; b.partial_pitch = s->Ppad;
         b.gx = nullptr; b.gx_stride = 0; b.n = s->S; b.counts = s->ncount; b.state = s->state; b.npairs = npairs;
         b.hgbuf = s->hgbuf; b.hgbuf_stride = (long long)s->tiles * NDP_HGREC;
+        b.tpc = s->tpc;
 
         NdpAdamArgs ad;
         ad.lay = L; ad.params = lvl_params; ad.params_stride = pstride; ad.pack = s->pack; ad.pack_stride = s->packn;
@@ -481,7 +505,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         ad.partials = s->partials; ad.partials_stride = b.partials_stride; ad.partial_pitch = s->Ppad;
         ad.n = s->S; ad.counts = s->ncount; ad.grads_out = nullptr; ad.grads_stride = 0; ad.state = s->state;
         ad.fixed_step = 0; ad.lr = c.lr; ad.beta1 = 0.9; ad.beta2 = 0.999; ad.eps = 1e-8; ad.do_adam = 1; ad.npairs = npairs;
-        ad.tiles_per_row = s->mlp_mode == 0 ? ndp_bwd_tc_tiles_per_cta(L.hidden, s->S) : 1;
+        ad.tiles_per_row = s->mlp_mode == 0 ? ndp_bwd_tc_tiles_per_cta(L.hidden, s->S, s->tpc) : 1;
 
         // the batch is split into stream groups (contiguous pair ranges, sizes differ by at most one)
         const int ng = npairs < s->nstreams ? npairs : s->nstreams;
@@ -555,6 +579,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         }
         cur ^= 1;   // the level's output feeds the next level (registration.py:249)
     }
+    s->last_npairs = npairs; s->last_cur = cur;
 
     // final warp of the full, centred source cloud through every level (registration.py:254-259)
     const float* xin = s->src_c;
@@ -571,6 +596,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         f.y_add = last ? s->means + 3 : nullptr; f.y_add_stride = 6;
         f.y4 = nullptr; f.y4_stride = 0; f.orig = nullptr; f.orig_stride = 0; f.ybox = nullptr; f.box_stride = 0;
         f.n = s->NS; f.counts = s->nscount; f.state = nullptr; f.npairs = npairs;
+        f.rounds = s->fwd_rounds;
         if (s->mlp_mode == 0) ndp_launch_fwd_tc(f, st); else ndp_launch_fwd(f, st);
         s->launches += 2;
         xin = s->wbuf[wb];
@@ -581,12 +607,17 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
     return NDP_OK;
 }
 
-static int solver_counts(ndp_solver* s, int npairs, const int32_t* ns, const int32_t* nt, cudaStream_t st) {
+static int solver_counts(ndp_solver* s, int npairs, const int32_t* ns, const int32_t* nt, const int32_t* nss,
+                         const int32_t* nts, cudaStream_t st) {
     if (npairs < 1 || npairs > s->B) return fail(NDP_E_INVALID, "npairs exceeds max_pairs");
     for (int p = 0; p < npairs; ++p) {
         if (ns[p] < 1 || ns[p] > s->NS || nt[p] < 1 || nt[p] > s->NT) return fail(NDP_E_INVALID, "cloud size out of range");
-        s->h_counts[p] = ns[p] < s->S ? ns[p] : s->S;                     // src[: samples]
-        s->h_counts[s->B + p] = nt[p] < s->S ? nt[p] : s->S;
+        const int ds = ns[p] < s->S ? ns[p] : s->S, dt = nt[p] < s->S ? nt[p] : s->S;       // src[: samples]
+        const int cs = nss ? nss[p] : ds, ct = nts ? nts[p] : dt;
+        if (cs < 1 || cs > ds || ct < 1 || ct > dt)
+            return fail(NDP_E_INVALID, "sample counts must be in [1, min(samples, cloud size)]");
+        s->h_counts[p] = cs;
+        s->h_counts[s->B + p] = ct;
         s->h_counts[2 * s->B + p] = ns[p];
         s->h_counts[3 * s->B + p] = nt[p];
     }
@@ -597,14 +628,29 @@ static int solver_counts(ndp_solver* s, int npairs, const int32_t* ns, const int
     return NDP_OK;
 }
 
+// The solver's buffers, streams and events belong to the device that was current at creation: make it
+// current for the duration of a call (and restore the caller's), whatever the calling thread had selected.
+struct DeviceGuard {
+    int prev = -1; bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+        if (prev == dev) prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 static int solver_register(ndp_solver* s, int32_t npairs, const float* const* src, const int32_t* ns,
                            const float* const* tgt, const int32_t* nt, const int32_t* const* src_perm,
-                           const int32_t* const* tgt_perm, float* params_host, float* const* params_dev,
+                           const int32_t* const* tgt_perm, const int32_t* src_samples, const int32_t* tgt_samples,
+                           float* params_host, float* const* params_dev,
                            int params_out, float* const* warped, int32_t* iters_out, float* loss_out,
                            cudaStream_t st, cudaMemcpyKind in_kind, cudaMemcpyKind out_kind) {
     if (!s || !src || !ns || !tgt || !nt || !warped) return fail(NDP_E_INVALID, "NULL argument");
     if (!params_host && !params_dev) return fail(NDP_E_INVALID, "initial weights are required");
-    if (int e = solver_counts(s, npairs, ns, nt, st)) return e;
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(NDP_E_CUDA, "cannot select the solver's device");
+    if (int e = solver_counts(s, npairs, ns, nt, src_samples, tgt_samples, st)) return e;
     const ndp_solver_cfg& c = s->cfg;
     bool hps = src_perm != nullptr, hpt = tgt_perm != nullptr;
     for (int p = 0; p < npairs; ++p) {
@@ -640,18 +686,68 @@ static int solver_register(ndp_solver* s, int32_t npairs, const float* const* sr
 
 extern "C" int ndp_solver_register_host(ndp_solver* s, int32_t npairs, const float* const* src, const int32_t* ns,
                                         const float* const* tgt, const int32_t* nt, const int32_t* const* src_perm,
-                                        const int32_t* const* tgt_perm, float* params, int32_t params_out,
+                                        const int32_t* const* tgt_perm, const int32_t* src_samples,
+                                        const int32_t* tgt_samples, float* params, int32_t params_out,
                                         float* const* warped, int32_t* iters_out, float* loss_out, void* stream) {
-    return solver_register(s, npairs, src, ns, tgt, nt, src_perm, tgt_perm, params, nullptr, params_out, warped,
-                           iters_out, loss_out, (cudaStream_t)stream, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost);
+    return solver_register(s, npairs, src, ns, tgt, nt, src_perm, tgt_perm, src_samples, tgt_samples, params, nullptr,
+                           params_out, warped, iters_out, loss_out, (cudaStream_t)stream, cudaMemcpyHostToDevice,
+                           cudaMemcpyDeviceToHost);
 }
 
 extern "C" int ndp_solver_register_device(ndp_solver* s, int32_t npairs, const float* const* src, const int32_t* ns,
                                           const float* const* tgt, const int32_t* nt, const int32_t* const* src_perm,
-                                          const int32_t* const* tgt_perm, float* const* params, float* const* warped,
+                                          const int32_t* const* tgt_perm, const int32_t* src_samples,
+                                          const int32_t* tgt_samples, float* const* params, float* const* warped,
                                           int32_t* iters_out, float* loss_out, void* stream) {
-    return solver_register(s, npairs, src, ns, tgt, nt, src_perm, tgt_perm, nullptr, params, 1, warped, iters_out,
-                           loss_out, (cudaStream_t)stream, cudaMemcpyDeviceToDevice, cudaMemcpyDeviceToDevice);
+    return solver_register(s, npairs, src, ns, tgt, nt, src_perm, tgt_perm, src_samples, tgt_samples, nullptr, params, 1,
+                           warped, iters_out, loss_out, (cudaStream_t)stream, cudaMemcpyDeviceToDevice,
+                           cudaMemcpyDeviceToDevice);
+}
+
+// Nearest neighbours of the LAST loss evaluation of the last register call (last level), in the sample
+// index space of that call: idx_x[i] = index (into the target samples) of the nearest target sample of
+// warped source sample i, d2_x[i] its squared distance; idx_y / d2_y the converse; warped_samples = the
+// warped source samples the search ran on.  Host buffers of `samples` entries (x 3 floats for the cloud).
+extern "C" int ndp_solver_last_nn(ndp_solver* s, int32_t pair, int64_t* idx_x, float* d2_x, int64_t* idx_y, float* d2_y,
+                                  float* warped_samples, void* stream) {
+    if (!s || pair < 0 || pair >= s->last_npairs) return fail(NDP_E_INVALID, "no such pair in the last register call");
+    if ((idx_x == nullptr) != (d2_x == nullptr) || (idx_y == nullptr) != (d2_y == nullptr))
+        return fail(NDP_E_INVALID, "d2/idx outputs must be given in pairs");
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(NDP_E_CUDA, "cannot select the solver's device");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long S = s->S;
+    const int n = s->h_counts[pair], m = s->h_counts[s->B + pair];
+    const bool culled = s->cfg.nn_mode == 0;
+    NdpNnExportArgs e;
+    e.part = s->nnpart + (long long)pair * 2LL * s->plan.chunks * s->plan.qpitch;
+    e.qpitch = s->plan.qpitch; e.chunks = s->plan.chunks; e.chunk_targets = s->plan.chunk_targets;
+    e.n = n; e.m = m;
+    e.orig_s = culled ? s->orig_s + pair * S : nullptr; e.orig_t = culled ? s->orig_t + pair * S : nullptr;
+    e.warped = s->smp[s->last_cur] + pair * S * 3;
+    long long* d_idx = nullptr; float* d_d2 = nullptr; float* d_w = nullptr;
+    if (cudaMalloc((void**)&d_idx, sizeof(long long) * 2 * S) != cudaSuccess ||
+        cudaMalloc((void**)&d_d2, sizeof(float) * 2 * S) != cudaSuccess ||
+        cudaMalloc((void**)&d_w, sizeof(float) * 3 * S) != cudaSuccess) {
+        cudaFree(d_idx); cudaFree(d_d2); cudaFree(d_w);
+        return fail(NDP_E_NOMEM, "cudaMalloc failed");
+    }
+    e.idx_x = d_idx; e.idx_y = d_idx + S; e.d2_x = d_d2; e.d2_y = d_d2 + S; e.warped_out = d_w;
+    ndp_launch_nn_export(e, st);
+    if (idx_x) {
+        CK(cudaMemcpyAsync(idx_x, d_idx, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(d2_x, d_d2, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    }
+    if (idx_y) {
+        CK(cudaMemcpyAsync(idx_y, d_idx + S, sizeof(long long) * m, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(d2_y, d_d2 + S, sizeof(float) * m, cudaMemcpyDeviceToHost, st));
+    }
+    if (warped_samples) CK(cudaMemcpyAsync(warped_samples, d_w, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
+    const cudaError_t se = cudaStreamSynchronize(st);
+    cudaFree(d_idx); cudaFree(d_d2); cudaFree(d_w);
+    CK(se);
+    CK(cudaGetLastError());
+    return NDP_OK;
 }
 
 extern "C" int ndp_solver_losses(ndp_solver* s, int32_t pair, float* out, void* stream) {

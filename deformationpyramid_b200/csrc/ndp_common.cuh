@@ -83,8 +83,13 @@ static inline NdpLayout ndp_make_layout(int depth, int motion, int rot, int nonr
 // mbarrier transaction-count completion.  Sizes and addresses must be multiples of 16 bytes.
 // ------------------------------------------------------------------------------------------------
 #ifdef NDP_EMU
-struct NdpMbar { volatile long long pending; volatile unsigned phase; unsigned pad; };
-static inline void ndp_mbar_init(NdpMbar* b, int) { b->pending = 0; b->phase = 0; }
+struct NdpMbar { volatile long long pending; volatile unsigned phase; unsigned count; volatile unsigned arrived; unsigned pad; };
+static inline void ndp_mbar_init(NdpMbar* b, int count) { b->pending = 0; b->phase = 0; b->count = (unsigned)count; b->arrived = 0; }
+// plain arrival (no transaction bytes): the phase completes when `count` arrivals have been made
+static inline void ndp_mbar_arrive(NdpMbar* b) {
+    const unsigned have = __atomic_add_fetch((unsigned*)&b->arrived, 1u, __ATOMIC_SEQ_CST);
+    if (have == b->count) { __atomic_store_n((unsigned*)&b->arrived, 0u, __ATOMIC_SEQ_CST); __atomic_fetch_add((unsigned*)&b->phase, 1u, __ATOMIC_SEQ_CST); }
+}
 static inline void ndp_mbar_expect_tx(NdpMbar* b, unsigned bytes) { __atomic_fetch_add((long long*)&b->pending, (long long)bytes, __ATOMIC_SEQ_CST); }
 static inline void ndp_bulk_g2s(void* dst, const void* src, unsigned bytes, NdpMbar* b) {
     memcpy(dst, src, bytes);
@@ -111,6 +116,10 @@ __device__ __forceinline__ void ndp_mbar_init(NdpMbar* b, int count) {
 }
 __device__ __forceinline__ void ndp_mbar_expect_tx(NdpMbar* b, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ndp_smem_u32(b)), "r"(bytes) : "memory");
+}
+// plain arrival (release at CTA scope): the phase completes when the barrier's arrival count is reached
+__device__ __forceinline__ void ndp_mbar_arrive(NdpMbar* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ndp_smem_u32(b)) : "memory");
 }
 __device__ __forceinline__ void ndp_bulk_g2s(void* dst, const void* src, unsigned bytes, NdpMbar* b) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -25,7 +25,8 @@ struct NdpFwdArgs {
     const NdpPairState* state;                       // pairs with state.stopped are skipped, or null
     int npairs;
     int pair0 = 0;                                   // first pair of this launch (the driver splits a batch over stream groups)
-    int rounds = 1;                                  // tensor-core version: tile pairs per CTA (set by the launcher)
+    int rounds = 0;                                  // tensor-core version: tile pairs per CTA; 0 = default (1)
+    int tc_version = 0;                              // 0 = default (2: operand in TMEM when depth <= 3), 1 = shared-memory operand
 };
 void ndp_launch_fwd(const NdpFwdArgs& a, cudaStream_t s);      // FP32-pipe version (act: fp32 [L+1][n][128])
 // tensor-core version: act = [tile][L+1] fp16 hi/lo image sets (65536 bytes each), act_stride in floats per pair
@@ -50,9 +51,10 @@ struct NdpBwdArgs {
     const NdpPairState* state;
     int npairs;
     int pair0 = 0;
-    int tpc = 1;                                       // tensor-core version: tiles per CTA = tiles per partial row (set by the launcher)
+    int tpc = 0;                                       // tensor-core versions: tiles per CTA = tiles per partial row; 0 = by cloud size
 };
-int ndp_bwd_tc_tiles_per_cta(int hidden, int n);
+int ndp_bwd_tc_tiles_per_cta(int hidden, int n, int forced);
+bool ndp_tc_recompute(int hidden);                     // the tensor-core backward rebuilds the activations (no saved images needed)
 #define NDP_HGREC (NDP_TP * 24)    // floats per tile: hg[128][16], e[128][8] (e[0][7] = tile max |hg|)
 void ndp_launch_bwd(const NdpBwdArgs& a, cudaStream_t s);
 void ndp_launch_bwd_tc(const NdpBwdArgs& a, cudaStream_t s);   // needs `pack` (weight image sets)
@@ -153,6 +155,18 @@ struct NdpPrunedArgs {
 };
 void ndp_launch_nn_pruned(const NdpPrunedArgs& a, cudaStream_t s);
 
+// Nearest-neighbour results of one pair's last search, exported in the SAMPLE index space of the register call
+// (the culled search works on Morton-sorted clouds): ndp_solver_last_nn.
+struct NdpNnExportArgs {
+    const float2* part; int qpitch; int chunks; int chunk_targets;   // [dir][chunk][qpitch] (d2, index bits)
+    int n, m;                                                        // source / target samples
+    const int* orig_s; const int* orig_t;                            // sorted position -> sample index (null: already sample order)
+    const float* warped;                                             // [n][3] warped source samples, in search order
+    long long* idx_x; float* d2_x; long long* idx_y; float* d2_y;    // [n] / [m]
+    float* warped_out;                                               // [n][3] in sample order
+};
+void ndp_launch_nn_export(const NdpNnExportArgs& a, cudaStream_t s);
+
 // ---- small helpers of the per-pair driver -------------------------------------------------------
 struct NdpCenterArgs {                                // registration.py:150-159
     const float* src; long long src_stride; int ns; const int* nscounts;   // full clouds
@@ -180,5 +194,6 @@ int ndp_fwd_init();   // opt-in dynamic shared memory size; returns cudaError_t
 int ndp_bwd_init();
 int ndp_fwd_tc_init();
 int ndp_bwd_tc_init();
+int ndp_bwd_rc_init();
 size_t ndp_fwd_tc_smem_bytes();
 size_t ndp_bwd_tc_smem_bytes();

@@ -240,3 +240,34 @@ void ndp_launch_nn_pruned(const NdpPrunedArgs& a, cudaStream_t s) {
     dim3 grid(((nmax + 31) / 32 + NDP_PN_WARPS - 1) / NDP_PN_WARPS, 1, 2 * a.npairs);
     NDP_LAUNCH(ndp_nn_pruned_kernel, grid, dim3(NDP_PN_WARPS * 32), 0, s, a);
 }
+
+// ---- export of the last search in sample order (ndp_solver_last_nn) --------------------------------
+__global__ void __launch_bounds__(256) ndp_nn_export_kernel(NdpNnExportArgs a) {
+    const int q = blockIdx.x * 256 + threadIdx.x, dir = blockIdx.y;
+    const int nq = dir ? a.m : a.n, nt = dir ? a.n : a.m;
+    if (q >= nq) return;
+    const int chunks = (nt + a.chunk_targets - 1) / a.chunk_targets;
+    const float2* part = a.part + (long long)dir * a.chunks * a.qpitch;
+    float2 best = part[q];
+    for (int c = 1; c < chunks; ++c) {             // brute-force mode: target chunks in ascending order, strict '<'
+        const float2 p = part[(long long)c * a.qpitch + q];
+        if (p.x < best.x) best = p;
+    }
+    const int* oq = dir ? a.orig_t : a.orig_s;
+    const int* ot = dir ? a.orig_s : a.orig_t;
+    const int i = oq ? oq[q] : q;
+    const int j = __float_as_int(best.y);
+    (dir ? a.idx_y : a.idx_x)[i] = ot ? ot[j] : j;
+    (dir ? a.d2_y : a.d2_x)[i] = best.x;
+    if (dir == 0 && a.warped_out) {
+        a.warped_out[(long long)i * 3] = a.warped[(long long)q * 3];
+        a.warped_out[(long long)i * 3 + 1] = a.warped[(long long)q * 3 + 1];
+        a.warped_out[(long long)i * 3 + 2] = a.warped[(long long)q * 3 + 2];
+    }
+}
+
+void ndp_launch_nn_export(const NdpNnExportArgs& a, cudaStream_t s) {
+    const int nmax = a.n > a.m ? a.n : a.m;
+    if (nmax <= 0) return;
+    NDP_LAUNCH(ndp_nn_export_kernel, dim3((nmax + 255) / 256, 2), dim3(256), 0, s, a);
+}

@@ -1,0 +1,437 @@
+// Kernel (3a), recomputing tensor-core version (depth 3 = two hidden layers, the reference's
+// configuration): backward of kernel (1) WITHOUT saved activations.
+//
+// Replaces the autograd backward of NDPLayer.forward (model/nets.py:111-140) that the reference
+// runs in loss.backward() (model/registration.py:236).
+//
+// Why recompute: streaming the saved activations (12.6 MB per 8192-point pair and iteration, written
+// by the forward kernel and read back here) plus one 64 KB weight image set per layer and tile costs
+// 320 KB of L2 -> shared-memory traffic per 128 points -- more than the tensor pipe's time for those
+// points leaves room for -- and ties up 128 KB of shared memory per tile, so only ONE dependency chain
+// fits per SM.  Here the activations are rebuilt from x (12 bytes per point) on the tensor cores
+// (+53 % MMAs), nothing but x, z and dL/dy is read per point, and the work is laid out so that TWO
+// independent chains (64-point half tiles) share an SM: one chain's epilogue runs under the other
+// chain's MMAs.
+//
+// Everything is TRANSPOSED relative to kernel (1): TMEM lanes / image rows are FEATURES, columns are
+// POINTS.  An activation / delta image is [128 features][64 points] (fp16 hi + lo, core-matrix layout
+// of ndp_tc.cuh with row pitch NDP_RS64), which makes
+//   * the bias a per-thread scalar and the bias gradient a per-thread sum (no shuffles),
+//   * every epilogue store a 16-byte vector (8 consecutive points of one feature),
+//   * ONE image serve as the MN-major B operand of the layer products (N = points) and as the K-major
+//     A / B operand of the weight-gradient products (K = points).
+// Per half tile (chain), with X, Y the chain's two image buffers and WB the shared weight buffer:
+//   h0  -> X    CUDA cores: relu(W_in e + b_in), 6 FMAs per element (also rebuilt later, see below)
+//   F1: acc = W_0 X           -> Y = h1 = relu(acc + b_0)                 A = W_0 (K-major), B = X (MN-major)
+//   F2: acc = W_1 Y           -> X = h2 = relu(acc + b_1)
+//   B2: acc = W_h^T hg^T,  dW_h^T += X hg          -> X = delta2 = acc . relu'(h2)   (in place)
+//   B1: acc = W_1^T X,     dW_1^T += Y X^T         -> Y = delta1 = acc . relu'(h1),  X = h0 again
+//   B0: dW_0^T += X Y^T,   acc = W_0^T Y           -> X = delta0 = acc . relu'(h0)
+//   Bin: dW_in += X E
+// h0 is rebuilt because only two buffers per chain fit next to the weight buffer (2 x 2 x 32 KB + 64 KB).
+// The weight buffer holds W_0 during B0 / Bin / F1 and W_1 during F2 / B2 / B1: two TMA loads of 64 KB per
+// 128 points (the old kernel: two weight sets + three activation sets).  Gradients accumulate in TMEM
+// over all tiles of the CTA (dW_1^T, dW_0^T: 128 columns each, dW_h^T, dW_in: 16 each) and leave once.
+// A 17th warp's elected lane issues every MMA and TMA copy from a static schedule, alternating between
+// the chains; chains and issuer meet only through mbarriers (operands ready: 8 warp arrivals; MMAs
+// retired: tcgen05.commit), never through a CTA-wide barrier inside the tile loop.
+// Deltas are carried multiplied by the CTA's power-of-two scale (fp16 range), as in ndp_warp_bwd_tc.cu.
+// No atomics: one partial row per CTA, fixed summation order => bit-reproducible.
+#include "ndp_kernels.h"
+#include "ndp_tc.cuh"
+
+#ifndef NDP_EMU
+__device__ unsigned long long ndp_dbg_rc[64];
+#define NDP_TR(i) do { if ((tid & 255) == 0 && blockIdx.x == 0 && blockIdx.y == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ndp_dbg_rc[(i) + 24 * (tid >> 8)] = t_; } } while (0)
+#else
+#define NDP_TR(i) do {} while (0)
+#endif
+
+#define NDP_RC_THREADS 544                 // 2 chains x 8 warps + the issuing warp
+#define NDP_HP 64                          // points per half tile (one chain)
+#define NDP_RS64 NDP_IMG_RS(64)            // 1024: bytes between 8-feature row groups of a [128][64] image
+#define NDP_IMG64 NDP_IMG_BYTES(64)        // 16384
+#define NDP_SET64 (2 * NDP_IMG64)          // 32768: hi + lo
+#define NDP_RS16 NDP_IMG_RS(16)            // 256
+#define NDP_IMG16F NDP_IMG_BYTES(16)       // [128 features][16]: 4096
+#define NDP_IMG16H (8 * NDP_RS16)          // [64 points][16]: 2048
+
+struct BwdRcSmem {
+    unsigned char WB[NDP_SET128];          // hidden weight hi/lo images of the current step (TMA)
+    unsigned char X[2][NDP_SET64];         // per chain: h0 -> h2 -> delta2 -> h0 -> delta0
+    unsigned char Y[2][NDP_SET64];         // per chain: h1 -> delta1
+    unsigned char HG[2][2 * NDP_IMG16H];   // per chain [64 points][16]: scaled mlp_scale * dL/dz; at the very end: bias-gradient scratch
+    unsigned char E[2][2 * NDP_IMG16H];    // per chain [64 points][16]: cols 0..5 positional encoding, rest 0
+    unsigned char HWT[2 * NDP_IMG16F];     // [128 features][16 head rows]: head weights transposed, rows >= head_dim zero
+    float ef[2][NDP_HP][8];                // per chain: fp32 positional encoding (h0 on the CUDA cores)
+    NdpMbar bar_w, bar_wfree, bar_ready[2], bar_mma[2];
+    unsigned tmem_slot, pad[3];
+};
+size_t ndp_bwd_rc_smem_bytes() { return sizeof(BwdRcSmem) + 128; }
+
+// TMEM columns
+#define RC_ACC(c) (64u * (unsigned)(c))    // per chain: layer accumulator [128 features][64 points]
+#define RC_DW1 128u                        // dW_1^T [128 i][128 o]
+#define RC_DW0 256u                        // dW_0^T
+#define RC_DWH 384u                        // dW_h^T [128 i][16 head rows]
+#define RC_DWIN 400u                       // dW_in  [128 o][16] (cols 0..5)
+
+__global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpBwdArgs a) {
+    NDP_DYN_SMEM(smem_raw);
+    BwdRcSmem& S = *(BwdRcSmem*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+
+    const int tid = threadIdx.x, pair = blockIdx.y + a.pair0, tile0 = blockIdx.x * a.tpc;
+    const int n = a.counts ? a.counts[pair] : a.n;
+    if (tile0 * NDP_TP >= n) return;
+    if (a.state && a.state[pair].stopped) return;
+    const int tiles_all = (n + NDP_TP - 1) / NDP_TP;
+    const int ntl = tiles_all - tile0 < a.tpc ? tiles_all - tile0 : a.tpc;     // tiles of this CTA
+    const NdpLayout& L = a.lay;
+    const float* params = a.params + (long long)pair * a.params_stride;
+    const unsigned char* wimg = (const unsigned char*)(a.pack + (long long)pair * a.pack_stride + L.pack_img);
+    const int HD = L.head_dim;
+    float* part = a.partials + (long long)pair * a.partials_stride + (long long)blockIdx.x * a.partial_pitch;
+    const int warp = tid >> 5, lane = tid & 31;
+    const bool issw = ndp_warp_uniform(warp) == 16;
+    // chain thread: chain c, TMEM lane quarter q (hardware: warp % 4), feature f = its TMEM lane / image row,
+    // column half ch: points [32 ch, 32 ch + 32) of the chain's 64
+    const int c = (warp >> 3) & 1, q = warp & 3, ch = (warp >> 2) & 1, f = q * 32 + lane, ct = tid & 255;
+    const int RS = NDP_IMG_RS(128), CS = NDP_IMG_CS;
+    NDP_TR(0);
+
+    if (warp == 0) ndp_tmem_alloc_warp(&S.tmem_slot, 512);
+    if (issw && ndp_elect_one()) {
+        ndp_mbar_init(&S.bar_w, 1); ndp_mbar_init(&S.bar_wfree, 1);
+        ndp_mbar_init(&S.bar_ready[0], 8); ndp_mbar_init(&S.bar_ready[1], 8);
+        ndp_mbar_init(&S.bar_mma[0], 1); ndp_mbar_init(&S.bar_mma[1], 1);
+        ndp_stage_bulk(S.WB, wimg, NDP_SET128, &S.bar_w);                      // W_0 for the first F1
+    }
+    float w_in[6], b_in = 0.0f, b_0 = 0.0f, b_1 = 0.0f;
+    if (!issw) {
+        // transposed head weight image: row i = ct & 127, 8-column chunk ct >> 7 (head rows 8 chunk .. 8 chunk + 7)
+        const int i = ct & 127, c8 = ct >> 7;
+        if (c == 0) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const int r = c8 * 8 + j; v[j] = (r < HD) ? __ldg(params + L.head_w[r < NDP_MAX_HEAD ? r : 0] + i) : 0.0f; }
+            ndp_store_chunk2(S.HWT, NDP_IMG16F, ndp_img_off(i, c8 * 8, NDP_RS16), v);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) w_in[k] = __ldg(params + L.off_w_in + f * 6 + k);
+        b_in = __ldg(params + L.off_b_in + f); b_0 = __ldg(params + L.off_b[0] + f); b_1 = __ldg(params + L.off_b[1] + f);
+    }
+    // the CTA's delta scale: an exact power of two that brings the largest head gradient of its tiles
+    // into [1, 2) (fp16 operand range, see ndp_tc.cuh); undone when the gradients leave TMEM
+    const float* rec0 = a.hgbuf + (long long)pair * a.hgbuf_stride + (long long)tile0 * NDP_HGREC;
+    float dscale, dinv;
+    {
+        float mx = 0.0f;
+        for (int t = 0; t < ntl; ++t) mx = fmaxf(mx, rec0[(long long)t * NDP_HGREC + NDP_TP * 16 + 7]);
+        ndp_pow2_scale(mx, dscale, dinv);
+    }
+    ndp_tc_fence_before();
+    ndp_fence_proxy_async();
+    __syncthreads();
+    ndp_tc_fence_after();
+    const unsigned tmem = S.tmem_slot;
+    NDP_TR(1);
+
+    if (issw) {
+      if (ndp_elect_one()) {
+        // ================================================================ the issuing thread
+        unsigned rph[2] = {0u, 0u}, wph = 0u, fph = 0u;
+        const unsigned id_f = ndp_idesc_f16(128, 64, 0, 1);      // A K-major (weights), B MN-major (image, N = points)
+        const unsigned id_h = ndp_idesc_f16(128, 64, 0, 0);      // A K-major (HWT), B K-major (HG rows = points)
+        const unsigned id_b = ndp_idesc_f16(128, 64, 1, 1);      // A MN-major (weights transposed), B MN-major
+        const unsigned id_w = ndp_idesc_f16(128, 128, 0, 0);     // both K-major over the points
+        const unsigned id_s = ndp_idesc_f16(128, 16, 0, 1);      // A K-major over the points, B = [points][16] MN-major
+        const NdpUmmaDesc dW_k = ndp_umma_desc(S.WB, CS, RS), dW_mn = ndp_umma_desc(S.WB, RS, CS);
+        const NdpUmmaDesc dHWT = ndp_umma_desc(S.HWT, CS, NDP_RS16);
+#define RC_READY(cc) do { ndp_mbar_wait(&S.bar_ready[cc], rph[cc]); rph[cc] ^= 1u; ndp_tc_fence_after(); } while (0)
+#define RC_WAIT_W() do { ndp_mbar_wait(&S.bar_w, wph); wph ^= 1u; ndp_tc_fence_after(); } while (0)
+#define RC_RELOAD_W(layer) do { ndp_mbar_wait(&S.bar_wfree, fph); fph ^= 1u; \
+                                ndp_stage_bulk(S.WB, wimg + (long long)(layer) * NDP_SET128, NDP_SET128, &S.bar_w); } while (0)
+        for (int t = 0; t < ntl; ++t) {
+            // ---- F1: acc = W_0 h0
+            for (int cc = 0; cc < 2; ++cc) {
+                RC_READY(cc);
+                if (t == 0 && cc == 0) RC_WAIT_W();
+                ndp_umma_gemm3(tmem + RC_ACC(cc), dW_k, NDP_IMG128, 2 * CS, ndp_umma_desc(S.X[cc], NDP_RS64, CS), NDP_IMG64, 2 * NDP_RS64, 8, id_f, false);
+                ndp_umma_commit(&S.bar_mma[cc]);
+            }
+            ndp_umma_commit(&S.bar_wfree);
+            RC_RELOAD_W(1);
+            // ---- F2: acc = W_1 h1
+            for (int cc = 0; cc < 2; ++cc) {
+                RC_READY(cc);
+                if (cc == 0) RC_WAIT_W();
+                ndp_umma_gemm3(tmem + RC_ACC(cc), dW_k, NDP_IMG128, 2 * CS, ndp_umma_desc(S.Y[cc], NDP_RS64, CS), NDP_IMG64, 2 * NDP_RS64, 8, id_f, false);
+                ndp_umma_commit(&S.bar_mma[cc]);
+            }
+            // ---- B2: acc = W_h^T hg^T;  dW_h^T += h2 hg
+            for (int cc = 0; cc < 2; ++cc) {
+                RC_READY(cc);
+                const bool acc = !(t == 0 && cc == 0);
+                ndp_umma_gemm3(tmem + RC_ACC(cc), dHWT, NDP_IMG16F, 0, ndp_umma_desc(S.HG[cc], CS, NDP_RS16), NDP_IMG16H, 0, 1, id_h, false);
+                ndp_umma_gemm3(tmem + RC_DWH, ndp_umma_desc(S.X[cc], CS, NDP_RS64), NDP_IMG64, 2 * CS,
+                               ndp_umma_desc(S.HG[cc], NDP_RS16, CS), NDP_IMG16H, 2 * NDP_RS16, 4, id_s, acc);
+                ndp_umma_commit(&S.bar_mma[cc]);
+            }
+            // ---- B1: acc = W_1^T delta2;  dW_1^T += h1 delta2^T
+            for (int cc = 0; cc < 2; ++cc) {
+                RC_READY(cc);
+                const bool acc = !(t == 0 && cc == 0);
+                ndp_umma_gemm3(tmem + RC_ACC(cc), dW_mn, NDP_IMG128, 2 * RS, ndp_umma_desc(S.X[cc], NDP_RS64, CS), NDP_IMG64, 2 * NDP_RS64, 8, id_b, false);
+                if (cc == 1) ndp_umma_commit(&S.bar_wfree);       // W_1 is free once both chains' products have retired
+                ndp_umma_gemm3(tmem + RC_DW1, ndp_umma_desc(S.Y[cc], CS, NDP_RS64), NDP_IMG64, 2 * CS,
+                               ndp_umma_desc(S.X[cc], CS, NDP_RS64), NDP_IMG64, 2 * CS, 4, id_w, acc);
+                ndp_umma_commit(&S.bar_mma[cc]);
+            }
+            RC_RELOAD_W(0);
+            // ---- B0: dW_0^T += h0 delta1^T (needs no weights: runs while W_0 lands);  acc = W_0^T delta1
+            for (int cc = 0; cc < 2; ++cc) {
+                RC_READY(cc);
+                const bool acc = !(t == 0 && cc == 0);
+                ndp_umma_gemm3(tmem + RC_DW0, ndp_umma_desc(S.X[cc], CS, NDP_RS64), NDP_IMG64, 2 * CS,
+                               ndp_umma_desc(S.Y[cc], CS, NDP_RS64), NDP_IMG64, 2 * CS, 4, id_w, acc);
+                if (cc == 0) RC_WAIT_W();
+                ndp_umma_gemm3(tmem + RC_ACC(cc), dW_mn, NDP_IMG128, 2 * RS, ndp_umma_desc(S.Y[cc], NDP_RS64, CS), NDP_IMG64, 2 * NDP_RS64, 8, id_b, false);
+                ndp_umma_commit(&S.bar_mma[cc]);
+            }
+            // ---- Bin: dW_in += delta0 E
+            for (int cc = 0; cc < 2; ++cc) {
+                RC_READY(cc);
+                const bool acc = !(t == 0 && cc == 0);
+                ndp_umma_gemm3(tmem + RC_DWIN, ndp_umma_desc(S.X[cc], CS, NDP_RS64), NDP_IMG64, 2 * CS,
+                               ndp_umma_desc(S.E[cc], NDP_RS16, CS), NDP_IMG16H, 2 * NDP_RS16, 4, id_s, acc);
+                ndp_umma_commit(&S.bar_mma[cc]);
+            }
+        }
+#undef RC_READY
+#undef RC_WAIT_W
+#undef RC_RELOAD_W
+      }
+    } else {
+        // ================================================================ the two chains
+        unsigned mph = 0u;
+        unsigned char* const X = S.X[c];
+        unsigned char* const Y = S.Y[c];
+        const unsigned tacc = tmem + ((unsigned)(q * 32) << 16) + RC_ACC(c) + 32u * (unsigned)ch;
+        float dbs0 = 0.0f, dbs1 = 0.0f, dbs2 = 0.0f;            // sum over points of delta0 / delta1 / delta2 (this thread's feature, its column half)
+        const float (*ef)[8] = S.ef[c];
+
+        // every chain thread announces "my part of the next batch's operands is in shared memory and I have
+        // finished reading the accumulator": one arrival per warp
+        auto signal_ready = [&]() {
+            ndp_fence_proxy_async();
+            ndp_tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ndp_mbar_arrive(&S.bar_ready[c]);
+        };
+        auto wait_mma = [&]() {
+            ndp_mbar_wait(&S.bar_mma[c], mph); mph ^= 1u;
+            ndp_tc_fence_after();
+        };
+        // h0 = relu(W_in e + b_in) for this thread's feature and its 32 points -> dst image (nets.py:114, 164-177)
+        auto gen_h0 = [&](unsigned char* dst) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float u[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int p = 32 * ch + 8 * k + j;
+                    const float4 e0 = *(const float4*)&ef[p][0], e1 = *(const float4*)&ef[p][4];
+                    float v = fmaf(w_in[0], e0.x, b_in);
+                    v = fmaf(w_in[1], e0.y, v); v = fmaf(w_in[2], e0.z, v); v = fmaf(w_in[3], e0.w, v);
+                    v = fmaf(w_in[4], e1.x, v); v = fmaf(w_in[5], e1.y, v);
+                    u[j] = ndp_relu_img(v);
+                }
+                ndp_store_chunk2(dst, NDP_IMG64, ndp_img_off(f, 32 * ch + 8 * k, NDP_RS64), u);
+            }
+        };
+        // forward epilogue: dst = relu(acc + bias) re-split into the image
+        auto epi_fwd = [&](unsigned char* dst, float bias) {
+            float v[32];
+            ndp_tmem_ld32(tacc, v);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float u[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) u[j] = ndp_relu_img(v[8 * k + j] + bias);
+                ndp_store_chunk2(dst, NDP_IMG64, ndp_img_off(f, 32 * ch + 8 * k, NDP_RS64), u);
+            }
+        };
+        // backward epilogue: buf holds h (relu' = "hi > 0"); buf <- delta = acc . relu'(h); returns sum over the points
+        auto epi_bwd = [&](unsigned char* buf) -> float {
+            unsigned mask = 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                mask |= ndp_pos_mask8(*(const uint4*)(buf + ndp_img_off(f, 32 * ch + 8 * k, NDP_RS64))) << (8 * k);
+            float v[32];
+            ndp_tmem_ld32(tacc, v);
+            float s = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float u[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { u[j] = ((mask >> (8 * k + j)) & 1u) ? v[8 * k + j] : 0.0f; s += u[j]; }
+                ndp_store_chunk2(buf, NDP_IMG64, ndp_img_off(f, 32 * ch + 8 * k, NDP_RS64), u);
+            }
+            return s;
+        };
+
+        for (int t = 0; t < ntl; ++t) {
+            const int tile = tile0 + t;
+            const float* rec = rec0 + (long long)t * NDP_HGREC + (long long)c * NDP_HP * 16;          // hg rows of this half
+            const float* rece = rec0 + (long long)t * NDP_HGREC + NDP_TP * 16 + (long long)c * NDP_HP * 8;
+            if (t > 0) wait_mma();          // the previous tile's Bin products have retired: X, E are free
+            NDP_TR(2);
+            // head-gradient / encoding images of this half tile from the record of ndp_head_grad_kernel
+            if (ct < 128) {
+                const int pt = ct >> 1, c8 = ct & 1;
+                const float4 h0 = *(const float4*)(rec + pt * 16 + c8 * 8), h1 = *(const float4*)(rec + pt * 16 + c8 * 8 + 4);
+                float v[8] = {h0.x * dscale, h0.y * dscale, h0.z * dscale, h0.w * dscale, h1.x * dscale, h1.y * dscale, h1.z * dscale, h1.w * dscale};
+                ndp_store_chunk2(S.HG[c], NDP_IMG16H, ndp_img_off(pt, c8 * 8, NDP_RS16), v);
+            } else if (ct < 192) {
+                const int pt = ct - 128;
+                const float4 e0 = *(const float4*)(rece + pt * 8), e1 = *(const float4*)(rece + pt * 8 + 4);
+                float e[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, 0.0f, 0.0f};
+                ndp_store_chunk2(S.E[c], NDP_IMG16H, ndp_img_off(pt, 0, NDP_RS16), e);
+                *(float4*)&S.ef[c][pt][0] = e0;
+                *(float4*)&S.ef[c][pt][4] = make_float4(e1.x, e1.y, 0.0f, 0.0f);
+            } else {
+                const int pt = ct - 192;
+                float e[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+                ndp_store_chunk2(S.E[c], NDP_IMG16H, ndp_img_off(pt, 8, NDP_RS16), e);
+            }
+            ndp_group_sync(1 + c, 256);     // ef complete
+            gen_h0(X);
+            signal_ready();                 // -> F1
+            NDP_TR(3);
+            wait_mma(); NDP_TR(4);
+            epi_fwd(Y, b_0);
+            signal_ready();                 // -> F2
+            wait_mma(); NDP_TR(5);
+            epi_fwd(X, b_1);
+            signal_ready();                 // -> B2
+            wait_mma(); NDP_TR(6);
+            dbs2 += epi_bwd(X);
+            signal_ready();                 // -> B1
+            wait_mma(); NDP_TR(7);
+            dbs1 += epi_bwd(Y);
+            gen_h0(X);                      // delta2 is dead (B1 retired): h0 again, for dW_0 and relu'(h0)
+            signal_ready();                 // -> B0
+            wait_mma(); NDP_TR(8);
+            dbs0 += epi_bwd(X);
+            signal_ready();                 // -> Bin
+            NDP_TR(9);
+            if (a.gx) {     // optional dL/dx: + the path through the positional encoding (ndp_head_grad_kernel wrote the direct part)
+                ndp_group_sync(1 + c, 256); // delta0 complete
+                const int p = ct >> 2, oq = ct & 3;
+                float de[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+                const float* wi = params + L.off_w_in;
+                for (int o = 32 * oq; o < 32 * oq + 32; ++o) {
+                    const unsigned off = ndp_img_off(o, p, NDP_RS64);
+                    const float d = (ndp_f16_to_f32(*(const unsigned short*)(X + off)) + ndp_f16_to_f32(*(const unsigned short*)(X + NDP_IMG64 + off))) * dinv;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) de[k] = fmaf(d, __ldg(wi + o * 6 + k), de[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    de[k] += __shfl_xor_sync(0xffffffffu, de[k], 1);
+                    de[k] += __shfl_xor_sync(0xffffffffu, de[k], 2);
+                }
+                const int gp = tile * NDP_TP + c * NDP_HP + p;
+                if (oq == 0 && gp < n) {
+                    const float* xp = a.x + (long long)pair * a.x_stride + (long long)gp * 3;
+                    float* gxp = a.gx + (long long)pair * a.gx_stride + (long long)gp * 3;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        float sn, cs;
+                        sincosf(__ldg(xp + d) * L.freq, &sn, &cs);
+                        gxp[d] += L.freq * (cs * de[2 * d] - sn * de[2 * d + 1]);
+                    }
+                }
+            }
+        }
+        wait_mma();                         // the last Bin
+        NDP_TR(10);
+        // bias gradients: this thread's sums, combined below in a fixed order
+        ndp_tc_fence_before();
+        ndp_group_sync(1 + c, 256);         // everybody's last products have retired: HG is free
+        float* dbred = (float*)S.HG[0];     // [chain][column half][layer][feature] = 6 KB <= 8 KB
+        dbred[((c * 2 + ch) * 3 + 0) * NDP_W + f] = dbs0;
+        dbred[((c * 2 + ch) * 3 + 1) * NDP_W + f] = dbs1;
+        dbred[((c * 2 + ch) * 3 + 2) * NDP_W + f] = dbs2;
+    }
+    ndp_tc_fence_before();
+    __syncthreads();            // every MMA of the CTA has retired (each chain waited for its last commit), dbred complete
+    ndp_tc_fence_after();
+    NDP_TR(11);
+    if (!issw) {
+        const unsigned tlane = tmem + ((unsigned)(q * 32) << 16);
+        const int cq = warp >> 2;                               // 0..3: 32-column group of the 128-column accumulators
+        float w[32];
+        // dW_l^T leaves TMEM: lane = input feature i, column = output o, so every store instruction of a warp
+        // writes 128 contiguous bytes of the canonical [o][i] block
+        ndp_tmem_ld32(tlane + RC_DW1 + 32u * (unsigned)cq, w);
+        {
+            float* dst = part + L.off_w[1] + (32 * cq) * NDP_W + f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst[j * NDP_W] = w[j] * dinv;
+        }
+        ndp_tmem_ld32(tlane + RC_DW0 + 32u * (unsigned)cq, w);
+        {
+            float* dst = part + L.off_w[0] + (32 * cq) * NDP_W + f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst[j * NDP_W] = w[j] * dinv;
+        }
+        if (cq == 0) {          // head weight gradients dW_h^T[i][r]
+            float h[16];
+            ndp_tmem_ld16(tlane + RC_DWH, h);
+#pragma unroll
+            for (int r = 0; r < NDP_MAX_HEAD; ++r)
+                if (r < HD) part[L.head_w[r] + f] = h[r] * dinv;
+        } else if (cq == 1) {   // input layer dW_in[o][0..5]
+            float h[16];
+            ndp_tmem_ld16(tlane + RC_DWIN, h);
+            float* dst = part + L.off_w_in + f * 6;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) dst[k] = h[k] * dinv;
+        } else if (cq == 2) {   // bias gradients: column halves, then chains, in fixed order
+            const float* dbred = (const float*)S.HG[0];
+            float tot[3];
+#pragma unroll
+            for (int l = 0; l < 3; ++l)
+                tot[l] = (dbred[((0 * 2 + 0) * 3 + l) * NDP_W + f] + dbred[((0 * 2 + 1) * 3 + l) * NDP_W + f]) +
+                         (dbred[((1 * 2 + 0) * 3 + l) * NDP_W + f] + dbred[((1 * 2 + 1) * 3 + l) * NDP_W + f]);
+            part[L.off_b_in + f] = tot[0] * dinv;
+            part[L.off_b[0] + f] = tot[1] * dinv;
+            part[L.off_b[1] + f] = tot[2] * dinv;
+        }
+    }
+    if (tid < HD) {             // db_h: per-tile sums of the pre-kernel, tiles in order
+        float sv = 0.0f;
+        for (int t = 0; t < ntl; ++t) sv += rec0[(long long)t * NDP_HGREC + NDP_TP * 16 + (1 + tid) * 8 + 7];
+        part[L.head_b[tid]] = sv;
+    }
+    ndp_tc_fence_before();
+    __syncthreads();
+    NDP_TR(12);
+    if (warp == 0) ndp_tmem_dealloc(S.tmem_slot, 512);
+}
+
+void ndp_launch_bwd_rc_main(const NdpBwdArgs& b, int grid_x, cudaStream_t s) {
+    NDP_LAUNCH(ndp_warp_bwd_rc_kernel, dim3(grid_x, b.npairs), dim3(NDP_RC_THREADS), ndp_bwd_rc_smem_bytes(), s, b);
+}
+
+int ndp_bwd_rc_init() {
+    return (int)cudaFuncSetAttribute(ndp_warp_bwd_rc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)ndp_bwd_rc_smem_bytes());
+}
+
+#ifndef NDP_EMU
+int ndp_debug_copy_rc(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, ndp_dbg_rc, sizeof(unsigned long long) * 64); }
+#else
+int ndp_debug_copy_rc(unsigned long long* out) { for (int i = 0; i < 64; ++i) out[i] = 0; return 0; }
+#endif

@@ -24,7 +24,6 @@
 // No atomics: one partial row per tile.
 #include "ndp_kernels.h"
 #include "ndp_tc.cuh"
-#include <stdlib.h>
 
 // optional phase timestamps of CTA (0,0) (debug aid, read back through ndp_debug_phase_times)
 #ifndef NDP_EMU
@@ -442,27 +441,32 @@ __global__ void __launch_bounds__(NDP_BWD_TC_THREADS, 1) ndp_warp_bwd_tc_kernel(
 #undef iss
 }
 
-// Tiles whose gradients one CTA accumulates (= tiles per partial row).  The dW accumulators are per
-// layer parity, so accumulation over tiles needs at most two hidden layers.
-int ndp_bwd_tc_tiles_per_cta(int hidden, int n) {
-    int forced = 0;             // read on every call so that tests can switch it
-    if (const char* env = getenv("NDP_BWD_TPC")) { const int v = atoi(env); if (v >= 1 && v <= 16) forced = v; }
+// Tiles whose gradients one CTA accumulates (= tiles per partial row).  `forced` > 0 (ndp_solver_cfg::
+// tiles_per_bwd_cta / ndp_set_layer_tuning) wins; otherwise a function of the cloud size only -- never of
+// the batch: the summation grouping must not depend on what a pair is batched with.  The old kernel keeps
+// per-layer-parity dW accumulators, so it accumulates over tiles only for at most two hidden layers.
+int ndp_bwd_tc_tiles_per_cta(int hidden, int n, int forced) {
     if (hidden > 2) return 1;
-    if (forced > 0) return forced;
-    // A function of the cloud size only (never of the batch: the summation grouping must not depend on what
-    // a pair is batched with): at least 16 CTAs per pair, at most 8 tiles per CTA.  8192 points -> 4.
+    if (forced > 0) return forced > 16 ? 16 : forced;
+    // at least 16 CTAs per pair, at most 8 tiles per CTA.  8192 points -> 4.
     const int tiles = (n + NDP_TP - 1) / NDP_TP;
     int tpc = 1;
     while (tpc < 8 && tiles / (2 * tpc) >= 16) tpc *= 2;
     return tpc;
 }
+// hidden == 2 (depth 3, the reference's configuration): the recomputing kernel of ndp_warp_bwd_rc.cu, which
+// needs no saved activations; every other depth: the kernel above, fed by the forward kernel's saved images.
+bool ndp_tc_recompute(int hidden) { return hidden == 2; }
+void ndp_launch_bwd_rc_main(const NdpBwdArgs& b, int grid_x, cudaStream_t s);
 void ndp_launch_bwd_tc(const NdpBwdArgs& a, cudaStream_t s) {
     if (a.npairs <= 0 || a.n <= 0) return;
     const int tiles = (a.n + NDP_TP - 1) / NDP_TP;
     NDP_LAUNCH(ndp_head_grad_kernel, dim3(tiles, a.npairs), dim3(NDP_TP), 0, s, a);
     NdpBwdArgs b = a;
-    b.tpc = ndp_bwd_tc_tiles_per_cta(a.lay.hidden, a.n);
-    NDP_LAUNCH(ndp_warp_bwd_tc_kernel, dim3((tiles + b.tpc - 1) / b.tpc, a.npairs), dim3(NDP_BWD_TC_THREADS), ndp_bwd_tc_smem_bytes(), s, b);
+    b.tpc = ndp_bwd_tc_tiles_per_cta(a.lay.hidden, a.n, a.tpc);
+    const int gx = (tiles + b.tpc - 1) / b.tpc;
+    if (ndp_tc_recompute(a.lay.hidden)) { ndp_launch_bwd_rc_main(b, gx, s); return; }
+    NDP_LAUNCH(ndp_warp_bwd_tc_kernel, dim3(gx, a.npairs), dim3(NDP_BWD_TC_THREADS), ndp_bwd_tc_smem_bytes(), s, b);
 }
 
 int ndp_bwd_tc_init() {

@@ -19,7 +19,6 @@
 // (rigid_body.py) stays scalar.
 #include "ndp_kernels.h"
 #include "ndp_tc.cuh"
-#include <stdlib.h>
 
 // optional phase timestamps of CTA (0,0), group 0 (debug aid, read back through ndp_debug_phase_times)
 #ifndef NDP_EMU
@@ -460,25 +459,16 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc2_kernel
 void ndp_launch_fwd_tc(const NdpFwdArgs& a, cudaStream_t s) {
     if (a.npairs <= 0 || a.n <= 0) return;
     const int tiles = (a.n + NDP_TP - 1) / NDP_TP;
-    static int rounds = 0;
-    if (rounds == 0) {
-        rounds = 1;     // measured: more rounds only help at large batches (+1 %) and cost at small ones
-        if (const char* env = getenv("NDP_FWD_ROUNDS")) { const int v = atoi(env); if (v >= 1 && v <= NDP_FWD_MAX_ROUNDS) rounds = v; }
-    }
-    static int version = 0;
-    if (version == 0) {
-        version = 2;
-        if (const char* env = getenv("NDP_FWD_TC_VERSION")) { const int v = atoi(env); if (v == 1 || v == 2) version = v; }
-    }
-    if (version == 2 && a.lay.hidden <= 2) {      // A operand in TMEM, both hidden weight sets resident
-        int rounds2 = 1;          // read on every call so that tests / the throughput profile can switch it
-        if (const char* env = getenv("NDP_FWD_ROUNDS2")) { const int v = atoi(env); if (v >= 1 && v <= 8) rounds2 = v; }
+    int rounds = a.rounds > 0 ? a.rounds : 1;    // measured: more rounds only help at large batches and cost at small ones
+    if (a.tc_version != 1 && a.lay.hidden <= 2) {      // A operand in TMEM, both hidden weight sets resident
+        if (rounds > 8) rounds = 8;
         NdpFwdArgs b2 = a;
-        b2.rounds = rounds2;
-        NDP_LAUNCH(ndp_warp_fwd_tc2_kernel, dim3((tiles + 2 * rounds2 - 1) / (2 * rounds2), a.npairs), dim3(NDP_FWD_TC_THREADS),
+        b2.rounds = rounds;
+        NDP_LAUNCH(ndp_warp_fwd_tc2_kernel, dim3((tiles + 2 * rounds - 1) / (2 * rounds), a.npairs), dim3(NDP_FWD_TC_THREADS),
                    ndp_fwd_tc2_smem_bytes(), s, b2);
         return;
     }
+    if (rounds > NDP_FWD_MAX_ROUNDS) rounds = NDP_FWD_MAX_ROUNDS;
     NdpFwdArgs b = a;
     b.rounds = rounds;
     dim3 grid((tiles + 2 * rounds - 1) / (2 * rounds), a.npairs);

@@ -120,6 +120,12 @@ def set_mlp_mode(mode: int, lib=None) -> None:
     _lib.check(lib, lib.ndp_set_mlp_mode(int(mode)), "ndp_set_mlp_mode")
 
 
+def set_layer_tuning(tiles_per_bwd_cta: int = 0, fwd_rounds: int = 0, lib=None) -> None:
+    """Work grouping of the tensor-core kernels behind layer_forward / layer_backward (0 = automatic)."""
+    lib = _get(lib)
+    _lib.check(lib, lib.ndp_set_layer_tuning(int(tiles_per_bwd_cta), int(fwd_rounds)), "ndp_set_layer_tuning")
+
+
 def chamfer(x: torch.Tensor, y: torch.Tensor, trunc: float, grad_scale: float = 1.0,
             want_nn: bool = False, lib=None):
     """compute_truncated_chamfer_distance for one pair (model/loss.py:94-258).
@@ -170,17 +176,31 @@ class Solver:
     def __init__(self, *, max_pairs: int, max_src_points: int, max_tgt_points: int, samples: int, levels: int,
                  k0: int, depth: int, width: int, motion: str, rotation_format: str, iters: int,
                  max_break_count: int, break_threshold_ratio: float, lr: float, trunc: float = 1e9,
-                 record_loss: bool = False, profile_every: int = 0, nn_mode: int = 0, lib=None):
+                 record_loss: bool = False, profile_every: int = 0, nn_mode: int = 0, mlp_mode: Optional[str] = None,
+                 tiles_per_bwd_cta: int = 0, fwd_rounds: int = 0, streams: int = 0, device=None, lib=None):
+        """mlp_mode: None = process default, "tensor" = tcgen05 tensor cores, "fp32" = FP32 pipes.
+        tiles_per_bwd_cta / fwd_rounds / streams: execution profile (0 = library default), see
+        include/ndp_b200.h.  device: the CUDA device the solver lives on (default: torch's current device)."""
         self.lib = _get(lib)
+        if mlp_mode not in (None, "tensor", "fp32"):
+            raise ValueError("mlp_mode must be None, 'tensor' or 'fp32'")
         if motion not in MOTION:
             raise AssertionError(f"motion must be one of {list(MOTION)}")
         self.cfg = SolverCfg(int(max_pairs), int(max_src_points), int(max_tgt_points), int(samples), int(levels),
                              int(k0), int(depth), int(width), MOTION[motion],
                              ROT_FORMAT.get(rotation_format, 0), int(iters),
                              int(min(max_break_count, 2 ** 31 - 1)), float(break_threshold_ratio), float(lr),
-                             float(trunc), int(bool(record_loss)), int(profile_every), int(nn_mode))
+                             float(trunc), int(bool(record_loss)), int(profile_every), int(nn_mode),
+                             {None: 0, "tensor": 1, "fp32": 2}[mlp_mode], int(tiles_per_bwd_cta), int(fwd_rounds),
+                             int(streams))
         h = ctypes.c_void_p(0)
-        _lib.check(self.lib, self.lib.ndp_solver_create(ctypes.byref(self.cfg), ctypes.byref(h)), "ndp_solver_create")
+        cuda = getattr(self.lib, "_ndp_requires_cuda", False)
+        if cuda and device is not None:
+            with torch.cuda.device(torch.device(device) if not isinstance(device, int) else device):
+                rc = self.lib.ndp_solver_create(ctypes.byref(self.cfg), ctypes.byref(h))
+        else:
+            rc = self.lib.ndp_solver_create(ctypes.byref(self.cfg), ctypes.byref(h))
+        _lib.check(self.lib, rc, "ndp_solver_create")
         self.handle = h
         self.params_per_pair = int(self.lib.ndp_solver_params_per_pair(h))
 
@@ -210,8 +230,11 @@ class Solver:
 
     def register(self, src: Sequence[torch.Tensor], tgt: Sequence[torch.Tensor], params: Sequence[torch.Tensor],
                  src_perm: Optional[Sequence[torch.Tensor]] = None, tgt_perm: Optional[Sequence[torch.Tensor]] = None,
-                 host: bool = False):
+                 host: bool = False, src_samples: Optional[Sequence[int]] = None,
+                 tgt_samples: Optional[Sequence[int]] = None):
         """src[p] [ns,3], tgt[p] [nt,3], params[p] flat [levels*P] (updated in place), perms int32.
+        src_samples / tgt_samples: points optimised per pair (default min(samples, n)); a permutation must hold
+        exactly that many indices (its length is checked here, the C ABI receives the counts explicitly).
         host=True: all tensors are (pinned) CPU tensors and the copies run inside the call.
         Returns (warped list, iters [npairs, levels] int32, last loss [npairs, levels])."""
         lib = self.lib
@@ -229,6 +252,18 @@ class Solver:
                 raise ValueError("params[p] must hold levels * param_count floats")
         ns = (ctypes.c_int32 * npairs)(*[int(t.shape[0]) for t in src])
         nt = (ctypes.c_int32 * npairs)(*[int(t.shape[0]) for t in tgt])
+        S = int(self.cfg.samples)
+        cnt_s = [min(S, int(t.shape[0])) for t in src] if src_samples is None else [int(v) for v in src_samples]
+        cnt_t = [min(S, int(t.shape[0])) for t in tgt] if tgt_samples is None else [int(v) for v in tgt_samples]
+        for perms, cnts, nm in ((src_perm, cnt_s, "src_perm"), (tgt_perm, cnt_t, "tgt_perm")):
+            if perms is not None:
+                if len(perms) != npairs:
+                    raise ValueError(f"{nm} must hold one permutation per pair")
+                for t, k in zip(perms, cnts):
+                    if t.numel() < k:
+                        raise ValueError(f"{nm}: a permutation holds {t.numel()} indices, {k} samples are optimised")
+        a_cs, a_ct = (ctypes.c_int32 * npairs)(*cnt_s), (ctypes.c_int32 * npairs)(*cnt_t)
+        self._last_counts = (cnt_s, cnt_t)
         dev = src[0].device
         warped = [torch.empty_like(t) for t in src]
         iters = torch.zeros(npairs, self.cfg.levels, dtype=torch.int32)
@@ -240,14 +275,14 @@ class Solver:
         a_w = self._ptr_array(warped, npairs)
         if host:
             flat = torch.stack([p.reshape(-1) for p in params]).contiguous()
-            rc = lib.ndp_solver_register_host(self.handle, npairs, a_src, ns, a_tgt, nt, a_ps, a_pt, _ptr(flat), 1,
+            rc = lib.ndp_solver_register_host(self.handle, npairs, a_src, ns, a_tgt, nt, a_ps, a_pt, a_cs, a_ct, _ptr(flat), 1,
                                               a_w, _ptr(iters), _ptr(loss), stream)
             _lib.check(lib, rc, "ndp_solver_register_host")
             for p, f in zip(params, flat):
                 p.copy_(f.view_as(p))
         else:
             a_par = self._ptr_array(params, npairs)
-            rc = lib.ndp_solver_register_device(self.handle, npairs, a_src, ns, a_tgt, nt, a_ps, a_pt, a_par, a_w,
+            rc = lib.ndp_solver_register_device(self.handle, npairs, a_src, ns, a_tgt, nt, a_ps, a_pt, a_cs, a_ct, a_par, a_w,
                                                 _ptr(iters), _ptr(loss), stream)
             _lib.check(lib, rc, "ndp_solver_register_device")
         return warped, iters, loss
@@ -265,6 +300,17 @@ class Solver:
     def profiled_pairs(self) -> int:
         """Pairs per sampled launch (the driver runs two half-batches on two streams)."""
         return int(self.lib.ndp_solver_profiled_pairs(self.handle))
+
+    def last_nn(self, pair: int):
+        """The two K=1 searches of the last loss evaluation of the last register call (model/loss.py:177-181), in
+        the sample order of that call: (idx_x int64 [n], d2_x [n], idx_y int64 [m], d2_y [m], warped samples [n,3])."""
+        n, m = self._last_counts[0][pair], self._last_counts[1][pair]
+        idx_x, d2_x = torch.empty(n, dtype=torch.int64), torch.empty(n, dtype=torch.float32)
+        idx_y, d2_y = torch.empty(m, dtype=torch.int64), torch.empty(m, dtype=torch.float32)
+        w = torch.empty(n, 3, dtype=torch.float32)
+        _lib.check(self.lib, self.lib.ndp_solver_last_nn(self.handle, int(pair), _ptr(idx_x), _ptr(d2_x), _ptr(idx_y),
+                                                         _ptr(d2_y), _ptr(w), ctypes.c_void_p(0)), "ndp_solver_last_nn")
+        return idx_x, d2_x, idx_y, d2_y, w
 
     def losses(self, pair: int) -> torch.Tensor:
         out = torch.full((self.cfg.levels, self.cfg.iters), float("nan"), dtype=torch.float32)

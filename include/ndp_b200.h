@@ -47,13 +47,21 @@ int32_t ndp_version(void);
 int64_t ndp_param_count(const ndp_layer_cfg* cfg);
 /* Floats in the kernel-layout block of transposed weight copies ("pack"). */
 int64_t ndp_pack_count(const ndp_layer_cfg* cfg);
-/* Floats the forward pass saves for the backward pass of n points (activations + head vectors). */
+/* Floats the forward pass saves for the backward pass of n points: the head vectors (12 per point) and,
+ * except on the tensor-core path at depth 3 (whose backward kernel REBUILDS the activations from x), the
+ * hidden activations. */
 int64_t ndp_saved_floats(const ndp_layer_cfg* cfg, int64_t n);
 /* Where the layer's contractions run: 0 = tensor cores (tcgen05 / TMEM, every fp32 operand split into
  * an fp16 hi and an fp16 lo term, three partial products, fp32 accumulation: fp32-level accuracy) --
  * the default; 1 = FP32 pipes.  Process-wide; a solver captures the mode at creation. */
 int ndp_set_mlp_mode(int32_t mode);
 int32_t ndp_get_mlp_mode(void);
+/* Work grouping of the tensor-core kernels behind the STANDALONE layer calls below (solvers take theirs
+ * from ndp_solver_cfg): tiles (of 128 points) whose gradients one backward CTA accumulates = tiles per
+ * partial row of the reduction (0 = a function of n only: 4 at 8192 points), and tile pairs one forward
+ * CTA processes (0 = 1).  Both only regroup work; the gradient's summation order follows the first.
+ * Process-wide. */
+int ndp_set_layer_tuning(int32_t tiles_per_bwd_cta, int32_t fwd_rounds);
 /* Bytes of scratch ndp_layer_backward needs for n points. */
 int64_t ndp_backward_workspace_bytes(const ndp_layer_cfg* cfg, int64_t n);
 /* Bytes of scratch ndp_chamfer needs for clouds of n and m points. */
@@ -117,6 +125,13 @@ typedef struct ndp_solver_cfg {
                                    events on `stream` (see ndp_solver_profile); 0: off            */
     int32_t nn_mode;            /* 0: exact culled search (Morton blocks + boxes + temporal seeds),
                                    1: plain brute force; identical results                        */
+    /* ---- execution profile (0 = default everywhere).  These regroup work; none changes the arithmetic
+     * of a single product, but tiles_per_bwd_cta sets the summation grouping of the gradients, so results
+     * are bit-reproducible for a given value.                                                       */
+    int32_t mlp_mode;           /* 0: process default (ndp_set_mlp_mode), 1: tensor cores, 2: FP32 pipes */
+    int32_t tiles_per_bwd_cta;  /* 1..16 tiles of 128 samples per backward CTA; 0: by `samples` (4 at 8192) */
+    int32_t fwd_rounds;         /* 1..8 tile pairs per forward CTA; 0: 1                             */
+    int32_t streams;            /* 1..8 stream groups the batch is split into; 0: 4                  */
 } ndp_solver_cfg;
 
 typedef struct ndp_solver ndp_solver;
@@ -129,14 +144,17 @@ int64_t ndp_solver_params_per_pair(const ndp_solver* s);
 
 /* Register `npairs` pairs whose clouds and initial weights live in HOST memory (pinned for
  * asynchronous copies).  src[p] -> ns[p] x 3 floats, tgt[p] -> nt[p] x 3; src_perm[p] / tgt_perm[p]
- * hold at least min(samples, n) int32 indices (the head of torch.randperm, registration.py:156-159)
- * or NULL for the identity; params -> npairs x params_per_pair floats (updated in place with the
+ * hold src_samples[p] / tgt_samples[p] int32 indices (the head of torch.randperm, registration.py:156-159)
+ * or NULL for the identity; src_samples / tgt_samples (npairs entries each, or NULL = min(samples, n))
+ * are the numbers of points optimised per pair, 1 <= count <= min(samples, n) -- the length of the
+ * permutation arrays is explicit, never inferred; params -> npairs x params_per_pair floats (updated in place with the
  * optimised weights when params_out != 0); warped[p] receives ns[p] x 3 floats (the return value
  * of Registration.register()).  iters_out / loss_out (npairs x levels, may be NULL) receive the
  * Adam steps taken and the last loss per level.  Synchronises `stream` before returning.       */
 int ndp_solver_register_host(ndp_solver* s, int32_t npairs, const float* const* src,
                              const int32_t* ns, const float* const* tgt, const int32_t* nt,
                              const int32_t* const* src_perm, const int32_t* const* tgt_perm,
+                             const int32_t* src_samples, const int32_t* tgt_samples,
                              float* params, int32_t params_out, float* const* warped,
                              int32_t* iters_out, float* loss_out, void* stream);
 
@@ -145,8 +163,19 @@ int ndp_solver_register_host(ndp_solver* s, int32_t npairs, const float* const* 
 int ndp_solver_register_device(ndp_solver* s, int32_t npairs, const float* const* src,
                                const int32_t* ns, const float* const* tgt, const int32_t* nt,
                                const int32_t* const* src_perm, const int32_t* const* tgt_perm,
+                               const int32_t* src_samples, const int32_t* tgt_samples,
                                float* const* params, float* const* warped, int32_t* iters_out,
                                float* loss_out, void* stream);
+
+/* Nearest neighbours of the LAST loss evaluation of the last register call (last level) for pair `pair`,
+ * i.e. the two pytorch3d knn_points(K=1) results of model/loss.py:177-181 that the reference computes but
+ * does not return.  Index space = the sample order of that call (position i = src[src_perm[i]]):
+ * idx_x[i] / d2_x[i] = nearest target sample of warped source sample i and its squared distance (n_src
+ * samples), idx_y / d2_y the converse (n_tgt samples); warped_samples (n_src x 3) = the warped source samples
+ * the search ran on.  HOST buffers of `samples` entries; any pair of outputs may be NULL.  Bit-exact with
+ * the reference contract (ascending scan, strict '<', fma distance): oracle/knn_oracle.c.  Synchronises.  */
+int ndp_solver_last_nn(ndp_solver* s, int32_t pair, int64_t* idx_x, float* d2_x, int64_t* idx_y, float* d2_y,
+                       float* warped_samples, void* stream);
 
 /* Loss curve of the last register call (record_loss = 1): copies levels x iters floats of pair
  * `pair` to the host buffer `out`; entries past the evaluations done are left untouched.       */
@@ -158,8 +187,8 @@ int64_t ndp_solver_launch_count(const ndp_solver* s);
  * *samples sampled iterations (each sample is one launch of each kernel over
  * ndp_solver_profiled_pairs() pairs).                                                          */
 int ndp_solver_profile(const ndp_solver* s, double* ms, int64_t* samples);
-/* The driver splits a batch into up to four contiguous stream groups (env NDP_SOLVER_STREAMS,
- * default 4) that run on `stream` and on internal streams, so that one group's small kernels fill
+/* The driver splits a batch into contiguous stream groups (ndp_solver_cfg::streams, default 4)
+ * that run on `stream` and on internal streams, so that one group's small kernels fill
  * the SM time the other groups' tensor-core CTAs leave idle.  The sampled launches of
  * ndp_solver_profile are the FIRST group's: this many pairs each.                            */
 int32_t ndp_solver_profiled_pairs(const ndp_solver* s);

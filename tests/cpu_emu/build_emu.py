@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "deformationpyramid_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libndp_emu.so")
-SOURCES = ["ndp_warp_fwd.cu", "ndp_warp_bwd.cu", "ndp_warp_fwd_tc.cu", "ndp_warp_bwd_tc.cu", "ndp_chamfer.cu", "ndp_spatial.cu", "ndp_adam.cu", "ndp_cabi.cu"]
+SOURCES = ["ndp_warp_fwd.cu", "ndp_warp_bwd.cu", "ndp_warp_fwd_tc.cu", "ndp_warp_bwd_tc.cu", "ndp_warp_bwd_rc.cu", "ndp_chamfer.cu", "ndp_spatial.cu", "ndp_adam.cu", "ndp_cabi.cu"]
 
 
 def build(force: bool = False) -> str:

@@ -220,8 +220,7 @@ def check_culled_search_equals_brute_force(lib, device, n=700, m=650, samples=60
     rounding (2e-6), far below what a single wrong neighbour would change."""
     specs = O.make_specs(3, 128, -8, levels, "axis_angle")
     curves = []
-    ops.set_mlp_mode(1, lib=lib)
-    try:
+    if True:
         for mode in (0, 1):
             pairs, params = [], []
             for p in range(2):
@@ -233,12 +232,10 @@ def check_culled_search_equals_brute_force(lib, device, n=700, m=650, samples=60
             solver = ops.Solver(max_pairs=2, max_src_points=n, max_tgt_points=m + 40, samples=samples, levels=levels,
                                 k0=-8, depth=3, width=128, motion="SE3", rotation_format="axis_angle", iters=iters,
                                 max_break_count=10 ** 9, break_threshold_ratio=0.001, lr=0.01, record_loss=True,
-                                nn_mode=mode, lib=lib)
+                                nn_mode=mode, mlp_mode="fp32", lib=lib)
             warped, its, last = solver.register([a for a, _ in pairs], [b for _, b in pairs], params)
             curves.append((torch.stack([solver.losses(p) for p in range(2)]), [w.cpu() for w in warped]))
             solver.close()
-    finally:
-        ops.set_mlp_mode(0, lib=lib)
     (c0, w0), (c1, w1) = curves
     assert torch.allclose(c0, c1, rtol=tol, atol=0), (c0, c1)
     for a, b in zip(w0, w1):      # different summation order (sorted vs unsorted) + chaotic trajectory

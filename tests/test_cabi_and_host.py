@@ -38,7 +38,9 @@ def test_library_builds_loads_and_exports_every_symbol():
     assert lib.ndp_param_count(ctypes.byref(cfg)) == 34694
     cfg2 = _lib.LayerCfg(128, 3, 1, 1, 0, 2.0 ** -7, 0.001)
     assert lib.ndp_param_count(ctypes.byref(cfg2)) == 34823
-    assert lib.ndp_saved_floats(ctypes.byref(cfg), 256) == 2 * 3 * 16384 + 256 * 12      # tensor-core fp16 hi/lo image sets (65536 B per tile and layer)
+    assert lib.ndp_saved_floats(ctypes.byref(cfg), 256) == 256 * 12     # depth 3 on the tensor cores: head vectors only (the backward recomputes)
+    cfg5 = _lib.LayerCfg(128, 5, 0, 0, 0, 2.0 ** -7, 0.001)
+    assert lib.ndp_saved_floats(ctypes.byref(cfg5), 256) == 2 * 5 * 16384 + 256 * 12    # other depths: fp16 hi/lo image sets (65536 B per tile and layer)
     bad = _lib.LayerCfg(64, 3, 0, 0, 0, 1.0, 0.001)
     assert lib.ndp_param_count(ctypes.byref(bad)) == -1
     assert b"width" in lib.ndp_last_error()
@@ -52,6 +54,8 @@ def test_sass_shows_bulk_tma_and_fp32_pipeline():
     assert "sm_100a" in out
     assert "UBLKCP" in out          # cp.async.bulk (TMA) staging of the MLP weights
     assert "FFMA" in out
+    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTCBAR"):      # tcgen05.mma / tcgen05.ld / tcgen05.st / tcgen05.commit
+        assert mnemonic in out, mnemonic
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the GPU-less failure mode")

@@ -29,16 +29,19 @@ def test_layers_golden(lib, golden_dir):
     check_layers_against_golden(lib, golden_dir, device="cpu")
 
 
-def test_backward_accumulates_over_tiles(lib, monkeypatch):
+def test_backward_accumulates_over_tiles(lib):
     """Gradients of several tiles accumulated in TMEM by one CTA (what 8192-point clouds use) on small inputs."""
-    monkeypatch.setenv("NDP_BWD_TPC", "4")
-    check_layers_vs_oracle_depths(lib, "cpu", cases=((3, 700), (2, 257)))
-    monkeypatch.setenv("NDP_BWD_TPC", "2")
-    check_layers_vs_oracle_depths(lib, "cpu", cases=((3, 385),))
-    # the throughput profile bench.py uses: 8 tiles per backward CTA, 2 tile-pair rounds per forward CTA
-    monkeypatch.setenv("NDP_BWD_TPC", "8")
-    monkeypatch.setenv("NDP_FWD_ROUNDS2", "2")
-    check_layers_vs_oracle_depths(lib, "cpu", cases=((3, 1300),) if "cpu" != "cpu" else ((3, 700),))
+    from deformationpyramid_b200 import ops
+    try:
+        ops.set_layer_tuning(4, 0, lib=lib)
+        check_layers_vs_oracle_depths(lib, "cpu", cases=((3, 700), (2, 257)))
+        ops.set_layer_tuning(2, 0, lib=lib)
+        check_layers_vs_oracle_depths(lib, "cpu", cases=((3, 385),))
+        # the throughput profile of large batches: 8 tiles per backward CTA, 2 tile-pair rounds per forward CTA
+        ops.set_layer_tuning(8, 2, lib=lib)
+        check_layers_vs_oracle_depths(lib, "cpu", cases=((3, 700),))
+    finally:
+        ops.set_layer_tuning(0, 0, lib=lib)
 
 
 def test_layers_other_depths_vs_oracle(lib):

@@ -35,16 +35,19 @@ def test_layers_golden(lib, golden_dir):
     check_layers_against_golden(lib, golden_dir, DEV)
 
 
-def test_backward_accumulates_over_tiles(lib, monkeypatch):
+def test_backward_accumulates_over_tiles(lib):
     """Gradients of several tiles accumulated in TMEM by one CTA (what 8192-point clouds use) on small inputs."""
-    monkeypatch.setenv("NDP_BWD_TPC", "4")
-    check_layers_vs_oracle_depths(lib, DEV, cases=((3, 700), (2, 257)))
-    monkeypatch.setenv("NDP_BWD_TPC", "2")
-    check_layers_vs_oracle_depths(lib, DEV, cases=((3, 385),))
-    # the throughput profile bench.py uses: 8 tiles per backward CTA, 2 tile-pair rounds per forward CTA
-    monkeypatch.setenv("NDP_BWD_TPC", "8")
-    monkeypatch.setenv("NDP_FWD_ROUNDS2", "2")
-    check_layers_vs_oracle_depths(lib, DEV, cases=((3, 1300),) if DEV != "cpu" else ((3, 700),))
+    from deformationpyramid_b200 import ops
+    try:
+        ops.set_layer_tuning(4, 0, lib=lib)
+        check_layers_vs_oracle_depths(lib, DEV, cases=((3, 700), (2, 257)))
+        ops.set_layer_tuning(2, 0, lib=lib)
+        check_layers_vs_oracle_depths(lib, DEV, cases=((3, 385),))
+        # the throughput profile of large batches: 8 tiles per backward CTA, 2 tile-pair rounds per forward CTA
+        ops.set_layer_tuning(8, 2, lib=lib)
+        check_layers_vs_oracle_depths(lib, DEV, cases=((3, 1300),))
+    finally:
+        ops.set_layer_tuning(0, 0, lib=lib)
 
 
 def test_layers_other_depths_vs_oracle(lib):
@@ -157,7 +160,7 @@ def test_culled_search_equals_brute_force(lib):
     check_culled_search_equals_brute_force(lib, DEV, n=8300, m=8250, samples=8192, levels=1, iters=6)   # BASELINE size
 
 
-def test_full_size_regrouping_invariance(lib, monkeypatch):
+def test_full_size_regrouping_invariance(lib):
     """BASELINE.json size (8192 samples): the tensor-core path's work grouping (tiles per backward CTA,
     tile-pair rounds per forward CTA, stream groups) only regroups fp32 sums -- loss curves of a short
     run agree to rounding across groupings, and each grouping is bit-reproducible."""
@@ -170,10 +173,11 @@ def test_full_size_regrouping_invariance(lib, monkeypatch):
     torch.manual_seed(1)
     flats0 = [torch.cat([O.flatten_params(s, O.init_params(s)) for s in specs]) for _ in pairs]
 
-    def run():
+    def run(tpc=0, rounds=0, streams=0):
         solver = ops.Solver(max_pairs=3, max_src_points=S, max_tgt_points=S, samples=S, levels=levels, k0=-8, depth=3,
                             width=128, motion="SE3", rotation_format="axis_angle", iters=iters, max_break_count=10 ** 9,
-                            break_threshold_ratio=0.001, lr=0.01, record_loss=True, lib=lib)
+                            break_threshold_ratio=0.001, lr=0.01, record_loss=True, tiles_per_bwd_cta=tpc,
+                            fwd_rounds=rounds, streams=streams, lib=lib)
         warped, _, _ = solver.register([a.to(DEV) for a, _ in pairs], [b.to(DEV) for _, b in pairs],
                                        [f.clone().to(DEV) for f in flats0])
         out = torch.stack([solver.losses(p) for p in range(3)]), [w.cpu() for w in warped]
@@ -182,10 +186,8 @@ def test_full_size_regrouping_invariance(lib, monkeypatch):
     base, wbase = run()
     again, wagain = run()
     assert torch.equal(base, again) and all(torch.equal(a, b) for a, b in zip(wbase, wagain))
-    for tpc, rounds, streams in (("1", "1", "1"), ("8", "2", "3"), ("2", "4", "2")):
-        monkeypatch.setenv("NDP_BWD_TPC", tpc); monkeypatch.setenv("NDP_FWD_ROUNDS2", rounds)
-        monkeypatch.setenv("NDP_SOLVER_STREAMS", streams)
-        other, wother = run()
+    for tpc, rounds, streams in ((1, 1, 1), (8, 2, 3), (2, 4, 2)):
+        other, wother = run(tpc, rounds, streams)
         assert torch.allclose(base, other, rtol=2e-5, atol=0), (tpc, rounds, streams)
         for a, b in zip(wbase, wother):
             assert rel(a.numpy(), b.numpy()) < REL_TOL
