@@ -49,7 +49,21 @@ def parse():
     ap.add_argument("--cpu-sample-iters", type=int, default=3, help="iterations per level of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nn-mode", type=int, default=0, help="0: exact culled NN search (default), 1: brute force")
+    ap.add_argument("--mlp", default="tensor", choices=["tensor", "fp32"], help="tcgen05 tensor cores (default) or FP32 pipes")
+    ap.add_argument("--tpc", type=int, default=None, help="override: tiles per backward CTA")
+    ap.add_argument("--fwd-rounds", type=int, default=None, help="override: tile pairs per forward CTA")
+    ap.add_argument("--streams", type=int, default=None, help="override: stream groups")
     return ap.parse_args()
+
+
+def _profile(a):
+    """ndp_solver_cfg execution profile selected from the batch size (identical in both arms' config)."""
+    from deformationpyramid_b200.ops import execution_profile
+    prof = execution_profile(a.pairs)
+    for k, v in (("tiles_per_bwd_cta", a.tpc), ("fwd_rounds", a.fwd_rounds), ("streams", a.streams)):
+        if v is not None:
+            prof[k] = v
+    return prof
 
 
 def workload(a):
@@ -59,11 +73,8 @@ def workload(a):
                            else "shipped early-stop thresholds (mode B)"),
             "points": a.points, "levels": a.levels, "iters_per_level": a.iters, "mode": a.mode,
             "pairs_per_step_per_gpu": a.pairs,
-            "tuning": "NDP_BWD_TPC=%s tiles per backward CTA, NDP_FWD_ROUNDS2=%s tile-pair rounds per forward CTA "
-                      "(throughput profile 8 / 2 from 24 pairs per step, library defaults below)"
-                      % (os.environ.get("NDP_BWD_TPC", "default"), os.environ.get("NDP_FWD_ROUNDS2", "default")),
-            "streams": os.environ.get("NDP_SOLVER_STREAMS", "4") + " stream groups (contiguous pair ranges)",
-            "mlp": "tcgen05 fp16 hi/lo split, 3 partial products, fp32 accumulate (fp32-accurate)" if os.environ.get("NDP_MLP_MODE", "0") == "0" else "fp32 pipes", "nn_search": "exact culled (Morton blocks + boxes + seeds)" if a.nn_mode == 0 else "brute force", "width": 128, "depth": 3, "motion": "SE3", "rotation": "axis_angle",
+            "profile": _profile(a),
+            "mlp": "tcgen05 fp16 hi/lo split, 3 partial products, fp32 accumulate (fp32-accurate)" if a.mlp == "tensor" else "fp32 pipes", "nn_search": "exact culled (Morton blocks + boxes + seeds)" if a.nn_mode == 0 else "brute force", "width": 128, "depth": 3, "motion": "SE3", "rotation": "axis_angle",
             "l2": "flushed (256 MiB write) between timed steps; one step streams >= 100 MiB of saved activations "
                   "and gradient partials per iteration (larger than L2)"}
 
@@ -180,12 +191,6 @@ def main():
         run_reference(a, rank)
         return
 
-    # Throughput profile of the library for large batches (documented in INTEGRATION.md): 8 instead of 4 tiles
-    # per backward CTA and two tile-pair rounds per forward CTA.  Both only regroup work (fewer, longer CTAs);
-    # the latency-oriented defaults are better below ~16 pairs per step.
-    if a.pairs >= 24:
-        os.environ.setdefault("NDP_BWD_TPC", "8")
-        os.environ.setdefault("NDP_FWD_ROUNDS2", "2")
     from deformationpyramid_b200 import ops
     from deformationpyramid_b200.config import ndp_config
     from deformationpyramid_b200.model.registration import Registration, _init_flat_cpu
@@ -193,12 +198,8 @@ def main():
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    mlp_mode = int(os.environ.get("NDP_MLP_MODE", "0"))      # 0: tcgen05 tensor cores (default), 1: FP32 pipes
-    ops.set_mlp_mode(mlp_mode)
     dist = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
@@ -210,7 +211,7 @@ def main():
 
     B, N = a.pairs, a.points
     mbc = 10 ** 9 if a.mode == "fixed" else 15
-    cfg = ndp_config(samples=N, m=a.levels, iters=a.iters, max_break_count=mbc, device=local)
+    cfg = ndp_config(samples=N, m=a.levels, iters=a.iters, max_break_count=mbc, device=local, **_profile(a))
     # pairs of this rank: global pair index = rank * B + p (independent units, no data-path collective)
     gids = [rank * B + p for p in range(B)]
     pairs = [make_pair(g, N, N) for g in gids]
@@ -219,7 +220,7 @@ def main():
     solver = ops.Solver(max_pairs=B, max_src_points=N, max_tgt_points=N, samples=N, levels=a.levels, k0=cfg.k0,
                         depth=cfg.depth, width=cfg.width, motion=cfg.motion_type, rotation_format=cfg.rotation_format,
                         iters=a.iters, max_break_count=mbc, break_threshold_ratio=cfg.break_threshold_ratio, lr=cfg.lr,
-                        profile_every=16, nn_mode=a.nn_mode)
+                        profile_every=16, nn_mode=a.nn_mode, mlp_mode=a.mlp, **_profile(a))
     d_src = [s.to(dev) for s, _ in pairs]
     d_tgt = [t.to(dev) for _, t in pairs]
     flats0, sps, tps = [], [], []

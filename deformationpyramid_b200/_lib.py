@@ -80,7 +80,7 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
                                              P(c_int32), P(c_int32), c_void_p, c_int32, pp, c_void_p, c_void_p, c_void_p]
     lib.ndp_solver_register_device.argtypes = [c_void_p, c_int32, pp, P(c_int32), pp, P(c_int32), pp, pp,
                                                P(c_int32), P(c_int32), pp, pp, c_void_p, c_void_p, c_void_p]
-    lib.ndp_solver_last_nn.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.ndp_solver_last_nn.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.ndp_solver_losses.argtypes = [c_void_p, c_int32, c_void_p, c_void_p]
     lib.ndp_solver_profile.argtypes = [c_void_p, P(c_double), P(c_int64)]
     lib.ndp_solver_profile.restype = ctypes.c_int

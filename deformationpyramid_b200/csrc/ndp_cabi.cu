@@ -706,10 +706,10 @@ extern "C" int ndp_solver_register_device(ndp_solver* s, int32_t npairs, const f
 
 // Nearest neighbours of the LAST loss evaluation of the last register call (last level), in the sample
 // index space of that call: idx_x[i] = index (into the target samples) of the nearest target sample of
-// warped source sample i, d2_x[i] its squared distance; idx_y / d2_y the converse; warped_samples = the
-// warped source samples the search ran on.  Host buffers of `samples` entries (x 3 floats for the cloud).
+// warped source sample i, d2_x[i] its squared distance; idx_y / d2_y the converse; warped_samples /
+// target_samples = the two clouds the search ran on.  Host buffers of `samples` entries (x 3 floats for a cloud).
 extern "C" int ndp_solver_last_nn(ndp_solver* s, int32_t pair, int64_t* idx_x, float* d2_x, int64_t* idx_y, float* d2_y,
-                                  float* warped_samples, void* stream) {
+                                  float* warped_samples, float* target_samples, void* stream) {
     if (!s || pair < 0 || pair >= s->last_npairs) return fail(NDP_E_INVALID, "no such pair in the last register call");
     if ((idx_x == nullptr) != (d2_x == nullptr) || (idx_y == nullptr) != (d2_y == nullptr))
         return fail(NDP_E_INVALID, "d2/idx outputs must be given in pairs");
@@ -725,14 +725,15 @@ extern "C" int ndp_solver_last_nn(ndp_solver* s, int32_t pair, int64_t* idx_x, f
     e.n = n; e.m = m;
     e.orig_s = culled ? s->orig_s + pair * S : nullptr; e.orig_t = culled ? s->orig_t + pair * S : nullptr;
     e.warped = s->smp[s->last_cur] + pair * S * 3;
+    e.target = s->tsmp + pair * S * 3;
     long long* d_idx = nullptr; float* d_d2 = nullptr; float* d_w = nullptr;
     if (cudaMalloc((void**)&d_idx, sizeof(long long) * 2 * S) != cudaSuccess ||
         cudaMalloc((void**)&d_d2, sizeof(float) * 2 * S) != cudaSuccess ||
-        cudaMalloc((void**)&d_w, sizeof(float) * 3 * S) != cudaSuccess) {
+        cudaMalloc((void**)&d_w, sizeof(float) * 6 * S) != cudaSuccess) {
         cudaFree(d_idx); cudaFree(d_d2); cudaFree(d_w);
         return fail(NDP_E_NOMEM, "cudaMalloc failed");
     }
-    e.idx_x = d_idx; e.idx_y = d_idx + S; e.d2_x = d_d2; e.d2_y = d_d2 + S; e.warped_out = d_w;
+    e.idx_x = d_idx; e.idx_y = d_idx + S; e.d2_x = d_d2; e.d2_y = d_d2 + S; e.warped_out = d_w; e.target_out = d_w + 3 * S;
     ndp_launch_nn_export(e, st);
     if (idx_x) {
         CK(cudaMemcpyAsync(idx_x, d_idx, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
@@ -743,6 +744,7 @@ extern "C" int ndp_solver_last_nn(ndp_solver* s, int32_t pair, int64_t* idx_x, f
         CK(cudaMemcpyAsync(d2_y, d_d2 + S, sizeof(float) * m, cudaMemcpyDeviceToHost, st));
     }
     if (warped_samples) CK(cudaMemcpyAsync(warped_samples, d_w, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
+    if (target_samples) CK(cudaMemcpyAsync(target_samples, d_w + 3 * S, sizeof(float) * 3 * m, cudaMemcpyDeviceToHost, st));
     const cudaError_t se = cudaStreamSynchronize(st);
     cudaFree(d_idx); cudaFree(d_d2); cudaFree(d_w);
     CK(se);
@@ -761,9 +763,25 @@ extern "C" int ndp_solver_losses(ndp_solver* s, int32_t pair, float* out, void* 
 
 // Debug aid (not part of the public header): globaltimer stamps of CTA (0,0) of the last
 // tensor-core forward (which = 0) / backward (which = 1) launch; see NDP_T in the kernels.
+size_t ndp_bwd_rc_smem_bytes();
+size_t ndp_fwd_tc2_smem_bytes();
+// Debug aid (not part of the public header): dynamic shared memory of the tensor-core kernels, for the
+// "fits the 227 KB opt-in limit" check that runs without a GPU.
+extern "C" long long ndp_debug_smem_bytes(int which) {
+    switch (which) {
+        case 0: return (long long)ndp_fwd_tc_smem_bytes();
+        case 1: return (long long)ndp_fwd_tc2_smem_bytes();
+        case 2: return (long long)ndp_bwd_tc_smem_bytes();
+        case 3: return (long long)ndp_bwd_rc_smem_bytes();
+        case 4: return (long long)ndp_fwd_smem_bytes();
+        case 5: return (long long)ndp_bwd_smem_bytes();
+    }
+    return -1;
+}
 int ndp_debug_copy_fwd(unsigned long long* out);
 int ndp_debug_copy_bwd(unsigned long long* out);
+int ndp_debug_copy_rc(unsigned long long* out);
 extern "C" int ndp_debug_phase_times(int which, unsigned long long* out) {
     cudaDeviceSynchronize();
-    return which ? ndp_debug_copy_bwd(out) : ndp_debug_copy_fwd(out);
+    return which == 2 ? ndp_debug_copy_rc(out) : (which ? ndp_debug_copy_bwd(out) : ndp_debug_copy_fwd(out));
 }

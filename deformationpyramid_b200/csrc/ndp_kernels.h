@@ -161,9 +161,9 @@ struct NdpNnExportArgs {
     const float2* part; int qpitch; int chunks; int chunk_targets;   // [dir][chunk][qpitch] (d2, index bits)
     int n, m;                                                        // source / target samples
     const int* orig_s; const int* orig_t;                            // sorted position -> sample index (null: already sample order)
-    const float* warped;                                             // [n][3] warped source samples, in search order
+    const float* warped; const float* target;                        // [n][3] warped source / [m][3] target samples, in search order
     long long* idx_x; float* d2_x; long long* idx_y; float* d2_y;    // [n] / [m]
-    float* warped_out;                                               // [n][3] in sample order
+    float* warped_out; float* target_out;                            // [n][3] / [m][3] in sample order
 };
 void ndp_launch_nn_export(const NdpNnExportArgs& a, cudaStream_t s);
 

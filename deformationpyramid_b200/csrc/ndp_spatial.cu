@@ -259,10 +259,12 @@ __global__ void __launch_bounds__(256) ndp_nn_export_kernel(NdpNnExportArgs a) {
     const int j = __float_as_int(best.y);
     (dir ? a.idx_y : a.idx_x)[i] = ot ? ot[j] : j;
     (dir ? a.d2_y : a.d2_x)[i] = best.x;
-    if (dir == 0 && a.warped_out) {
-        a.warped_out[(long long)i * 3] = a.warped[(long long)q * 3];
-        a.warped_out[(long long)i * 3 + 1] = a.warped[(long long)q * 3 + 1];
-        a.warped_out[(long long)i * 3 + 2] = a.warped[(long long)q * 3 + 2];
+    const float* cin = dir ? a.target : a.warped;
+    float* cout = dir ? a.target_out : a.warped_out;
+    if (cout) {
+        cout[(long long)i * 3] = cin[(long long)q * 3];
+        cout[(long long)i * 3 + 1] = cin[(long long)q * 3 + 1];
+        cout[(long long)i * 3 + 2] = cin[(long long)q * 3 + 2];
     }
 }
 

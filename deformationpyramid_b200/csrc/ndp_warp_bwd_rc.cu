@@ -29,6 +29,9 @@
 //   B0: dW_0^T += X Y^T,   acc = W_0^T Y           -> X = delta0 = acc . relu'(h0)
 //   Bin: dW_in += X E
 // h0 is rebuilt because only two buffers per chain fit next to the weight buffer (2 x 2 x 32 KB + 64 KB).
+// relu' of every activation stays in a register of the thread that produced it (the same thread handles the
+// same (feature, points) cell in every epilogue).  X and Y swap roles from tile to tile and the encoding
+// image is double buffered, so the chain never waits for the tile's last products (Bin).
 // The weight buffer holds W_0 during B0 / Bin / F1 and W_1 during F2 / B2 / B1: two TMA loads of 64 KB per
 // 128 points (the old kernel: two weight sets + three activation sets).  Gradients accumulate in TMEM
 // over all tiles of the CTA (dW_1^T, dW_0^T: 128 columns each, dW_h^T, dW_in: 16 each) and leave once.
@@ -43,8 +46,10 @@
 #ifndef NDP_EMU
 __device__ unsigned long long ndp_dbg_rc[64];
 #define NDP_TR(i) do { if ((tid & 255) == 0 && blockIdx.x == 0 && blockIdx.y == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ndp_dbg_rc[(i) + 24 * (tid >> 8)] = t_; } } while (0)
+#define NDP_TI(i) do { if (blockIdx.x == 0 && blockIdx.y == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ndp_dbg_rc[i] = t_; } } while (0)
 #else
 #define NDP_TR(i) do {} while (0)
+#define NDP_TI(i) do {} while (0)
 #endif
 
 #define NDP_RC_THREADS 544                 // 2 chains x 8 warps + the issuing warp
@@ -64,7 +69,7 @@ struct BwdRcSmem {
     unsigned char E[2][2 * NDP_IMG16H];    // per chain [64 points][16]: cols 0..5 positional encoding, rest 0
     unsigned char HWT[2 * NDP_IMG16F];     // [128 features][16 head rows]: head weights transposed, rows >= head_dim zero
     float ef[2][NDP_HP][8];                // per chain: fp32 positional encoding (h0 on the CUDA cores)
-    NdpMbar bar_w, bar_wfree, bar_ready[2], bar_mma[2];
+    NdpMbar bar_w, bar_wfree, bar_ready[2][2], bar_mma[2], bar_fin;   // ready: [chain][signal parity]
     unsigned tmem_slot, pad[3];
 };
 size_t ndp_bwd_rc_smem_bytes() { return sizeof(BwdRcSmem) + 128; }
@@ -102,8 +107,9 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
     if (warp == 0) ndp_tmem_alloc_warp(&S.tmem_slot, 512);
     if (issw && ndp_elect_one()) {
         ndp_mbar_init(&S.bar_w, 1); ndp_mbar_init(&S.bar_wfree, 1);
-        ndp_mbar_init(&S.bar_ready[0], 8); ndp_mbar_init(&S.bar_ready[1], 8);
-        ndp_mbar_init(&S.bar_mma[0], 1); ndp_mbar_init(&S.bar_mma[1], 1);
+        ndp_mbar_init(&S.bar_ready[0][0], 8); ndp_mbar_init(&S.bar_ready[0][1], 8);
+        ndp_mbar_init(&S.bar_ready[1][0], 8); ndp_mbar_init(&S.bar_ready[1][1], 8);
+        ndp_mbar_init(&S.bar_mma[0], 1); ndp_mbar_init(&S.bar_mma[1], 1); ndp_mbar_init(&S.bar_fin, 1);
         ndp_stage_bulk(S.WB, wimg, NDP_SET128, &S.bar_w);                      // W_0 for the first F1
     }
     float w_in[6], b_in = 0.0f, b_0 = 0.0f, b_1 = 0.0f;
@@ -115,6 +121,10 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
 #pragma unroll
             for (int j = 0; j < 8; ++j) { const int r = c8 * 8 + j; v[j] = (r < HD) ? __ldg(params + L.head_w[r < NDP_MAX_HEAD ? r : 0] + i) : 0.0f; }
             ndp_store_chunk2(S.HWT, NDP_IMG16F, ndp_img_off(i, c8 * 8, NDP_RS16), v);
+        }
+        {   // columns 8..15 of the encoding images stay zero: written once
+            float z8[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+            if (ct < 64) ndp_store_chunk2(S.E[c], NDP_IMG16H, ndp_img_off(ct, 8, NDP_RS16), z8);
         }
 #pragma unroll
         for (int k = 0; k < 6; ++k) w_in[k] = __ldg(params + L.off_w_in + f * 6 + k);
@@ -139,7 +149,10 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
     if (issw) {
       if (ndp_elect_one()) {
         // ================================================================ the issuing thread
-        unsigned rph[2] = {0u, 0u}, wph = 0u, fph = 0u;
+        // The chains do not wait after their last signal of a tile (-> Bin), so a warp may make its NEXT arrival before the
+        // other warps have made this one: consecutive signals therefore alternate between two barriers per chain (a warp
+        // can run at most one signal ahead: its next wait needs the issuer to have consumed both).
+        unsigned rph[2][2] = {{0u, 0u}, {0u, 0u}}, rk[2] = {0u, 0u}, wph = 0u, fph = 0u;
         const unsigned id_f = ndp_idesc_f16(128, 64, 0, 1);      // A K-major (weights), B MN-major (image, N = points)
         const unsigned id_h = ndp_idesc_f16(128, 64, 0, 0);      // A K-major (HWT), B K-major (HG rows = points)
         const unsigned id_b = ndp_idesc_f16(128, 64, 1, 1);      // A MN-major (weights transposed), B MN-major
@@ -147,66 +160,85 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
         const unsigned id_s = ndp_idesc_f16(128, 16, 0, 1);      // A K-major over the points, B = [points][16] MN-major
         const NdpUmmaDesc dW_k = ndp_umma_desc(S.WB, CS, RS), dW_mn = ndp_umma_desc(S.WB, RS, CS);
         const NdpUmmaDesc dHWT = ndp_umma_desc(S.HWT, CS, NDP_RS16);
-#define RC_READY(cc) do { ndp_mbar_wait(&S.bar_ready[cc], rph[cc]); rph[cc] ^= 1u; ndp_tc_fence_after(); } while (0)
+#define RC_READY(cc) do { const unsigned k_ = rk[cc] & 1u; ndp_mbar_wait(&S.bar_ready[cc][k_], rph[cc][k_]); rph[cc][k_] ^= 1u; rk[cc] += 1u; \
+                          ndp_tc_fence_after(); } while (0)
 #define RC_WAIT_W() do { ndp_mbar_wait(&S.bar_w, wph); wph ^= 1u; ndp_tc_fence_after(); } while (0)
 #define RC_RELOAD_W(layer) do { ndp_mbar_wait(&S.bar_wfree, fph); fph ^= 1u; \
                                 ndp_stage_bulk(S.WB, wimg + (long long)(layer) * NDP_SET128, NDP_SET128, &S.bar_w); } while (0)
         for (int t = 0; t < ntl; ++t) {
+            // X and Y swap roles from tile to tile: A holds h0 -> h2 -> delta2 -> h0 -> delta0, B holds h1 -> delta1
+            unsigned char* const A0 = (t & 1) ? S.Y[0] : S.X[0];
+            unsigned char* const A1 = (t & 1) ? S.Y[1] : S.X[1];
+            unsigned char* const B0 = (t & 1) ? S.X[0] : S.Y[0];
+            unsigned char* const B1 = (t & 1) ? S.X[1] : S.Y[1];
+            const bool first = t == 0;
             // ---- F1: acc = W_0 h0
             for (int cc = 0; cc < 2; ++cc) {
                 RC_READY(cc);
-                if (t == 0 && cc == 0) RC_WAIT_W();
-                ndp_umma_gemm3(tmem + RC_ACC(cc), dW_k, NDP_IMG128, 2 * CS, ndp_umma_desc(S.X[cc], NDP_RS64, CS), NDP_IMG64, 2 * NDP_RS64, 8, id_f, false);
+                if (first && cc == 0) RC_WAIT_W();
+                NDP_TI(40 + cc * 2);
+                ndp_umma_gemm3(tmem + RC_ACC(cc), dW_k, NDP_IMG128, 2 * CS, ndp_umma_desc(cc ? A1 : A0, NDP_RS64, CS), NDP_IMG64, 2 * NDP_RS64, 8, id_f, false);
                 ndp_umma_commit(&S.bar_mma[cc]);
+                NDP_TI(41 + cc * 2);
             }
             ndp_umma_commit(&S.bar_wfree);
             RC_RELOAD_W(1);
+            NDP_TI(44);
             // ---- F2: acc = W_1 h1
             for (int cc = 0; cc < 2; ++cc) {
                 RC_READY(cc);
+                NDP_TI(45 + cc * 3);
                 if (cc == 0) RC_WAIT_W();
-                ndp_umma_gemm3(tmem + RC_ACC(cc), dW_k, NDP_IMG128, 2 * CS, ndp_umma_desc(S.Y[cc], NDP_RS64, CS), NDP_IMG64, 2 * NDP_RS64, 8, id_f, false);
+                NDP_TI(46 + cc * 3);
+                ndp_umma_gemm3(tmem + RC_ACC(cc), dW_k, NDP_IMG128, 2 * CS, ndp_umma_desc(cc ? B1 : B0, NDP_RS64, CS), NDP_IMG64, 2 * NDP_RS64, 8, id_f, false);
                 ndp_umma_commit(&S.bar_mma[cc]);
+                NDP_TI(47 + cc * 3);
             }
             // ---- B2: acc = W_h^T hg^T;  dW_h^T += h2 hg
             for (int cc = 0; cc < 2; ++cc) {
                 RC_READY(cc);
-                const bool acc = !(t == 0 && cc == 0);
+                const bool acc = !(first && cc == 0);
                 ndp_umma_gemm3(tmem + RC_ACC(cc), dHWT, NDP_IMG16F, 0, ndp_umma_desc(S.HG[cc], CS, NDP_RS16), NDP_IMG16H, 0, 1, id_h, false);
-                ndp_umma_gemm3(tmem + RC_DWH, ndp_umma_desc(S.X[cc], CS, NDP_RS64), NDP_IMG64, 2 * CS,
+                ndp_umma_gemm3(tmem + RC_DWH, ndp_umma_desc(cc ? A1 : A0, CS, NDP_RS64), NDP_IMG64, 2 * CS,
                                ndp_umma_desc(S.HG[cc], NDP_RS16, CS), NDP_IMG16H, 2 * NDP_RS16, 4, id_s, acc);
                 ndp_umma_commit(&S.bar_mma[cc]);
             }
             // ---- B1: acc = W_1^T delta2;  dW_1^T += h1 delta2^T
             for (int cc = 0; cc < 2; ++cc) {
                 RC_READY(cc);
-                const bool acc = !(t == 0 && cc == 0);
-                ndp_umma_gemm3(tmem + RC_ACC(cc), dW_mn, NDP_IMG128, 2 * RS, ndp_umma_desc(S.X[cc], NDP_RS64, CS), NDP_IMG64, 2 * NDP_RS64, 8, id_b, false);
+                const bool acc = !(first && cc == 0);
+                NDP_TI(51 + cc * 3);
+                ndp_umma_gemm3(tmem + RC_ACC(cc), dW_mn, NDP_IMG128, 2 * RS, ndp_umma_desc(cc ? A1 : A0, NDP_RS64, CS), NDP_IMG64, 2 * NDP_RS64, 8, id_b, false);
                 if (cc == 1) ndp_umma_commit(&S.bar_wfree);       // W_1 is free once both chains' products have retired
-                ndp_umma_gemm3(tmem + RC_DW1, ndp_umma_desc(S.Y[cc], CS, NDP_RS64), NDP_IMG64, 2 * CS,
-                               ndp_umma_desc(S.X[cc], CS, NDP_RS64), NDP_IMG64, 2 * CS, 4, id_w, acc);
+                NDP_TI(52 + cc * 3);
+                ndp_umma_gemm3(tmem + RC_DW1, ndp_umma_desc(cc ? B1 : B0, CS, NDP_RS64), NDP_IMG64, 2 * CS,
+                               ndp_umma_desc(cc ? A1 : A0, CS, NDP_RS64), NDP_IMG64, 2 * CS, 4, id_w, acc);
                 ndp_umma_commit(&S.bar_mma[cc]);
+                NDP_TI(53 + cc * 3);
             }
             RC_RELOAD_W(0);
+            NDP_TI(57);
             // ---- B0: dW_0^T += h0 delta1^T (needs no weights: runs while W_0 lands);  acc = W_0^T delta1
             for (int cc = 0; cc < 2; ++cc) {
                 RC_READY(cc);
-                const bool acc = !(t == 0 && cc == 0);
-                ndp_umma_gemm3(tmem + RC_DW0, ndp_umma_desc(S.X[cc], CS, NDP_RS64), NDP_IMG64, 2 * CS,
-                               ndp_umma_desc(S.Y[cc], CS, NDP_RS64), NDP_IMG64, 2 * CS, 4, id_w, acc);
+                const bool acc = !(first && cc == 0);
+                NDP_TI(58 + cc * 2);
+                ndp_umma_gemm3(tmem + RC_DW0, ndp_umma_desc(cc ? A1 : A0, CS, NDP_RS64), NDP_IMG64, 2 * CS,
+                               ndp_umma_desc(cc ? B1 : B0, CS, NDP_RS64), NDP_IMG64, 2 * CS, 4, id_w, acc);
                 if (cc == 0) RC_WAIT_W();
-                ndp_umma_gemm3(tmem + RC_ACC(cc), dW_mn, NDP_IMG128, 2 * RS, ndp_umma_desc(S.Y[cc], NDP_RS64, CS), NDP_IMG64, 2 * NDP_RS64, 8, id_b, false);
+                ndp_umma_gemm3(tmem + RC_ACC(cc), dW_mn, NDP_IMG128, 2 * RS, ndp_umma_desc(cc ? B1 : B0, NDP_RS64, CS), NDP_IMG64, 2 * NDP_RS64, 8, id_b, false);
                 ndp_umma_commit(&S.bar_mma[cc]);
+                NDP_TI(59 + cc * 2);
             }
-            // ---- Bin: dW_in += delta0 E
+            // ---- Bin: dW_in += delta0 E.  Nobody waits for these: the next commit (or the final one) covers them
             for (int cc = 0; cc < 2; ++cc) {
                 RC_READY(cc);
-                const bool acc = !(t == 0 && cc == 0);
-                ndp_umma_gemm3(tmem + RC_DWIN, ndp_umma_desc(S.X[cc], CS, NDP_RS64), NDP_IMG64, 2 * CS,
+                const bool acc = !(first && cc == 0);
+                ndp_umma_gemm3(tmem + RC_DWIN, ndp_umma_desc(cc ? A1 : A0, CS, NDP_RS64), NDP_IMG64, 2 * CS,
                                ndp_umma_desc(S.E[cc], NDP_RS16, CS), NDP_IMG16H, 2 * NDP_RS16, 4, id_s, acc);
-                ndp_umma_commit(&S.bar_mma[cc]);
             }
         }
+        ndp_umma_commit(&S.bar_fin);
 #undef RC_READY
 #undef RC_WAIT_W
 #undef RC_RELOAD_W
@@ -222,18 +254,22 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
 
         // every chain thread announces "my part of the next batch's operands is in shared memory and I have
         // finished reading the accumulator": one arrival per warp
+        unsigned sk = 0u;           // signals made so far: they alternate between the chain's two "ready" barriers
         auto signal_ready = [&]() {
             ndp_fence_proxy_async();
             ndp_tc_fence_before();
             __syncwarp();
-            if (lane == 0) ndp_mbar_arrive(&S.bar_ready[c]);
+            if (lane == 0) ndp_mbar_arrive(&S.bar_ready[c][sk & 1u]);
+            sk += 1u;
         };
         auto wait_mma = [&]() {
             ndp_mbar_wait(&S.bar_mma[c], mph); mph ^= 1u;
             ndp_tc_fence_after();
         };
-        // h0 = relu(W_in e + b_in) for this thread's feature and its 32 points -> dst image (nets.py:114, 164-177)
-        auto gen_h0 = [&](unsigned char* dst) {
+        // h0 = relu(W_in e + b_in) for this thread's feature and its 32 points -> dst image (nets.py:114, 164-177);
+        // returns relu' as a bit mask (bit j = point 32 ch + j)
+        auto gen_h0 = [&](unsigned char* dst) -> unsigned {
+            unsigned mask = 0u;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 float u[8];
@@ -244,29 +280,33 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
                     float v = fmaf(w_in[0], e0.x, b_in);
                     v = fmaf(w_in[1], e0.y, v); v = fmaf(w_in[2], e0.z, v); v = fmaf(w_in[3], e0.w, v);
                     v = fmaf(w_in[4], e1.x, v); v = fmaf(w_in[5], e1.y, v);
-                    u[j] = ndp_relu_img(v);
+                    mask |= (v > 0.0f ? 1u : 0u) << (8 * k + j);
+                    u[j] = fmaxf(v, 0.0f);
                 }
                 ndp_store_chunk2(dst, NDP_IMG64, ndp_img_off(f, 32 * ch + 8 * k, NDP_RS64), u);
             }
+            return mask;
         };
-        // forward epilogue: dst = relu(acc + bias) re-split into the image
-        auto epi_fwd = [&](unsigned char* dst, float bias) {
+        // forward epilogue: dst = relu(acc + bias) re-split into the image; returns relu' as a bit mask
+        auto epi_fwd = [&](unsigned char* dst, float bias) -> unsigned {
             float v[32];
             ndp_tmem_ld32(tacc, v);
+            unsigned mask = 0u;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 float u[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) u[j] = ndp_relu_img(v[8 * k + j] + bias);
+                for (int j = 0; j < 8; ++j) {
+                    const float x = v[8 * k + j] + bias;
+                    mask |= (x > 0.0f ? 1u : 0u) << (8 * k + j);
+                    u[j] = fmaxf(x, 0.0f);
+                }
                 ndp_store_chunk2(dst, NDP_IMG64, ndp_img_off(f, 32 * ch + 8 * k, NDP_RS64), u);
             }
+            return mask;
         };
-        // backward epilogue: buf holds h (relu' = "hi > 0"); buf <- delta = acc . relu'(h); returns sum over the points
-        auto epi_bwd = [&](unsigned char* buf) -> float {
-            unsigned mask = 0u;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                mask |= ndp_pos_mask8(*(const uint4*)(buf + ndp_img_off(f, 32 * ch + 8 * k, NDP_RS64))) << (8 * k);
+        // backward epilogue: buf <- delta = acc . relu'(h) (mask from the epilogue that produced h); returns the sum over the points
+        auto epi_bwd = [&](unsigned char* buf, unsigned mask) -> float {
             float v[32];
             ndp_tmem_ld32(tacc, v);
             float s = 0.0f;
@@ -279,50 +319,61 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
             }
             return s;
         };
+        // this thread's share of the record of ndp_head_grad_kernel for one half tile: ct < 128: 8 head gradients of point
+        // ct / 2; 128 <= ct < 192: the encoding of point ct - 128.  Loaded one tile ahead (global latency off the chain).
+        float4 r0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), r1 = r0;
+        auto load_rec = [&](int t) {
+            const float* rec = rec0 + (long long)t * NDP_HGREC;
+            if (ct < 128) {
+                const float* hp = rec + (long long)c * NDP_HP * 16 + (ct >> 1) * 16 + (ct & 1) * 8;
+                r0 = *(const float4*)hp; r1 = *(const float4*)(hp + 4);
+            } else if (ct < 192) {
+                const float* ep = rec + NDP_TP * 16 + (long long)c * NDP_HP * 8 + (ct - 128) * 8;
+                r0 = *(const float4*)ep; r1 = *(const float4*)(ep + 4);
+            }
+        };
+        load_rec(0);
 
         for (int t = 0; t < ntl; ++t) {
             const int tile = tile0 + t;
-            const float* rec = rec0 + (long long)t * NDP_HGREC + (long long)c * NDP_HP * 16;          // hg rows of this half
-            const float* rece = rec0 + (long long)t * NDP_HGREC + NDP_TP * 16 + (long long)c * NDP_HP * 8;
-            if (t > 0) wait_mma();          // the previous tile's Bin products have retired: X, E are free
+            unsigned char* const A = (t & 1) ? Y : X;       // h0 -> h2 -> delta2 -> h0 -> delta0
+            unsigned char* const B = (t & 1) ? X : Y;       // h1 -> delta1
             NDP_TR(2);
-            // head-gradient / encoding images of this half tile from the record of ndp_head_grad_kernel
+            // head-gradient image and fp32 encoding of this half tile (HG: its readers, B2 of the previous tile, retired
+            // long ago; A = the previous tile's delta1, dead since B0).  The encoding IMAGE is still being read by the
+            // previous tile's Bin products: it is rewritten after the wait for F1 below, whose commit covers them.
             if (ct < 128) {
-                const int pt = ct >> 1, c8 = ct & 1;
-                const float4 h0 = *(const float4*)(rec + pt * 16 + c8 * 8), h1 = *(const float4*)(rec + pt * 16 + c8 * 8 + 4);
-                float v[8] = {h0.x * dscale, h0.y * dscale, h0.z * dscale, h0.w * dscale, h1.x * dscale, h1.y * dscale, h1.z * dscale, h1.w * dscale};
-                ndp_store_chunk2(S.HG[c], NDP_IMG16H, ndp_img_off(pt, c8 * 8, NDP_RS16), v);
+                float v[8] = {r0.x * dscale, r0.y * dscale, r0.z * dscale, r0.w * dscale, r1.x * dscale, r1.y * dscale, r1.z * dscale, r1.w * dscale};
+                ndp_store_chunk2(S.HG[c], NDP_IMG16H, ndp_img_off(ct >> 1, (ct & 1) * 8, NDP_RS16), v);
             } else if (ct < 192) {
                 const int pt = ct - 128;
-                const float4 e0 = *(const float4*)(rece + pt * 8), e1 = *(const float4*)(rece + pt * 8 + 4);
-                float e[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, 0.0f, 0.0f};
-                ndp_store_chunk2(S.E[c], NDP_IMG16H, ndp_img_off(pt, 0, NDP_RS16), e);
-                *(float4*)&S.ef[c][pt][0] = e0;
-                *(float4*)&S.ef[c][pt][4] = make_float4(e1.x, e1.y, 0.0f, 0.0f);
-            } else {
-                const int pt = ct - 192;
-                float e[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-                ndp_store_chunk2(S.E[c], NDP_IMG16H, ndp_img_off(pt, 8, NDP_RS16), e);
+                *(float4*)&S.ef[c][pt][0] = r0;
+                *(float4*)&S.ef[c][pt][4] = make_float4(r1.x, r1.y, 0.0f, 0.0f);
             }
             ndp_group_sync(1 + c, 256);     // ef complete
-            gen_h0(X);
+            unsigned m0 = gen_h0(A);
             signal_ready();                 // -> F1
             NDP_TR(3);
             wait_mma(); NDP_TR(4);
-            epi_fwd(Y, b_0);
+            if (ct >= 128 && ct < 192) {
+                float e[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, 0.0f, 0.0f};
+                ndp_store_chunk2(S.E[c], NDP_IMG16H, ndp_img_off(ct - 128, 0, NDP_RS16), e);
+            }
+            if (t + 1 < ntl) load_rec(t + 1);
+            const unsigned m1 = epi_fwd(B, b_0);
             signal_ready();                 // -> F2
             wait_mma(); NDP_TR(5);
-            epi_fwd(X, b_1);
+            const unsigned m2 = epi_fwd(A, b_1);
             signal_ready();                 // -> B2
             wait_mma(); NDP_TR(6);
-            dbs2 += epi_bwd(X);
+            dbs2 += epi_bwd(A, m2);
             signal_ready();                 // -> B1
             wait_mma(); NDP_TR(7);
-            dbs1 += epi_bwd(Y);
-            gen_h0(X);                      // delta2 is dead (B1 retired): h0 again, for dW_0 and relu'(h0)
+            dbs1 += epi_bwd(B, m1);
+            m0 = gen_h0(A);                 // delta2 is dead (B1 retired): h0 again, for dW_0 and relu'(h0)
             signal_ready();                 // -> B0
             wait_mma(); NDP_TR(8);
-            dbs0 += epi_bwd(X);
+            dbs0 += epi_bwd(A, m0);
             signal_ready();                 // -> Bin
             NDP_TR(9);
             if (a.gx) {     // optional dL/dx: + the path through the positional encoding (ndp_head_grad_kernel wrote the direct part)
@@ -332,7 +383,7 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
                 const float* wi = params + L.off_w_in;
                 for (int o = 32 * oq; o < 32 * oq + 32; ++o) {
                     const unsigned off = ndp_img_off(o, p, NDP_RS64);
-                    const float d = (ndp_f16_to_f32(*(const unsigned short*)(X + off)) + ndp_f16_to_f32(*(const unsigned short*)(X + NDP_IMG64 + off))) * dinv;
+                    const float d = (ndp_f16_to_f32(*(const unsigned short*)(A + off)) + ndp_f16_to_f32(*(const unsigned short*)(A + NDP_IMG64 + off))) * dinv;
 #pragma unroll
                     for (int k = 0; k < 6; ++k) de[k] = fmaf(d, __ldg(wi + o * 6 + k), de[k]);
                 }
@@ -354,7 +405,8 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
                 }
             }
         }
-        wait_mma();                         // the last Bin
+        ndp_mbar_wait(&S.bar_fin, 0u);      // every product of the CTA has retired
+        ndp_tc_fence_after();
         NDP_TR(10);
         // bias gradients: this thread's sums, combined below in a fixed order
         ndp_tc_fence_before();

@@ -73,8 +73,15 @@ class Registration():
     # ------------------------------------------------------------------------------------------
     def _get_solver(self, npairs: int, ns: int, nt: int) -> ops.Solver:
         c = self.config
+        profile = ops.execution_profile(npairs)
+        for k in profile:                                     # explicit config keys win over the batch-size rule
+            v = _cfg_get(c, k, None)
+            if v is not None:
+                profile[k] = int(v)
+        prof_every = int(_cfg_get(c, "profile_every", 0) or 0)
         key = (c.samples, c.m, c.k0, c.depth, c.width, c.motion_type, c.rotation_format, c.iters,
-               c.max_break_count, c.break_threshold_ratio, c.lr, str(self.src_pcd.device))
+               c.max_break_count, c.break_threshold_ratio, c.lr, str(self.src_pcd.device), tuple(sorted(profile.items())),
+               prof_every)
         s = self._solver
         if (s is None or self._solver_key != key or s.cfg.max_pairs < npairs or s.cfg.max_src_points < ns
                 or s.cfg.max_tgt_points < nt):
@@ -86,7 +93,8 @@ class Registration():
                                       motion=c.motion_type, rotation_format=c.rotation_format, iters=c.iters,
                                       max_break_count=c.max_break_count,
                                       break_threshold_ratio=c.break_threshold_ratio, lr=c.lr, trunc=1e9,
-                                      nn_mode=int(_cfg_get(c, "nn_mode", 0) or 0))
+                                      nn_mode=int(_cfg_get(c, "nn_mode", 0) or 0), profile_every=prof_every,
+                                      device=self.src_pcd.device, **profile)
             self._solver_key = key
         return self._solver
 

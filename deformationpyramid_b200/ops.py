@@ -170,6 +170,17 @@ def adam_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, 
                                       _ptr(pack), _stream(lib, params)), "ndp_adam_step")
 
 
+def execution_profile(npairs: int) -> dict:
+    """The execution profile (ndp_solver_cfg::tiles_per_bwd_cta / fwd_rounds / streams) that
+    Registration.register_batch, shard.evaluate and bench.py select from the number of pairs registered
+    concurrently: the throughput profile (fewer, longer tensor-core CTAs) from 24 pairs per call, the
+    library's latency-oriented defaults below.  Only regroups work; the gradient summation grouping follows
+    tiles_per_bwd_cta, so a pair's result is bit-reproducible for a given profile."""
+    if npairs >= 24:
+        return dict(tiles_per_bwd_cta=8, fwd_rounds=2, streams=4)
+    return dict(tiles_per_bwd_cta=0, fwd_rounds=0, streams=0)
+
+
 class Solver:
     """ndp_solver: the fused per-pair driver (model/registration.py:126-262), batched over pairs."""
 
@@ -303,14 +314,16 @@ class Solver:
 
     def last_nn(self, pair: int):
         """The two K=1 searches of the last loss evaluation of the last register call (model/loss.py:177-181), in
-        the sample order of that call: (idx_x int64 [n], d2_x [n], idx_y int64 [m], d2_y [m], warped samples [n,3])."""
+        the sample order of that call: (idx_x int64 [n], d2_x [n], idx_y int64 [m], d2_y [m], warped source samples
+        [n,3], target samples [m,3]) as CPU tensors."""
         n, m = self._last_counts[0][pair], self._last_counts[1][pair]
         idx_x, d2_x = torch.empty(n, dtype=torch.int64), torch.empty(n, dtype=torch.float32)
         idx_y, d2_y = torch.empty(m, dtype=torch.int64), torch.empty(m, dtype=torch.float32)
-        w = torch.empty(n, 3, dtype=torch.float32)
+        w, tg = torch.empty(n, 3, dtype=torch.float32), torch.empty(m, 3, dtype=torch.float32)
         _lib.check(self.lib, self.lib.ndp_solver_last_nn(self.handle, int(pair), _ptr(idx_x), _ptr(d2_x), _ptr(idx_y),
-                                                         _ptr(d2_y), _ptr(w), ctypes.c_void_p(0)), "ndp_solver_last_nn")
-        return idx_x, d2_x, idx_y, d2_y, w
+                                                         _ptr(d2_y), _ptr(w), _ptr(tg), ctypes.c_void_p(0)),
+                   "ndp_solver_last_nn")
+        return idx_x, d2_x, idx_y, d2_y, w, tg
 
     def losses(self, pair: int) -> torch.Tensor:
         out = torch.full((self.cfg.levels, self.cfg.iters), float("nan"), dtype=torch.float32)

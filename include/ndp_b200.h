@@ -171,11 +171,12 @@ int ndp_solver_register_device(ndp_solver* s, int32_t npairs, const float* const
  * i.e. the two pytorch3d knn_points(K=1) results of model/loss.py:177-181 that the reference computes but
  * does not return.  Index space = the sample order of that call (position i = src[src_perm[i]]):
  * idx_x[i] / d2_x[i] = nearest target sample of warped source sample i and its squared distance (n_src
- * samples), idx_y / d2_y the converse (n_tgt samples); warped_samples (n_src x 3) = the warped source samples
- * the search ran on.  HOST buffers of `samples` entries; any pair of outputs may be NULL.  Bit-exact with
+ * samples), idx_y / d2_y the converse (n_tgt samples); warped_samples (n_src x 3) / target_samples (n_tgt x 3)
+ * = the two clouds the search ran on (centred, sub-sampled, the source warped by the level's last weights).
+ * HOST buffers of `samples` entries; any output (indices and distances in pairs) may be NULL.  Bit-exact with
  * the reference contract (ascending scan, strict '<', fma distance): oracle/knn_oracle.c.  Synchronises.  */
 int ndp_solver_last_nn(ndp_solver* s, int32_t pair, int64_t* idx_x, float* d2_x, int64_t* idx_y, float* d2_y,
-                       float* warped_samples, void* stream);
+                       float* warped_samples, float* target_samples, void* stream);
 
 /* Loss curve of the last register call (record_loss = 1): copies levels x iters floats of pair
  * `pair` to the host buffer `out`; entries past the evaluations done are left untouched.       */

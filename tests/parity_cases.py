@@ -275,3 +275,91 @@ def check_solver_repeatable(lib, device, n=260, m=240, samples=200, levels=3, it
     assert int(outs[0][1].min()) < iters, "the case must exercise early stop"
     for o in outs[1:]:
         assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2])
+
+
+def check_solver_last_nn(lib, device, n, m, samples, levels=1, iters=6, lattice=False, nn_mode=0, dup=40):
+    """Row g1: the nearest-neighbour indices / squared distances the fused solver's search produced in its last loss
+    evaluation (model/loss.py:177-181) are bit-exact with the oracle's K=1 search (ascending scan, strict '<', fma
+    distance) on the solver's own warped samples -- ALL queries, both directions, after enough iterations that the
+    temporal seeds of the culled search are live; duplicated targets and a lattice cloud force exact ties."""
+    specs = O.make_specs(3, 128, -8, levels, "axis_angle")
+    src, tgt = make_pair(31, n, m)
+    if lattice:                       # both clouds on a coarse lattice: many exactly equal distances
+        src = torch.round(src * 16.0) / 16.0
+        tgt = torch.round(tgt * 16.0) / 16.0
+    if dup:
+        tgt = torch.cat([tgt, tgt[:dup]])
+    torch.manual_seed(5)
+    flat = torch.cat([O.flatten_params(s, O.init_params(s)) for s in specs]).to(device)
+    sp = torch.randperm(src.shape[0])[:samples].to(torch.int32)
+    tp = torch.randperm(tgt.shape[0])[:samples].to(torch.int32)
+    solver = ops.Solver(max_pairs=2, max_src_points=src.shape[0], max_tgt_points=tgt.shape[0], samples=samples,
+                        levels=levels, k0=-8, depth=3, width=128, motion="SE3", rotation_format="axis_angle", iters=iters,
+                        max_break_count=10 ** 9, break_threshold_ratio=0.001, lr=0.01, nn_mode=nn_mode, lib=lib)
+    # the pair of interest rides second in a batch of two (non-zero pair offset in every buffer)
+    src2, tgt2 = make_pair(32, n - 37, m - 11)
+    solver.register([src2.to(device), src.to(device)], [tgt2.to(device), tgt.to(device)], [flat.clone(), flat.clone()],
+                    [torch.randperm(src2.shape[0])[:samples].to(torch.int32).to(device), sp.to(device)],
+                    [torch.randperm(tgt2.shape[0])[:samples].to(torch.int32).to(device), tp.to(device)])
+    idx_x, d2_x, idx_y, d2_y, warped, tsamp = solver.last_nn(1)
+    # the target samples are the centred, sub-sampled target (registration.py:151-159)
+    want_t = (tgt - tgt.mean(dim=0, keepdim=True))[tp.long()]
+    assert rel(tsamp.numpy(), want_t.numpy()) < 1e-6
+    rd, ri = O.knn1(warped, tsamp, threads=O.max_threads())
+    assert torch.equal(idx_x, ri), int((idx_x != ri).sum())
+    assert torch.equal(d2_x, rd)
+    rd, ri = O.knn1(tsamp, warped, threads=O.max_threads())
+    assert torch.equal(idx_y, ri), int((idx_y != ri).sum())
+    assert torch.equal(d2_y, rd)
+    if lattice or dup:
+        # the case really contains ties: some query has two targets at exactly the minimum distance
+        dd = torch.cdist(warped[:256].double(), tsamp.double())
+        assert int(((dd - dd.min(dim=1, keepdim=True).values).abs() < 1e-12).sum(dim=1).max()) >= 1
+    solver.close()
+
+
+def check_headline_config_vs_oracle(lib, device, npairs=32, points=8192, levels=9, iters=3, check=(0, 31)):
+    """BASELINE.json's headline configuration (8192 samples, 9-level NDP.yaml pyramid) under exactly the
+    execution profile bench.py / Registration.register_batch select for this batch size, the checked pairs
+    batched with the others: loss curves, iteration counts and the 9-level warped cloud against the oracle
+    (= model/registration.py:126-262) on identical pairs, weights and permutations."""
+    from deformationpyramid_b200.config import ndp_config
+    from deformationpyramid_b200.model.registration import _init_flat_cpu
+    cfg = ndp_config(samples=points, m=levels, iters=iters, max_break_count=10 ** 9)
+    specs = O.make_specs(cfg.depth, cfg.width, cfg.k0, levels, cfg.rotation_format)
+    prof = ops.execution_profile(npairs)
+    solver = ops.Solver(max_pairs=npairs, max_src_points=points, max_tgt_points=points, samples=points, levels=levels,
+                        k0=cfg.k0, depth=cfg.depth, width=cfg.width, motion=cfg.motion_type,
+                        rotation_format=cfg.rotation_format, iters=iters, max_break_count=10 ** 9,
+                        break_threshold_ratio=cfg.break_threshold_ratio, lr=cfg.lr, record_loss=True, lib=lib, **prof)
+    srcs, tgts, flats, sps, tps = [], [], [], [], []
+    for p in range(npairs):
+        src, tgt = make_pair(200 + p, points, points)
+        torch.manual_seed(200 + p)
+        flats.append(_init_flat_cpu(cfg))
+        sps.append(torch.randperm(points)); tps.append(torch.randperm(points))
+        srcs.append(src); tgts.append(tgt)
+    mv = lambda ts: [t.to(device).contiguous() for t in ts]
+    warped, its, last = solver.register(mv(srcs), mv(tgts), mv(flats), mv([s[:points].to(torch.int32) for s in sps]),
+                                        mv([t[:points].to(torch.int32) for t in tps]))
+    P = flats[0].numel() // levels
+    for p in check:
+        init = [O.unflatten_params(specs[l], flats[p][l * P:(l + 1) * P]) for l in range(levels)]
+        ref = O.optimize_pair(O.NDPConfig(iters=iters, samples=points, m=levels, max_break_count=10 ** 9), srcs[p], tgts[p],
+                              init=init, src_perm=sps[p], tgt_perm=tps[p], knn_threads=O.max_threads())
+        curve = solver.losses(p)
+        devs = []
+        for lv in range(levels):
+            rc = np.array(ref.loss_curve[lv], np.float64)
+            assert int(its[p, lv]) == ref.iters_per_level[lv] == iters
+            mine = curve[lv].numpy()[:len(rc)].astype(np.float64)
+            devs.append(float(np.max(np.abs(mine - rc) / rc)))
+        print(f"headline pair {p}: max relative loss deviation per level " + " ".join(f"{d:.1e}" for d in devs)
+              + f"; warped rel {rel(warped[p].cpu().numpy(), ref.warped.numpy()):.1e}")
+        # Free-running trajectories are chaotic (SURVEY.md section 7, hard part 3: a 1-ulp perturbation of the
+        # reference against itself moves the loss by 1e-5 .. 9e-4 within 100-200 iterations): 2e-4 over the first
+        # ~10 iterations (levels 0-2 here), the reference's own perturbation spread (2e-3) for the later levels.
+        for lv, d in enumerate(devs):
+            assert d < (2e-4 if lv < 3 else 2e-3), (p, lv, devs)
+        assert rel(warped[p].cpu().numpy(), ref.warped.numpy()) < 2e-3, (p, devs)
+    solver.close()

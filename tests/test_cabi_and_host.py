@@ -46,6 +46,16 @@ def test_library_builds_loads_and_exports_every_symbol():
     assert b"width" in lib.ndp_last_error()
 
 
+def test_dynamic_shared_memory_fits_the_opt_in_limit():
+    """Every MLP kernel's dynamic shared memory fits sm_100's 227 KB per-block opt-in limit (cudaFuncSetAttribute fails
+    with 'invalid argument' otherwise -- only visible on a GPU)."""
+    lib = ctypes.CDLL(ndp_build.build())
+    lib.ndp_debug_smem_bytes.restype = ctypes.c_longlong
+    for which in range(6):
+        n = lib.ndp_debug_smem_bytes(which)
+        assert 0 < n <= 232448, (which, n)
+
+
 def test_sass_shows_bulk_tma_and_fp32_pipeline():
     """The built cubin carries the Blackwell bulk-copy (UBLKCP) path and was built for sm_100a."""
     import subprocess

@@ -84,6 +84,13 @@ def test_culled_search_equals_brute_force(lib):
     check_culled_search_equals_brute_force(lib, "cpu", n=330, m=300, samples=280, levels=2, iters=3)
 
 
+def test_solver_nn_indices_bit_exact(lib):
+    from parity_cases import check_solver_last_nn
+    check_solver_last_nn(lib, "cpu", n=300, m=280, samples=256, levels=1, iters=3, dup=20)
+    check_solver_last_nn(lib, "cpu", n=200, m=210, samples=192, levels=1, iters=2, lattice=True, dup=0)
+    check_solver_last_nn(lib, "cpu", n=150, m=140, samples=128, levels=1, iters=2, nn_mode=1, dup=10)
+
+
 def test_solver_repeatable_with_early_stop(lib):
     check_solver_repeatable(lib, "cpu", levels=2, iters=6)      # the GPU suite runs the full-size variant
 

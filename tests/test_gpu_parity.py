@@ -193,6 +193,21 @@ def test_full_size_regrouping_invariance(lib):
             assert rel(a.numpy(), b.numpy()) < REL_TOL
 
 
+def test_solver_nn_indices_bit_exact_full_size(lib):
+    """Row g1 at BASELINE.json's size: all 2 x 8192 indices and squared distances of the CULLED search the solver runs,
+    temporal seeds live (6 iterations), duplicated targets; then a lattice cloud (exact ties everywhere)."""
+    from parity_cases import check_solver_last_nn
+    check_solver_last_nn(lib, DEV, n=8300, m=8250, samples=8192, levels=2, iters=6)
+    check_solver_last_nn(lib, DEV, n=8200, m=8200, samples=8192, levels=1, iters=5, lattice=True, dup=0)
+    check_solver_last_nn(lib, DEV, n=700, m=650, samples=600, levels=1, iters=3, nn_mode=1)     # brute-force mode, ragged
+
+
+def test_headline_config_vs_oracle(lib):
+    """32 pairs x 8192 samples x 9 levels under the bench profile: pairs 0 and 31 (first / last stream group) vs the oracle."""
+    from parity_cases import check_headline_config_vs_oracle
+    check_headline_config_vs_oracle(lib, DEV)
+
+
 def test_solver_repeatable_with_early_stop(lib):
     check_solver_repeatable(lib, DEV)
 
