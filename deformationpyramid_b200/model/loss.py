@@ -85,7 +85,7 @@ def compute_truncated_chamfer_distance(
         raise NotImplementedError("batch weights are not used on the NDP path")
     if batch_reduction != "mean" or point_reduction != "mean":
         raise NotImplementedError("only the reference's 'mean'/'mean' reductions are implemented")
-    if not x.is_cuda:
+    if not x.is_cuda and ops.requires_cuda():
         raise RuntimeError("compute_truncated_chamfer_distance runs on CUDA only (no CPU fallback)")
     if x.dtype != torch.float32 or y.dtype != torch.float32:
         raise ValueError("float32 point clouds expected")

@@ -141,7 +141,7 @@ class NDPLayer(nn.Module):
 
     def forward(self, x):
         params = tuple(self.parameters())
-        if not params[0].is_cuda:
+        if not params[0].is_cuda and ops.requires_cuda():
             raise RuntimeError("NDPLayer runs on CUDA only (sm_100a kernels, no CPU fallback); "
                                "move the layer and its input to a CUDA device")
         if x.ndim != 2 or x.shape[-1] != 3:

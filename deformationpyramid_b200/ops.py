@@ -19,6 +19,12 @@ def _get(lib):
     return lib if lib is not None else _lib.load()
 
 
+def requires_cuda() -> bool:
+    """True for the product library (always: there is no CPU fallback).  Only the test suite's CPU-emulated build of
+    the kernel sources, injected by tests as _lib._LIB, reports False."""
+    return bool(getattr(_lib._LIB, "_ndp_requires_cuda", True))
+
+
 def _stream(lib, ref: torch.Tensor):
     if getattr(lib, "_ndp_requires_cuda", False):
         return ctypes.c_void_p(torch.cuda.current_stream(ref.device).cuda_stream)

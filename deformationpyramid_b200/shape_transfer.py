@@ -31,7 +31,9 @@ SHAPE_TRANSFER_CONFIG = dict(gpu_mode=True, iters=500, lr=0.01, max_break_count=
 
 def read_ply_ascii(path: str) -> Tuple[np.ndarray, np.ndarray, list]:
     """-> (vertices [V,3] float32, faces [F,3] int64 (polygons fan-triangulated), header property names)."""
-    with open(path, "r") as f:
+    import gzip
+    opener = (lambda q: gzip.open(q, "rt")) if str(path).endswith(".gz") else (lambda q: open(q, "r"))
+    with opener(path) as f:
         if f.readline().strip() != "ply":
             raise ValueError(f"{path}: not a PLY file")
         fmt = f.readline().split()
@@ -96,9 +98,10 @@ def sample_points_uniformly(verts: np.ndarray, faces: np.ndarray, number_of_poin
 
 
 def shape_transfer(src_pts: np.ndarray, tgt_pts: np.ndarray, src_verts: np.ndarray, device=0, seed: int = 0,
-                   **overrides):
+                   add_target_mean: bool = False, **overrides):
     """shape_transfer.py:92-165 for already sampled clouds.  Returns (warped vertices [V,3] numpy,
-    Adam steps per level, last loss per level)."""
+    Adam steps per level, last loss per level).  Like the reference (shape_transfer.py:161-165) the warped
+    vertices stay in the CENTRED target frame; add_target_mean=True moves them onto the target mesh."""
     from .model.registration import Registration
     cfg = AttrDict(SHAPE_TRANSFER_CONFIG)
     for k, v in overrides.items():
@@ -113,16 +116,18 @@ def shape_transfer(src_pts: np.ndarray, tgt_pts: np.ndarray, src_verts: np.ndarr
     torch.manual_seed(seed)
     reg = Registration(cfg)
     reg.load_pcds(cloud, tgt_pts.astype(np.float32))
-    warped, _, _ = _register_leading_samples(reg, n_s, tgt_pts.shape[0])
+    warped, _, _ = _register_leading_samples(reg, n_s, tgt_pts.shape[0], add_target_mean)
     return warped[n_s:].cpu().numpy(), reg.last_iters, reg.last_losses
 
 
-def _register_leading_samples(reg, n_src_samples: int, n_tgt_samples: int):
+def _register_leading_samples(reg, n_src_samples: int, n_tgt_samples: int, add_target_mean: bool = False):
     """The fused driver with the sub-sampling of registration.py:156-159 replaced by the identity on the
     leading n samples (shape_transfer.py optimises on all sampled points, :112-113) and the source centred
     on the mean of the SAMPLED points (shape_transfer.py:104-107, 163-164), not of the whole cloud.
     The native solver subtracts the mean of the cloud it is given, so the cloud is pre-centred here and one
-    balancing point is appended that makes that mean zero; it is warped along and dropped."""
+    balancing point is appended that makes that mean zero; it is warped along and dropped.  The numbers of
+    optimised points are passed to the solver explicitly (src_samples / tgt_samples of the C ABI), so clouds of
+    different sizes are fine: config.samples is only the capacity."""
     NDP = reg._build_pyramid()
     src, tgt = reg.src_pcd.contiguous(), reg.tgt_pcd.contiguous()
     dev = src.device
@@ -135,10 +140,12 @@ def _register_leading_samples(reg, n_src_samples: int, n_tgt_samples: int):
     sp = torch.arange(n_src_samples, dtype=torch.int32, device=dev)
     tp = torch.arange(n_tgt_samples, dtype=torch.int32, device=dev)
     solver = reg._get_solver(1, src_in.shape[0], tgt_in.shape[0])
-    warped, iters, losses = solver.register([src_in], [tgt_in], [flat], [sp], [tp])
+    warped, iters, losses = solver.register([src_in], [tgt_in], [flat], [sp], [tp], src_samples=[n_src_samples],
+                                            tgt_samples=[n_tgt_samples])
     NDP.load_flat_parameters(flat)
     reg.NDP, reg.last_iters, reg.last_losses = NDP, iters[0], losses[0]
-    return warped[0][:-1] + tgt_mean, {}, None
+    out = warped[0][:-1]            # the native solver adds the mean of the target cloud it was given: zero here
+    return (out + tgt_mean if add_target_mean else out), {}, None
 
 
 def main():
@@ -147,13 +154,15 @@ def main():
     ap.add_argument("-t", type=str, required=True, help="Path to the tgt mesh.")
     ap.add_argument("-o", type=str, default=None, help="Write the fitted mesh here (ASCII PLY).")
     ap.add_argument("--samples", type=int, default=SHAPE_TRANSFER_CONFIG["samples"])
+    ap.add_argument("--on-target", action="store_true", help="add the target mean back (the reference leaves the "
+                    "fitted vertices in the centred target frame, shape_transfer.py:161-165)")
     args = ap.parse_args()
     sv, sf, _ = read_ply_ascii(args.s)
     tv, tf, _ = read_ply_ascii(args.t)
     rng = np.random.default_rng(0)
     sp = sample_points_uniformly(sv, sf, args.samples, rng)
     tp = sample_points_uniformly(tv, tf, args.samples, rng)
-    warped, iters, losses = shape_transfer(sp, tp, sv)
+    warped, iters, losses = shape_transfer(sp, tp, sv, add_target_mean=args.on_target)
     print("Adam steps per level:", [int(v) for v in iters], "last loss per level:", [round(float(v), 5) for v in losses])
     if args.o:
         write_ply_ascii(args.o, warped, sf)

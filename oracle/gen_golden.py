@@ -175,10 +175,12 @@ class _RecAdam(torch.optim.Adam):
     log = []
     keep = None   # callable (level, it) -> bool
     level = -1
+    steps = []    # Adam steps taken per level
 
     def __init__(self, params, **kw):
         super().__init__(params, **kw)
         _RecAdam.level += 1
+        _RecAdam.steps.append(0)
         self._it = 0
 
     def _state(self):
@@ -195,6 +197,7 @@ class _RecAdam(torch.optim.Adam):
             r = dict(level=_RecAdam.level, it=self._it, step_before=st, params_before=flat(ps),
                      m_before=flat(m), v_before=flat(v), grads=flat([p.grad for p in ps]))
         res = super().step(closure)
+        _RecAdam.steps[_RecAdam.level] += 1
         if rec:
             ps, m, v, st = self._state()
             r.update(params_after=flat(ps), m_after=flat(m), v_after=flat(v))
@@ -206,7 +209,7 @@ class _RecAdam(torch.optim.Adam):
 def run_reference_register(cfg, src, tgt, seed, keep=None, landmarks=None):
     """Unmodified Registration.register() with instrumentation wrapped AROUND the reference's
     own calls (the recording Adam subclass and a recording wrapper of the Chamfer function)."""
-    _RecAdam.log, _RecAdam.keep, _RecAdam.level = [], keep, -1
+    _RecAdam.log, _RecAdam.keep, _RecAdam.level, _RecAdam.steps = [], keep, -1, []
     cd_log = []
     orig_cd = ref_loss.compute_truncated_chamfer_distance
 
@@ -277,11 +280,108 @@ def gen_pairs():
     np.savez_compressed(os.path.join(GOLD, "pairs.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------
+# G5: evaluation metrics of the unmodified model/loss.py:382-403, 431-471
+# ------------------------------------------------------------------------------------
+def gen_metrics():
+    out, names = {}, []
+    g = torch.Generator().manual_seed(9)
+    for name, n, noise, frac in (("small", 40, 0.01, 0.5), ("mixed", 3000, 0.03, 0.7), ("bad", 500, 0.4, 0.2),
+                                 ("allvis", 64, 0.02, 1.0)):
+        gt = 0.1 * torch.randn(n, 3, generator=g)
+        gt[: n // 8] *= 0.01                                   # tiny labels: the relative criteria decide
+        flow = gt + noise * torch.randn(n, 3, generator=g) * torch.rand(n, 1, generator=g)
+        overlap = torch.rand(n, generator=g) < frac
+        m = ref_loss.compute_flow_metrics(flow, gt, overlap=overlap)
+        m2 = ref_loss.compute_flow_metrics(flow, gt)
+        s = ref_loss.scene_flow_metrics(flow, gt)
+        out[f"{name}_flow"], out[f"{name}_gt"], out[f"{name}_overlap"] = flow.numpy(), gt.numpy(), overlap.numpy()
+        out[f"{name}_keys"] = np.array(list(m.keys()))
+        out[f"{name}_vals"] = np.array([m[k] for k in m], np.float64)
+        out[f"{name}_keys_noov"] = np.array(list(m2.keys()))
+        out[f"{name}_vals_noov"] = np.array([m2[k] for k in m2], np.float64)
+        out[f"{name}_scene"] = np.array(s, np.float64)
+        names.append(name)
+    out["meta"] = np.array(names)
+    np.savez_compressed(os.path.join(GOLD, "metrics.npz"), **out)
+    print("metrics.npz", names)
+
+
+# ------------------------------------------------------------------------------------
+# G6: the other branches of the unmodified Registration.register(): landmarks (LNDP, registration.py:187-203,
+#     with and without the truncated Chamfer term) and the nonrigidity regulariser (:216-220)
+# ------------------------------------------------------------------------------------
+def gen_branches():
+    out, meta = {}, []
+
+    def case(name, cfg, p, n, m, seed, n_ldmk):
+        src, tgt = make_pair(p, n, m)
+        landmarks = None
+        if n_ldmk:
+            g = torch.Generator().manual_seed(100 + p)
+            pick = torch.randperm(n, generator=g)[:n_ldmk]
+            ls = src[pick].clone()
+            # plausible correspondences: the source landmarks pushed through the pair generator's own smooth warp
+            # (a rotation about z, a shift and a sinusoidal displacement), plus a little noise
+            ang = 0.17
+            R = torch.tensor([[np.cos(ang), -np.sin(ang), 0.0], [np.sin(ang), np.cos(ang), 0.0], [0.0, 0.0, 1.0]], dtype=torch.float32)
+            lt = ls @ R.T + torch.tensor([0.03, -0.02, 0.01]) + 0.04 * torch.sin(3.0 * ls[:, [1, 2, 0]])
+            lt = lt + 0.002 * torch.randn(n_ldmk, 3, generator=g)
+            landmarks = (ls, lt)
+            out[f"{name}_ldmk_s"], out[f"{name}_ldmk_t"] = ls.numpy(), lt.numpy()
+        warped, cd_log, _ = run_reference_register(cfg, src, tgt, seed, landmarks=landmarks)
+        out[f"{name}_pair"] = np.array([p, n, m, seed, n_ldmk])
+        out[f"{name}_warped"] = warped.numpy()
+        out[f"{name}_steps"] = np.array(_RecAdam.steps, np.int64)
+        out[f"{name}_cd"] = np.array([c[2] for c in cd_log], np.float32)
+        out[f"{name}_cfg"] = np.array([f"{k}={v}" for k, v in cfg.items() if k != "device"])
+        meta.append(name)
+        print(name, "adam steps per level", _RecAdam.steps, "chamfer calls", len(cd_log))
+
+    # config/LNDP.yaml's shape (w_cd = 0: landmark loss only), 3 levels
+    case("ldmk", ndp_config(m=3, samples=256, iters=25, w_cd=0.0, trunc_cd=0.25), 41, 500, 480, 4, 60)
+    # landmark + truncated Chamfer (registration.py:189-197; trunc on SQUARED distances)
+    case("ldmk_cd", ndp_config(m=3, samples=256, iters=20, w_cd=0.1, trunc_cd=0.0025), 42, 500, 480, 5, 60)
+    # nonrigidity regulariser (registration.py:216-220): nr_branch on every level but the first
+    case("wreg", ndp_config(m=3, samples=256, iters=20, w_reg=0.2, max_break_count=10 ** 9), 43, 400, 380, 6, 0)
+    out["meta"] = np.array(meta)
+    np.savez_compressed(os.path.join(GOLD, "branches.npz"), **out)
+
+
+# ------------------------------------------------------------------------------------
+# G7: BASELINE.json config 2 AS WRITTEN (2048-pt pair, one level, 200 Adam iterations, early stop off):
+#     the reference's loss curve, sample permutations and final warped cloud (the per-step states are
+#     regenerated by the tests from the oracle, which this curve pins over all 200 steps)
+# ------------------------------------------------------------------------------------
+def gen_config2():
+    src, tgt = make_pair(12, 2048, 2048)
+    cfg = ndp_config(m=1, iters=200, samples=2048, max_break_count=10 ** 9)
+    warped, cd_log, _ = run_reference_register(cfg, src, tgt, seed=7)
+    out = dict(pair=np.array([12, 2048, 2048, 7]), losses=np.array([c[2] for c in cd_log], np.float64),
+               warped=warped.numpy(), x_last=cd_log[-1][0].numpy(), t_sample=cd_log[0][1].numpy(),
+               x_it100=cd_log[100][0].numpy())
+    np.savez_compressed(os.path.join(GOLD, "config2.npz"), **out)
+    print("config2.npz", len(cd_log), "iterations, loss", cd_log[0][2], "->", cd_log[-1][2])
+
+
+# ------------------------------------------------------------------------------------
+# G8: the reference's own fixtures for BASELINE.json config 1 (sim3_demo/*.ply), gzip-compressed byte for byte
+# ------------------------------------------------------------------------------------
+def gen_meshes():
+    import gzip
+    for name in ("AlienSoldier", "Ortiz"):
+        with open(f"/root/reference/sim3_demo/{name}.ply", "rb") as f:
+            raw = f.read()
+        with open(os.path.join(GOLD, f"{name}.ply.gz"), "wb") as f, gzip.GzipFile(fileobj=f, mode="wb", mtime=0, compresslevel=9) as z:
+            z.write(raw)
+        print(name, len(raw), "bytes, sha256", hashlib.sha256(raw).hexdigest()[:16])
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    gen_layers()
-    gen_chamfer()
-    gen_trajectory()
-    gen_pairs()
+    only = sys.argv[1:]
+    for fn in (gen_layers, gen_chamfer, gen_trajectory, gen_pairs, gen_metrics, gen_branches, gen_config2, gen_meshes):
+        if not only or fn.__name__ in only:
+            fn()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)) // 1024, "KiB")

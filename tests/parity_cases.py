@@ -363,3 +363,97 @@ def check_headline_config_vs_oracle(lib, device, npairs=32, points=8192, levels=
             assert d < (2e-4 if lv < 3 else 2e-3), (p, lv, devs)
         assert rel(warped[p].cpu().numpy(), ref.warped.numpy()) < 2e-3, (p, devs)
     solver.close()
+
+
+def check_config2_teacher_forced(lib, device, golden_dir, stride=1, free_run=True):
+    """BASELINE.json config 2 AS WRITTEN: 2048-pt pair, one level, 200 Adam iterations, early
+    stop off.  The per-step states come from the oracle run, which tests/golden/config2.npz pins to the unmodified
+    reference over all 200 iterations; from EVERY state one iteration of the CUDA path (forward, Chamfer with NN
+    indices, backward, Adam) is compared: warped points / loss 1e-4, NN indices bit-exact, gradients 5e-4 of the
+    largest entry, updated weights and moments 1e-5.  Then the fused solver runs the 200 iterations free: 1e-4 on
+    the first 10 losses; after that the trajectory is chaotic (the ORACLE itself, run on two hosts whose torch CPU
+    kernels round differently, drifts by 1.9e-2 in the loss by iteration 200), so the rest of the curve is held to 5e-2."""
+    G = np.load(os.path.join(golden_dir, "config2.npz"))
+    p, n, m, seed = [int(v) for v in G["pair"]]
+    src, tgt = make_pair(p, n, m)
+    spec = O.LayerSpec(depth=3, width=128, k0=-8, m=1)
+    names = [nm for nm, _ in O.param_layout(spec)]
+    states = []
+
+    def hook(level, it, st):
+        P, opt = st["params"], st["opt"]
+        ps = [P[nm] for nm in names]
+        grads = torch.autograd.grad(st["loss"], ps, retain_graph=True)
+        gy_ref, = torch.autograd.grad(st["loss"], st["x_out"], retain_graph=True)
+        mom = [opt.state[q]["exp_avg"].clone() if q in opt.state and "exp_avg" in opt.state[q] else torch.zeros_like(q) for q in ps]
+        var = [opt.state[q]["exp_avg_sq"].clone() if q in opt.state and "exp_avg_sq" in opt.state[q] else torch.zeros_like(q) for q in ps]
+        flat = lambda ts: torch.cat([t.detach().reshape(-1) for t in ts]).clone()
+        states.append(dict(params=flat(ps), grads=flat(grads), m=flat(mom), v=flat(var), step=it,
+                           loss=float(st["loss"]), x_in=st["x_in"].detach().clone(), x_out=st["x_out"].detach().clone(),
+                           gy=gy_ref.detach().clone()))
+
+    torch.manual_seed(seed)
+    cfgo = O.NDPConfig(m=1, iters=200, samples=2048, max_break_count=10 ** 9)
+    torch.manual_seed(seed)
+    init = [O.init_params(spec)]
+    sp, tp = torch.randperm(n), torch.randperm(m)
+    ref = O.optimize_pair(cfgo, src, tgt, init=init, src_perm=sp, tgt_perm=tp, knn_threads=O.max_threads(), hook=hook)
+    assert len(states) == 200
+    # the states ARE the reference's: its loss curve to rounding over the first iterations, within the free-running horizon
+    # after (torch's CPU kernels round differently from host to host; SURVEY.md section 7, hard part 3)
+    od = np.abs(np.array([s["loss"] for s in states]) - G["losses"]) / G["losses"]
+    assert od[:20].max() < 1e-5 and od.max() < 5e-2, (od[:20].max(), od.max())    # measured host to host: 1e-7 / 1.9e-2
+    t_sample = dev(torch.from_numpy(G["t_sample"]), device)
+    cfg = ops.make_layer_cfg(3, 128, -8, 1, "axis_angle", False, "SE3")
+    worst = dict(y=0.0, loss=0.0, gy=0.0, g=0.0, p=0.0)
+    nn_flips = 0
+    for k in range(0, 200, stride):
+        s = states[k]
+        params = dev(s["params"].clone(), device)
+        x_in = dev(s["x_in"], device)
+        pack = ops.pack_params(cfg, params, lib=lib)
+        y, _, saved = ops.layer_forward(cfg, params, pack, x_in, lib=lib)
+        worst["y"] = max(worst["y"], rel(y.cpu().numpy(), s["x_out"].numpy()))
+        loss, gy, nn = ops.chamfer(y, t_sample, 1e9, want_nn=True, lib=lib)
+        worst["loss"] = max(worst["loss"], abs(float(loss) - s["loss"]) / s["loss"])
+        yc = y.cpu()
+        rd, ri = O.knn1(yc, t_sample.cpu(), threads=O.max_threads())          # the oracle's search on the kernel's own output
+        assert torch.equal(nn[1].cpu(), ri) and torch.equal(nn[0].cpu(), rd), k
+        rd, ri = O.knn1(t_sample.cpu(), yc, threads=O.max_threads())
+        assert torch.equal(nn[3].cpu(), ri) and torch.equal(nn[2].cpu(), rd), k
+        # kernel (2) proper: on the ORACLE's warped points (the direction of a residual of length ~1e-4 is sensitive to a
+        # 1e-7 difference in y, so dL/dy is compared on identical inputs): loss, gradient, all neighbours bit-exact
+        xo = dev(s["x_out"], device)
+        loss2, gy2, nn2 = ops.chamfer(xo, t_sample, 1e9, want_nn=True, lib=lib)
+        oi = O.knn1(s["x_out"], t_sample.cpu(), threads=O.max_threads())
+        oj = O.knn1(t_sample.cpu(), s["x_out"], threads=O.max_threads())
+        assert torch.equal(nn2[1].cpu(), oi[1]) and torch.equal(nn2[0].cpu(), oi[0]) and torch.equal(nn2[3].cpu(), oj[1]), k
+        nn_flips += 0 if (torch.equal(oi[1], nn[1].cpu()) and torch.equal(oj[1], nn[3].cpu())) else 1
+        worst["gy"] = max(worst["gy"], rel(gy2.cpu().numpy(), s["gy"].numpy()), abs(float(loss2) - s["loss"]) / s["loss"])
+        # the backward kernel proper: fed the ORACLE's dL/dy, so that a flipped neighbour cannot leak into this figure
+        gp, _ = ops.layer_backward(cfg, params, pack, x_in, saved, dev(s["gy"], device), lib=lib)
+        worst["g"] = max(worst["g"], rel(gp.cpu().numpy(), s["grads"].numpy()))
+        if k + 1 < 200:
+            mm, vv = dev(s["m"].clone(), device), dev(s["v"].clone(), device)
+            ops.adam_step(params, dev(s["grads"], device), mm, vv, s["step"] + 1, 0.01, cfg=cfg, pack=pack, lib=lib)
+            worst["p"] = max(worst["p"], rel(params.cpu().numpy(), states[k + 1]["params"].numpy()),
+                             rel(mm.cpu().numpy(), states[k + 1]["m"].numpy()), rel(vv.cpu().numpy(), states[k + 1]["v"].numpy()))
+    print("config 2 teacher-forced, worst over the steps:", {k: f"{v:.1e}" for k, v in worst.items()},
+          f"steps with a flipped near-tie neighbour: {nn_flips}")
+    assert worst["y"] < REL_TOL and worst["loss"] < REL_TOL and worst["gy"] < REL_TOL and worst["g"] < 5 * REL_TOL and worst["p"] < 1e-5, worst
+
+    if not free_run:
+        return
+    # free-running: the fused solver over the same 200 iterations
+    solver = ops.Solver(max_pairs=1, max_src_points=n, max_tgt_points=m, samples=2048, levels=1, k0=-8, depth=3, width=128,
+                        motion="SE3", rotation_format="axis_angle", iters=200, max_break_count=10 ** 9,
+                        break_threshold_ratio=0.001, lr=0.01, record_loss=True, lib=lib)
+    flat = dev(O.flatten_params(spec, init[0]).clone(), device)
+    warped, its, last = solver.register([dev(src, device)], [dev(tgt, device)], [flat], [dev(sp[:2048].to(torch.int32), device)],
+                                        [dev(tp[:2048].to(torch.int32), device)])
+    curve = solver.losses(0)[0].numpy().astype(np.float64)
+    d = np.abs(curve - G["losses"]) / G["losses"]
+    print(f"config 2 free-running: max relative loss deviation first 10 {d[:10].max():.1e}, all 200 {d.max():.1e}; "
+          f"warped rel {rel(warped[0].cpu().numpy(), G['warped']):.1e}")
+    assert int(its[0, 0]) == 200 and d[:10].max() < REL_TOL and d.max() < 5e-2
+    solver.close()

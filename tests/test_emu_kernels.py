@@ -64,6 +64,12 @@ def test_trajectory(lib, golden_dir):
     check_trajectory_teacher_forced(lib, golden_dir, device="cpu")
 
 
+def test_config2_as_written_teacher_forced_sampled(lib, golden_dir):
+    """Three of the 200 steps in the emulation (all 200 + the free-running solver on the GPU: tests/test_gpu_parity.py)."""
+    from parity_cases import check_config2_teacher_forced
+    check_config2_teacher_forced(lib, "cpu", golden_dir, stride=90, free_run=False)
+
+
 def test_solver_small(lib):
     check_solver_against_oracle(lib, device="cpu", host=True, npairs=2, n=300, m=260, samples=200, levels=2,
                                 iters=5, early_stop=False)

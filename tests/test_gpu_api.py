@@ -204,7 +204,105 @@ def test_headless_shape_transfer_sim3_euler():
                           src_perm=torch.arange(500), tgt_perm=torch.arange(460))
     with torch.no_grad():
         ref_v, _ = O.pyramid_warp(specs, res.params, verts - s_mean)
-    ref_v = ref_v + t_mean
+    # like the reference (shape_transfer.py:161-165) the fitted vertices stay in the centred target frame
     assert [int(v) for v in iters] == res.iters_per_level
     assert np.allclose(np.array([float(v) for v in losses]), np.array(res.loss_per_level), rtol=5e-4)
     assert rel(warped, ref_v.numpy()) < 2e-3
+    torch.manual_seed(3)
+    on_tgt, _, _ = st.shape_transfer(src_pts.numpy(), tgt_pts.numpy(), verts.numpy(), device=0, seed=3, m=3, iters=6,
+                                     max_break_count=10 ** 9, add_target_mean=True)
+    assert rel(on_tgt, (ref_v + t_mean).numpy()) < 2e-3
+
+
+def test_config1_real_meshes_vs_oracle(golden_dir):
+    """BASELINE.json configs[0] on the reference's own fixtures (sim3_demo/AlienSoldier.ply -> Ortiz.ply, 24 856 / 26 575
+    vertices; shape_transfer.py:27-49: 6000 surface samples per mesh, Sim3 + euler, 9 levels; all 24 856 vertices
+    warped at the end) through the headless path: ASCII-PLY reader, area-weighted sampler, fused driver, inference
+    warp -- against the oracle on the same samples and weights, 3 iterations per level."""
+    import os
+    from deformationpyramid_b200 import shape_transfer as st
+    sv, sf, _ = st.read_ply_ascii(os.path.join(golden_dir, "AlienSoldier.ply.gz"))
+    tv, tf, _ = st.read_ply_ascii(os.path.join(golden_dir, "Ortiz.ply.gz"))
+    assert sv.shape == (24856, 3) and tv.shape == (26575, 3)
+    rng = np.random.default_rng(0)
+    sp = st.sample_points_uniformly(sv, sf, 6000, rng)
+    tp = st.sample_points_uniformly(tv, tf, 6000, rng)
+    warped, iters, losses = st.shape_transfer(sp, tp, sv, device=0, seed=11, iters=3, max_break_count=10 ** 9)
+    assert warped.shape == (24856, 3) and np.isfinite(warped).all()
+    cfgo = O.NDPConfig(iters=3, samples=6000, m=9, motion_type="Sim3", rotation_format="euler", max_break_count=10 ** 9)
+    torch.manual_seed(11)
+    specs = O.make_specs(3, 128, -8, 9, "euler", motion="Sim3")
+    init = [O.init_params(s) for s in specs]
+    spt, tpt = torch.from_numpy(sp), torch.from_numpy(tp)
+    res = O.optimize_pair(cfgo, spt, tpt, init=init, src_perm=torch.arange(6000), tgt_perm=torch.arange(6000),
+                          knn_threads=O.max_threads())
+    with torch.no_grad():
+        ref_v, _ = O.pyramid_warp(specs, res.params, torch.from_numpy(sv) - spt.mean(0, keepdim=True))
+    assert [int(v) for v in iters] == res.iters_per_level == [3] * 9
+    assert np.allclose(np.array([float(v) for v in losses]), np.array(res.loss_per_level), rtol=2e-3)
+    assert rel(warped, ref_v.numpy()) < 2e-3
+
+
+def _write_4dmatch_dir(root, n_pairs, lo, hi):
+    import os
+    for k in range(n_pairs):
+        d = os.path.join(root, "4DMatch-F", f"seq{k // 2:03d}")
+        os.makedirs(d, exist_ok=True)
+        g = np.random.default_rng(70 + k)
+        ns, nt = int(g.integers(lo, hi)), int(g.integers(lo, hi))
+        src, tgt = make_pair(500 + k, ns, nt)
+        rot = np.eye(3, dtype=np.float32)
+        trans = g.normal(0, 0.02, (3, 1)).astype(np.float32)
+        flow = (0.03 * np.sin(3.0 * src.numpy()[:, [1, 2, 0]])).astype(np.float32)
+        corr = np.stack([np.arange(0, ns, 3), np.arange(0, ns, 3) % nt], 1)
+        np.savez(os.path.join(d, f"cam1_{k:04d}_cam2_{k + 1:04d}.npz"), rot=rot, trans=trans, s2t_flow=flow, s_pc=src.numpy(),
+                 t_pc=tgt.numpy(), correspondences=corr)
+
+
+def test_shard_evaluate_with_the_real_registration_config5_shape(tmp_path):
+    """Row f1 on hardware, config-5 shape (config/NDP.yaml as shipped: samples = 2000, 9 levels; ragged clouds of several
+    thousand points, ~15.6 ragged tiles per pair): the 4DMatch .npz reader + shard.evaluate + Registration.register_batch
+    + flow metrics, per pair against the oracle driven with the same per-pair seed."""
+    from deformationpyramid_b200 import shard
+    from deformationpyramid_b200.model.registration import Registration
+    _write_4dmatch_dir(str(tmp_path), 5, 3000, 9000)
+    D = shard.FourDMatchPairs(str(tmp_path), "4DMatch-F")
+    assert len(D) == 5
+    cfg = ndp_config(iters=4, device=0)                     # NDP.yaml defaults otherwise (samples 2000, m 9, early stop on)
+    reg = Registration(cfg)
+    rows, avg = shard.evaluate(reg, len(D), D.__getitem__, rank=0, world=1, batch=3, base_seed=1000)
+    assert rows.shape == (5, 13) and [int(v) for v in rows[:, 0]] == list(range(5))
+    for i in range(5):
+        it = D[i]
+        src, tgt = torch.from_numpy(it["src_pcd"]), torch.from_numpy(it["tgt_pcd"])
+        torch.manual_seed(1000 + i)
+        ref = O.optimize_pair(O.NDPConfig(iters=4), src, tgt, knn_threads=O.max_threads())
+        gt, ov = shard.ground_truth_flow(it)
+        want = O.compute_flow_metrics(ref.warped - src, gt, overlap=ov)
+        for j, k in enumerate(shard.METRIC_KEYS):
+            # EPE (cm): relative; AccS / AccR / outlier are percentages of points under a threshold: a handful of points
+            # sitting on a threshold flip with fp32-level differences in the flow (1.5 percentage points)
+            # (EPE is in cm: 0.1 = 1 mm on metre-scale clouds after 36 free-running iterations)
+            tol = max(0.1, 5e-3 * abs(want[k])) if k.endswith("epe") else 1.5
+            assert abs(float(rows[i, 1 + j]) - want[k]) <= tol, (i, k, float(rows[i, 1 + j]), want[k])
+    assert set(avg) == set(shard.METRIC_KEYS)
+
+
+def test_registration_timer_keys_of_the_fused_route():
+    """registration.py:207-213, 234-238: a caller's Timers object receives lvl_warp / Chamfer / backprop (device time of
+    the sampled kernels scaled to the iterations executed) next to the fused call's wall clock."""
+    from deformationpyramid_b200.model.registration import Registration
+    from deformationpyramid_b200.utils import Timers
+    cfg = ndp_config(samples=1024, m=3, iters=40, max_break_count=10 ** 9, device=0)
+    src, tgt = make_pair(35, 1500, 1400)
+    reg = Registration(cfg)
+    reg.load_pcds(src.numpy(), tgt.numpy())
+    timer = Timers()
+    timer.tic("registration")
+    warped, _, timer2 = reg.register(timer=timer)
+    timer.toc("registration")
+    assert timer2 is timer
+    for key in ("lvl_warp", "Chamfer", "backprop"):
+        t = timer.timers[key]
+        assert t.calls == 120 and 0.0 < t.total_time < timer.timers["registration"].total_time, (key, t.calls, t.total_time)
+    assert all(isinstance(s, str) for s in timer.get_strings())

@@ -106,6 +106,11 @@ def test_trajectory_teacher_forced(lib, golden_dir):
     check_trajectory_teacher_forced(lib, golden_dir, DEV)
 
 
+def test_config2_as_written_every_step_teacher_forced(lib, golden_dir):
+    from parity_cases import check_config2_teacher_forced
+    check_config2_teacher_forced(lib, DEV, golden_dir)
+
+
 def test_solver_config2_shape(lib):
     """BASELINE.json configs[1] shape: 2048-pt pair, single level; free-running horizon per
     SURVEY.md section 7 (hard part 3): the first iterations agree with the oracle to 1e-4."""
