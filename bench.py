@@ -5,13 +5,18 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ndp|reference]
 
 A "step" registers `--pairs` independent synthetic pairs per GPU (fixed-iteration mode A: early
-stop disabled, exactly levels x iters Adam iterations per pair).  One JSON line on stdout (rank 0).
+stop disabled, exactly levels x iters Adam iterations per pair).  ONE JSON line on stdout (rank 0);
+everything else any library prints (e.g. NCCL_DEBUG=INFO) goes to stderr.
   value : pairs/s with the clouds, weights and permutations already resident in HBM
           (ndp_solver_register_device), device time from CUDA events, max over ranks.
-  e2e   : pairs/s through Registration.register_batches(host=True): weight construction on the host,
-          pinned-host -> device copies, the optimisation, device -> host read-back of the warped
-          clouds, all inside the timed region (wall clock bracketed by synchronize, max over ranks);
-          the host preparation of the next batch overlaps the GPU work of the current one.
+  e2e   : pairs/s through the public API with HOST buffers -- shard.evaluate over
+          Registration.register_batches(host=True): pair sharding by rank, per-pair seeding, weight
+          construction on the host, pinned-host -> device copies, the optimisation, device -> host
+          read-back of the warped clouds, and the path's only collective (the final all_gather of the
+          per-pair rows) all inside the timed region; the host work of batch k + 1 overlaps the GPU
+          work of batch k.
+  mode_b: the same workload with the shipped early-stop thresholds (config/NDP.yaml), iterations
+          executed reported next to the CPU oracle's on the same pairs.
 --impl reference times the CPU oracle port of the same path (oracle/ndp_oracle.py + the C kNN loop)
 on the host cores over a bounded sample of the same workload (see cpu_baseline.sample).
 """
@@ -29,10 +34,21 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# stdout carries exactly one JSON line: native libraries (NCCL's INFO log, when the caller asks for it) write to
+# file descriptor 1 directly, so fd 1 is pointed at stderr for the life of the process and the line goes to a
+# private duplicate of the original stdout
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+sys.stdout = os.fdopen(os.dup(2), "w", buffering=1)
+
 import torch  # noqa: E402
 
 METRIC = "registered point-cloud pairs/sec (8192-pt, 9-level NDP, 500 iters/level)"
 UNIT = "pairs/s"
+
+
+def emit(obj):
+    os.write(_JSON_FD, (json.dumps(obj) + "\n").encode())
 
 
 def parse():
@@ -46,8 +62,10 @@ def parse():
     ap.add_argument("--levels", type=int, default=9)
     ap.add_argument("--iters", type=int, default=500)
     ap.add_argument("--mode", default="fixed", choices=["fixed", "asconfigured"])
-    ap.add_argument("--cpu-sample-iters", type=int, default=3, help="iterations per level of the CPU sample")
+    ap.add_argument("--cpu-sample-iters", type=int, default=50, help="iterations per level of the CPU sample (BASELINE.md 3.4)")
+    ap.add_argument("--cpu-modeb-pairs", type=int, default=3, help="pairs the CPU oracle registers in full in mode B")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mode-b", action="store_true")
     ap.add_argument("--nn-mode", type=int, default=0, help="0: exact culled NN search (default), 1: brute force")
     ap.add_argument("--mlp", default="tensor", choices=["tensor", "fp32"], help="tcgen05 tensor cores (default) or FP32 pipes")
     ap.add_argument("--tpc", type=int, default=None, help="override: tiles per backward CTA")
@@ -67,16 +85,18 @@ def _profile(a):
 
 
 def workload(a):
+    """Identical in the ndp and the reference arm: nothing here depends on the environment or on which arm runs."""
     return {"workload": f"synthetic {a.points}-pt src/tgt pairs (deformationpyramid_b200.synthetic), {a.levels}-level "
                         f"config/NDP.yaml pyramid with samples={a.points}, {a.iters} iters/level, "
                         + ("early stop disabled (fixed-iter mode A)" if a.mode == "fixed"
                            else "shipped early-stop thresholds (mode B)"),
             "points": a.points, "levels": a.levels, "iters_per_level": a.iters, "mode": a.mode,
-            "pairs_per_step_per_gpu": a.pairs,
-            "profile": _profile(a),
-            "mlp": "tcgen05 fp16 hi/lo split, 3 partial products, fp32 accumulate (fp32-accurate)" if a.mlp == "tensor" else "fp32 pipes", "nn_search": "exact culled (Morton blocks + boxes + seeds)" if a.nn_mode == 0 else "brute force", "width": 128, "depth": 3, "motion": "SE3", "rotation": "axis_angle",
-            "l2": "flushed (256 MiB write) between timed steps; one step streams >= 100 MiB of saved activations "
-                  "and gradient partials per iteration (larger than L2)"}
+            "pairs_per_step_per_gpu": a.pairs, "profile": _profile(a),
+            "mlp": "tcgen05 fp16 hi/lo split, 3 partial products, fp32 accumulate (fp32-accurate)" if a.mlp == "tensor" else "fp32 pipes",
+            "nn_search": "exact culled (Morton blocks + boxes + seeds)" if a.nn_mode == 0 else "brute force",
+            "width": 128, "depth": 3, "motion": "SE3", "rotation": "axis_angle",
+            "l2": "flushed (256 MiB write) between timed steps: the per-iteration working set of a step (weights, "
+                  "Adam moments, gradient partials, clouds: ~60 MiB at 32 pairs) is smaller than the 126 MiB L2"}
 
 
 class ClockSampler:
@@ -137,22 +157,35 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(a, knn_threads: int, iters_cap: int):
-    """The oracle port (restatement of registration.py:126-262 on torch-CPU + the C kNN loop) on a
-    bounded sample: `iters_cap` iterations per level of ONE pair of the benchmark workload."""
+def cpu_sample(a, knn_threads: int, iters_cap, pair: int = 0, mode=None):
+    """The oracle port (restatement of registration.py:126-262 on torch-CPU + the C kNN loop) on ONE pair of the
+    benchmark workload (same synthetic pair, same per-pair seed as the GPU arm): `iters_cap` iterations per level
+    (None: as the configuration runs, i.e. mode B in full)."""
     from oracle import ndp_oracle as O
     from deformationpyramid_b200.synthetic import make_pair
-    src, tgt = make_pair(0, a.points, a.points)
+    mode = mode or a.mode
+    src, tgt = make_pair(pair, a.points, a.points)
     cfg = O.NDPConfig(iters=a.iters, samples=a.points, m=a.levels,
-                      max_break_count=10 ** 9 if a.mode == "fixed" else 15)
-    torch.manual_seed(0)
+                      max_break_count=10 ** 9 if mode == "fixed" else 15)
+    torch.manual_seed(pair)
+    timers = {}
     t0 = time.perf_counter()
-    res = O.optimize_pair(cfg, src, tgt, knn_threads=knn_threads, iters_cap=iters_cap)
+    res = O.optimize_pair(cfg, src, tgt, knn_threads=knn_threads, iters_cap=iters_cap, timers=timers)
     dt = time.perf_counter() - t0
     its = sum(len(c) for c in res.loss_curve)
     per_iter = dt / max(its, 1)
-    pair_s = per_iter * a.levels * a.iters
-    return {"seconds": dt, "iterations": its, "sec_per_iteration": per_iter, "pairs_per_s": 1.0 / pair_s}
+    pair_s = per_iter * a.levels * a.iters if mode == "fixed" else dt
+    return {"seconds": dt, "iterations": its, "adam_steps": int(sum(res.iters_per_level)), "sec_per_iteration": per_iter,
+            "pairs_per_s": 1.0 / pair_s, "timers_s": {k: round(v, 4) for k, v in timers.items()}}
+
+
+def cpu_mode_b(a, knn_threads: int, npairs: int):
+    """Mode B (shipped early-stop thresholds) in full on the first `npairs` pairs of the workload."""
+    runs = [cpu_sample(a, knn_threads, None, pair=p, mode="asconfigured") for p in range(npairs)]
+    sec = sum(r["seconds"] for r in runs)
+    return {"pairs": npairs, "value": npairs / sec, "unit": UNIT, "seconds": round(sec, 2),
+            "adam_steps_per_pair": [r["adam_steps"] for r in runs],
+            "timers_s": {k: round(sum(r["timers_s"].get(k, 0.0) for r in runs), 3) for k in ("lvl_warp", "Chamfer", "backprop")}}
 
 
 def run_reference(a, rank):
@@ -164,21 +197,26 @@ def run_reference(a, rank):
     kt = min(cores, O.max_threads())
     for _ in range(a.warmup):
         cpu_sample(a, kt, 1)
-    t, vals = 0.0, []
+    cap = a.cpu_sample_iters if a.mode == "fixed" else None
+    t, vals, last = 0.0, [], None
     for _ in range(a.steps):
-        r = cpu_sample(a, kt, a.cpu_sample_iters)
-        t += r["seconds"]; vals.append(r["pairs_per_s"])
+        last = cpu_sample(a, kt, cap)
+        t += last["seconds"]; vals.append(last["pairs_per_s"])
     v = sum(vals) / len(vals)
-    sample = (f"{a.levels} levels x {a.cpu_sample_iters} iterations of one {a.points}-pt pair per step (torch-CPU MLP/"
-              f"autograd/Adam with {cores} threads + OpenMP C kNN with {kt} threads), per-iteration time linearly "
-              f"extrapolated to {a.levels}x{a.iters} iterations")
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus,
-                      "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t / a.steps,
-                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                      "data": "synthetic", "config": workload(a),
-                      "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                      "gpu_launches": 0}))
+    if a.mode == "fixed":
+        sample = (f"{a.levels} levels x {a.cpu_sample_iters} iterations of one {a.points}-pt pair per step (torch-CPU MLP/"
+                  f"autograd/Adam with {cores} threads + OpenMP C kNN with {kt} threads), per-iteration time linearly "
+                  f"extrapolated to {a.levels}x{a.iters} iterations (BASELINE.md 3.4)")
+    else:
+        sample = f"one {a.points}-pt pair per step registered in full with the shipped early-stop thresholds ({last['adam_steps']} Adam steps)"
+    emit({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus,
+          "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t / a.steps,
+          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+          "data": "synthetic", "config": workload(a),
+          "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                           "spread": [min(vals), max(vals)], "timers_s_last_step": last["timers_s"]},
+          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+          "gpu_launches": 0})
 
 
 # ------------------------------------------------------------------------------------------------
@@ -191,7 +229,7 @@ def main():
         run_reference(a, rank)
         return
 
-    from deformationpyramid_b200 import ops
+    from deformationpyramid_b200 import ops, shard
     from deformationpyramid_b200.config import ndp_config
     from deformationpyramid_b200.model.registration import Registration, _init_flat_cpu
     from deformationpyramid_b200.synthetic import make_pair
@@ -210,17 +248,26 @@ def main():
         torch.cuda.synchronize()
 
     B, N = a.pairs, a.points
-    mbc = 10 ** 9 if a.mode == "fixed" else 15
-    cfg = ndp_config(samples=N, m=a.levels, iters=a.iters, max_break_count=mbc, device=local, **_profile(a))
+    prof = _profile(a)
+
+    def make_cfg(mode):
+        return ndp_config(samples=N, m=a.levels, iters=a.iters, max_break_count=10 ** 9 if mode == "fixed" else 15,
+                          device=local, **prof)
+
+    cfg = make_cfg(a.mode)
     # pairs of this rank: global pair index = rank * B + p (independent units, no data-path collective)
     gids = [rank * B + p for p in range(B)]
     pairs = [make_pair(g, N, N) for g in gids]
 
+    def make_solver(mode, profile_every):
+        c = make_cfg(mode)
+        return ops.Solver(max_pairs=B, max_src_points=N, max_tgt_points=N, samples=N, levels=a.levels, k0=c.k0,
+                          depth=c.depth, width=c.width, motion=c.motion_type, rotation_format=c.rotation_format,
+                          iters=a.iters, max_break_count=c.max_break_count, break_threshold_ratio=c.break_threshold_ratio,
+                          lr=c.lr, profile_every=profile_every, nn_mode=a.nn_mode, mlp_mode=a.mlp, **prof)
+
     # ---- device-resident arm -------------------------------------------------------------------
-    solver = ops.Solver(max_pairs=B, max_src_points=N, max_tgt_points=N, samples=N, levels=a.levels, k0=cfg.k0,
-                        depth=cfg.depth, width=cfg.width, motion=cfg.motion_type, rotation_format=cfg.rotation_format,
-                        iters=a.iters, max_break_count=mbc, break_threshold_ratio=cfg.break_threshold_ratio, lr=cfg.lr,
-                        profile_every=16, nn_mode=a.nn_mode, mlp_mode=a.mlp, **_profile(a))
+    solver = make_solver(a.mode, 16)
     d_src = [s.to(dev) for s, _ in pairs]
     d_tgt = [t.to(dev) for _, t in pairs]
     flats0, sps, tps = [], [], []
@@ -231,51 +278,80 @@ def main():
         tps.append(torch.randperm(N)[:N].to(torch.int32).to(dev))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def dev_step():
+    def dev_step(sv):
         flats = [f.clone() for f in flats0]
         flush.fill_(1)                                   # L2 flush, outside the event bracket
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _, its, last = solver.register(d_src, d_tgt, flats, sps, tps)
+        _, its, last = sv.register(d_src, d_tgt, flats, sps, tps)
         e1.record()
         e1.synchronize()
         return e0.elapsed_time(e1), its, last
 
     for _ in range(a.warmup):
-        dev_step()
+        dev_step(solver)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
     l0 = solver.launch_count
     prof0, ns0 = solver.profile()
+    nn0 = solver.nn_stats() if a.nn_mode == 0 else (0, 0)
     ms_dev, its = 0.0, None
     for _ in range(a.steps):
-        ms, its, last = dev_step()
+        ms, its, last = dev_step(solver)
         ms_dev += ms
     barrier()
     launches = solver.launch_count - l0
     prof1, ns1 = solver.profile()
+    nn1 = solver.nn_stats() if a.nn_mode == 0 else (0, 0)
     prof_pairs = solver.profiled_pairs
     clocks = sampler.stop() if rank == 0 else None
     solver.close()
 
-    # ---- end-to-end arm: the reference-facing API with host buffers ------------------------------
+    # ---- end-to-end arm: the reference-facing API with host buffers, through the sharded evaluation loop ----------
     reg = Registration(cfg)
-    h_pairs = [(s.pin_memory(), t.pin_memory()) for s, t in pairs]
-    for _ in range(min(a.warmup, 1) if a.warmup else 0):
-        reg.register_batch(h_pairs, seeds=gids, host=True)
+    all_pairs = {}                                        # global item index -> numpy clouds (this rank's only)
+
+    def get_item(i):
+        g = i % (B * world)                               # the step's pairs repeat; item i belongs to rank i % world
+        if g not in all_pairs:
+            s, t = make_pair(g, N, N)
+            all_pairs[g] = dict(src_pcd=s.numpy(), tgt_pcd=t.numpy())
+        return all_pairs[g]
+
+    n_items = B * world * a.steps
+    for i in shard.shard_indices(B * world, rank, world):
+        get_item(i)
+    if a.warmup:
+        shard.evaluate(reg, B * world, get_item, rank=rank, world=world, batch=B, base_seed=0, compute_metrics=False,
+                       gather_device=dev, host=True)
     barrier()
     t0 = time.perf_counter()
-    # every step = one batch through the public API: weights + permutations built on the host, pinned host ->
-    # device copies, optimisation, device -> host read-back; the host preparation of step k + 1 overlaps the
-    # GPU work of step k (Registration.register_batches), all of it inside the timed region
-    for warped, _, last_e2e in reg.register_batches([h_pairs] * a.steps, seeds=[gids] * a.steps, host=True):
-        if dist is not None:                              # the path's only collective: final metric gather
-            g = [torch.empty_like(last_e2e[:, -1].to(dev)) for _ in range(world)]
-            dist.all_gather(g, last_e2e[:, -1].contiguous().to(dev))
+    rows, _ = shard.evaluate(reg, n_items, get_item, rank=rank, world=world, batch=B, base_seed=0, compute_metrics=False,
+                             gather_device=dev, host=True, checksum=True)
     barrier()
     s_e2e = time.perf_counter() - t0
+    assert rows.shape[0] == n_items
+
+    # SURVEY.md section 4, T4 on hardware: a pair's result is independent of the rank / batch position it ran in.
+    # Rank 0 re-registers the batch that holds the LAST rank's first pair of the first step (same seeds, same batch
+    # size => same execution profile) in a different order and compares the warped cloud's checksum bit for bit.
+    t4 = None
+    if rank == 0:
+        foreign = [i for i in range(B * world) if i % world == world - 1][:B]
+        while len(foreign) < B:
+            foreign.append(foreign[-1])
+        order = foreign[::-1]
+        hp = []
+        for i in order:
+            s, t = make_pair(i % (B * world), N, N)
+            hp.append((s.pin_memory(), t.pin_memory()))
+        w2, _, _ = reg.register_batch(hp, seeds=[0 + i for i in order], host=True)
+        want = float(rows[foreign[0], -1])
+        got = shard.cloud_checksum(w2[len(order) - 1])
+        t4 = {"pair": foreign[0], "owner_rank": world - 1, "bit_identical": bool(got == want)}
+        assert t4["bit_identical"], ("pair result depends on the rank / batch position", t4, got, want)
 
     t_dev = torch.tensor([ms_dev / 1e3, s_e2e], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -284,6 +360,32 @@ def main():
     total_pairs = B * world * a.steps
     value = total_pairs / sec_dev
     e2e = total_pairs / sec_e2e
+
+    # ---- mode B (shipped early-stop thresholds): one step, device-resident and end to end --------------------
+    mode_b = None
+    if a.mode == "fixed" and not a.no_mode_b:
+        sb = make_solver("asconfigured", 0)
+        dev_step(sb)
+        barrier()
+        ms_b, its_b, _ = dev_step(sb)
+        barrier()
+        sb.close()
+        regb = Registration(make_cfg("asconfigured"))
+        shard.evaluate(regb, B * world, get_item, rank=rank, world=world, batch=B, base_seed=0, compute_metrics=False,
+                       gather_device=dev, host=True)
+        barrier()
+        tb0 = time.perf_counter()
+        shard.evaluate(regb, 2 * B * world, get_item, rank=rank, world=world, batch=B, base_seed=0, compute_metrics=False,
+                       gather_device=dev, host=True)
+        barrier()
+        tb = torch.tensor([ms_b / 1e3, time.perf_counter() - tb0], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        mode_b = {"value": B * world / float(tb[0]), "e2e": 2 * B * world / float(tb[1]), "unit": UNIT,
+                  "adam_steps_per_pair_mean": float(its_b.sum()) / B,
+                  "adam_steps_first_pairs": [int(v) for v in its_b.sum(dim=1)[:a.cpu_modeb_pairs]],
+                  "note": "same pairs, weights and permutations as mode A; shipped thresholds max_break_count=15, "
+                          "break_threshold_ratio=0.001 (config/NDP.yaml:10-11); e2e over two batches per rank"}
 
     if rank == 0:
         pk, pk_src = peaks()
@@ -298,46 +400,61 @@ def main():
             with open(tp) as f:
                 traffic = json.load(f)
         sm_clock = (clocks or {}).get("sm_mhz") or pk.get("sm_max_mhz", 1965.0)
-        # dominant kernel: the tensor-core backward (largest share of the step, profiles/r01_launches_*.csv).
+        bwd_kernel = "ndp_warp_bwd_rc_kernel" if a.mlp == "tensor" else "ndp_warp_bwd_kernel"
+        # dominant kernel: the tensor-core backward (largest share of the step, profiles/*launches*.csv).
         # Algorithmic flops per point (kernel (3a)): dW and dH of the two 128x128 layers
-        # 4 * 2*128*128, heads and their back-projection 2 * 2*6*128, input layer 2*128*6 = 135 680.
+        # 4 * 2*128*128, heads and their back-projection 2 * 2*6*128, input layer 2*128*6 = 135 680.  (The kernel
+        # REBUILDS the activations, +65 536 flop per point, and issues every product as 3 fp16 MMAs: neither counts.)
         bwd_flops = prof_pairs * N * (4 * 2 * 128 * 128 + 2 * 2 * 6 * 128 + 2 * 128 * 6)
         tensor_peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1400.0))   # kernel timed inside a long step
         ach_tf = bwd_flops / max(t_bwd, 1e-12) / 1e12
         iso_ms = None
         if traffic.get("pairs_per_launch") == prof_pairs:
-            ku = [(traffic.get(k) or {}).get("gpu__time_duration.sum") for k in ("ndp_warp_bwd_tc_kernel", "ndp_head_grad_kernel")]
+            ku = [(traffic.get(k) or {}).get("gpu__time_duration.sum") for k in (bwd_kernel, "ndp_head_grad_kernel")]
             if all(v is not None for v in ku):
                 iso_ms = sum(ku) * 1e-3
-        roofline = {"bound": "tensor", "kernel": "ndp_head_grad_kernel + ndp_warp_bwd_tc_kernel (one backward launch)",
+        step_flops = B * iters_done * N / 8192.0 * 1.67e9
+        roofline = {"bound": "tensor", "kernel": f"ndp_head_grad_kernel + {bwd_kernel} (one backward launch)",
                     "achieved": ach_tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach_tf / tensor_peak,
-                    "traffic": (traffic.get("ndp_warp_bwd_tc_kernel") or {}).get("dram_bytes_per_launch"),
+                    "traffic": (traffic.get(bwd_kernel) or {}).get("dram_bytes_per_launch"),
                     "peak_source": pk_src + " bf16_tflops_sustained", "algorithmic_flops_per_launch": bwd_flops,
+                    "algorithmic_bytes_per_launch": prof_pairs * (24 * N + 6 * 138776 + (64 // max(prof.get("tiles_per_bwd_cta") or 4, 1)) * 138776),
                     "pairs_per_launch": prof_pairs, "launch_ms": 1e3 * t_bwd,
                     "launch_ms_note": "sampled inside the step with the other stream groups' kernels interleaved on the same SMs; "
                                       "isolated = the ncu launch (profiles/kernel_traffic.json), same pairs per launch",
                     "isolated_launch_ms": iso_ms, "isolated_frac": (bwd_flops / (iso_ms * 1e-3) / 1e12 / tensor_peak) if iso_ms else None,
-                    # the launches of the four stream groups overlap, so per-launch durations overstate the cost:
-                    # the same ratio for the whole step = algorithmic MLP flops (forward 0.56 + backward 1.11 GFLOP per
-                    # pair and iteration at N = 8192) of everything the step registered / the step's device time
-                    "step_level": {"achieved": (B * iters_done * N / 8192.0 * 1.67e9) / (sec_dev / a.steps) / 1e12,
-                                   "frac": (B * iters_done * N / 8192.0 * 1.67e9) / (sec_dev / a.steps) / 1e12 / tensor_peak,
-                                   "unit": "TFLOP/s"},
-                    "note": "fp32-accurate products are issued as 3 fp16 MMAs: issued tensor flops = 3x algorithmic"}
+                    # the launches of the stream groups overlap, so per-launch durations overstate the cost: the same
+                    # ratio for the whole step = algorithmic MLP flops (forward 0.56 + backward 1.11 GFLOP per pair and
+                    # iteration at N = 8192) of everything the step registered / the step's device time
+                    "step_level": {"achieved": step_flops / (sec_dev / a.steps) / 1e12,
+                                   "frac": step_flops / (sec_dev / a.steps) / 1e12 / tensor_peak, "unit": "TFLOP/s"},
+                    "note": "fp32-accurate products are issued as 3 fp16 MMAs and the activations are recomputed: issued tensor "
+                            "flops = 4.4x algorithmic; SS-mode operand fetch (shared-memory bandwidth), not the tensor pipe, binds the kernel (DESIGN.md)"}
         # the metric's second half: one Chamfer call (NN search + epilogue) against the HBM roof
         alg_bytes = prof_pairs * (20 * (N + N) + 12 * N + 4)          # 425 988 B per pair at 8192^2
         achieved = alg_bytes / max(t_nn + t_ep, 1e-12) / 1e9
-        evals = prof_pairs * 2.0 * N * N
-        fp32_roof_evals = 148 * 128 * sm_clock * 1e6 / 8.0     # 8 FP32-pipe instructions per pair evaluation
         nn_names = ("ndp_nn_pruned_kernel", "ndp_chamfer_reduce_kernel") if a.nn_mode == 0 else ("ndp_nn_kernel", "ndp_chamfer_reduce_kernel")
         nn_traffic = [(traffic.get(k) or {}).get("dram_bytes_per_launch") for k in nn_names]
+        nn_work = None
+        if a.nn_mode == 0 and nn1[1] > nn0[1]:
+            evals, qblocks = nn1[0] - nn0[0], nn1[1] - nn0[1]
+            searches = qblocks / (2.0 * (N // 32))                   # (pair, iteration) searches behind the counters
+            per_search_s = t_nn / max(prof_pairs, 1)                 # sampled launch time / pairs per launch
+            issue_roof = 148 * 128 * sm_clock * 1e6 / 11.0           # 11 FP32-pipe instructions per candidate (ndp_spatial.cu)
+            nn_work = {"candidates_per_query": evals / (qblocks * 32.0), "brute_force_candidates_per_query": N,
+                       "pair_evals_issued_per_s": evals / searches / max(per_search_s, 1e-12),
+                       "issue_roof_pair_evals_per_s": issue_roof,
+                       "issue_frac": evals / searches / max(per_search_s, 1e-12) / issue_roof,
+                       "model": "distance evaluations the culled search actually issues (32 x 32 per scanned block) per second of its "
+                                "launch time, against 148 SM x 128 lanes x clock / 11 instructions per evaluation"}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": 1e3 * sec_dev / a.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload(a),
                "clocks": clocks,
                "e2e": {"value": e2e, "unit": UNIT,
                        "h2d_bytes_per_step": B * (2 * N * 12 + 2 * N * 4 + a.levels * P * 4),
-                       "d2h_bytes_per_step": B * (N * 12 + a.levels * P * 4 + a.levels * 8)},
+                       "d2h_bytes_per_step": B * (N * 12 + a.levels * P * 4 + a.levels * 8),
+                       "api": "shard.evaluate(Registration, host=True): pinned host clouds in, warped clouds out, final all_gather of the rows"},
                "gpu_launches": int(launches),
                "iterations_per_pair": iters_done,
                "roofline": roofline,
@@ -347,29 +464,31 @@ def main():
                                     "traffic": sum(nn_traffic) if all(v is not None for v in nn_traffic) else None,
                                     "peak_source": pk_src, "algorithmic_bytes_per_launch": alg_bytes,
                                     "pairs_per_launch": prof_pairs, "launch_ms": 1e3 * (t_nn + t_ep),
-                                    "note": "exact NN search is ALU-issue bound, not HBM bound (SURVEY.md 8d): see fp32"},
-               "fp32": {"pair_evals_per_s": evals / max(t_nn, 1e-12), "roof_pair_evals_per_s": fp32_roof_evals,
-                        "frac": evals / max(t_nn, 1e-12) / fp32_roof_evals, "sm_mhz_used": sm_clock,
-                        "model": "brute-force equivalent pair evaluations (2NM per pair) / time, against 148 SM x 128 lanes x "
-                                 "clock / 8 issue slots; the culled search skips most of them, so > 1 means 'faster than "
-                                 "any brute-force kernel could be'"},
-               "kernel_ms_per_launch": shares, "pairs_per_launch": prof_pairs}
-        if not a.no_cpu_baseline:
+                                    "note": "exact NN search is ALU-issue bound, not HBM bound (SURVEY.md 8d): see nn_search_work"},
+               "nn_search_work": nn_work,
+               "kernel_ms_per_launch": shares, "pairs_per_launch": prof_pairs,
+               "rank_independence": t4, "mode_b": mode_b}
+        if not a.no_cpu_baseline and world == 1:
             from oracle import ndp_oracle as O
             torch.set_num_threads(os.cpu_count() or 1)
             cores = os.cpu_count() or 1
             kt = min(cores, O.max_threads())
             cpu_sample(a, kt, 1)                              # warm the thread pools / the C library
-            par = cpu_sample(a, kt, a.cpu_sample_iters)
+            par = cpu_sample(a, kt, a.cpu_sample_iters if a.mode == "fixed" else None)
             one = cpu_sample(a, 1, 1)
             out["cpu_baseline"] = {
                 "value": par["pairs_per_s"], "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": f"{a.levels} levels x {a.cpu_sample_iters} iterations of one {a.points}-pt pair "
                           f"({par['seconds']:.1f} s; torch-CPU MLP/autograd/Adam on {cores} threads, OpenMP C kNN on "
-                          f"{kt} threads), per-iteration time extrapolated to {a.levels}x{a.iters} iterations",
+                          f"{kt} threads), per-iteration time extrapolated to {a.levels}x{a.iters} iterations (BASELINE.md 3.4)",
+                "timers_s": par["timers_s"],
                 "single_thread_knn_pairs_per_s": one["pairs_per_s"],
                 "single_thread_knn_note": "pytorch3d's CPU kNN is single-threaded: 9 levels x 1 iteration sample"}
-        print(json.dumps(out))
+            if mode_b is not None and a.cpu_modeb_pairs > 0:
+                cb = cpu_mode_b(a, kt, a.cpu_modeb_pairs)
+                out["cpu_baseline"]["mode_b"] = cb
+                mode_b["adam_steps_cpu_oracle_first_pairs"] = cb["adam_steps_per_pair"]
+        emit(out)
     if dist is not None:
         dist.destroy_process_group()
 

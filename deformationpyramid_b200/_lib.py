@@ -22,7 +22,7 @@ EXPORTS = [
     "ndp_pack_params", "ndp_layer_forward", "ndp_layer_backward", "ndp_chamfer", "ndp_adam_step",
     "ndp_solver_create", "ndp_solver_destroy", "ndp_solver_params_per_pair",
     "ndp_solver_register_host", "ndp_solver_register_device", "ndp_solver_last_nn", "ndp_solver_losses",
-    "ndp_solver_launch_count", "ndp_solver_profile", "ndp_solver_profiled_pairs",
+    "ndp_solver_launch_count", "ndp_solver_profile", "ndp_solver_profiled_pairs", "ndp_solver_nn_stats",
 ]
 
 
@@ -84,6 +84,8 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.ndp_solver_losses.argtypes = [c_void_p, c_int32, c_void_p, c_void_p]
     lib.ndp_solver_profile.argtypes = [c_void_p, P(c_double), P(c_int64)]
     lib.ndp_solver_profile.restype = ctypes.c_int
+    lib.ndp_solver_nn_stats.argtypes = [c_void_p, P(c_int64), P(c_int64)]
+    lib.ndp_solver_nn_stats.restype = ctypes.c_int
     lib.ndp_solver_profiled_pairs.argtypes = [c_void_p]
     lib.ndp_solver_profiled_pairs.restype = c_int32
     for name in ("ndp_pack_params", "ndp_layer_forward", "ndp_layer_backward", "ndp_chamfer",

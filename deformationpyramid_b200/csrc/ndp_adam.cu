@@ -10,18 +10,18 @@
 #include "ndp_kernels.h"
 #include "ndp_tc.cuh"
 
-__device__ __forceinline__ void ndp_pack_store(const NdpLayout& L, float* pack, int idx, float val) {
+__device__ __forceinline__ void ndp_pack_store(const NdpLayout& L, float* pack, int idx, float val, int fp32_copies) {
     // canonical index -> transposed copy (W_in[o][c] -> WT_in[c][o]; W_l[o][i] -> WT_l[i][o])
     if (idx < L.off_b_in) {
         const int o = idx / 6, c = idx - o * 6;
-        pack[L.pack_in + c * NDP_W + o] = val;
+        if (fp32_copies) pack[L.pack_in + c * NDP_W + o] = val;
         return;
     }
     for (int l = 0; l < L.hidden; ++l) {
         const int rel = idx - L.off_w[l];
         if (rel >= 0 && rel < NDP_W * NDP_W) {
             const int o = rel >> 7, i = rel & 127;
-            pack[L.pack_w[l] + i * NDP_W + o] = val;
+            if (fp32_copies) pack[L.pack_w[l] + i * NDP_W + o] = val;
             // fp16 hi/lo images of W_l (row o, column i) for the tensor-core kernels
             unsigned h1, h2;
             ndp_split2(val, h1, h2);
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) ndp_reduce_adam_kernel(NdpAdamArgs a) {
     const float denom = sqrtf(v) / bc2_sqrt + (float)a.eps;
     const float pv = *p - step_size * (m / denom);
     *mp = m; *vp = v; *p = pv;
-    if (a.pack) ndp_pack_store(L, a.pack + (long long)pair * a.pack_stride, idx, pv);
+    if (a.pack) ndp_pack_store(L, a.pack + (long long)pair * a.pack_stride, idx, pv, a.pack_fp32);
 }
 
 void ndp_launch_adam(const NdpAdamArgs& a, cudaStream_t s) {

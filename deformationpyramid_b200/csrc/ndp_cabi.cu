@@ -97,7 +97,7 @@ static NnPlan nn_plan(long long n, long long m) {
     p.chunks = (int)((big + p.chunk_targets - 1) / p.chunk_targets);
     if (p.chunks < 1) p.chunks = 1;
     p.qpitch = (int)pad4(big);
-    p.blocks = (int)((big + 255) / 256);
+    p.blocks = (int)((big + 127) / 128);          // per-CTA partial sums: 256 points per CTA of the stand-alone epilogue, 128 of the fused search
     if (p.blocks < 1) p.blocks = 1;
     return p;
 }
@@ -250,6 +250,18 @@ extern "C" int ndp_adam_step(const ndp_layer_cfg* c, float* params, const float*
 // Fused per-pair driver
 // =================================================================================================
 #define NDP_MAX_STREAMS 8
+// The solver's buffers, streams and events belong to the device that was current at creation: make it
+// current for the duration of a call (and restore the caller's), whatever the calling thread had selected.
+struct DeviceGuard {
+    int prev = -1; bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+        if (prev == dev) prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 struct ndp_solver {
     ndp_solver_cfg cfg;
     std::vector<NdpLayout> lay;
@@ -271,6 +283,7 @@ struct ndp_solver {
     int npad = 0, S128 = 0, nboxes = 0, mlp_mode = 0;
     int device = 0;                     // the CUDA device the solver's buffers, streams and events live on
     int tpc = 0, fwd_rounds = 0;        // work grouping of the tensor-core kernels (0 = automatic)
+    unsigned long long* nnstats = nullptr;   // [2] device counters of the culled search (profile_every > 0)
     int last_npairs = 0, last_cur = 0;  // the last register call: pairs, and which sample buffer holds the last warped samples
     long long act_pair = 0;
     double* blocksums = nullptr;
@@ -374,6 +387,7 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
         DA(orig_s, B * S); DA(orig_t, B * S); DA(inv_s, B * S); DA(inv_t, B * S); DA(prev_x, B * S); DA(prev_y, B * S);
     }
     if (c->record_loss) DA(loss_hist, B * c->levels * (long long)c->iters);
+    if (c->profile_every > 0 && c->nn_mode == 0) DA(nnstats, 2);
 #undef DA
     if (!e && cudaMallocHost((void**)&s->h_state, sizeof(NdpPairState) * B) != cudaSuccess) e = fail(NDP_E_NOMEM, "cudaMallocHost failed");
     if (!e && cudaMallocHost((void**)&s->h_counts, sizeof(int) * B * 4) != cudaSuccess) e = fail(NDP_E_NOMEM, "cudaMallocHost failed");
@@ -389,6 +403,7 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
                 e = fail(NDP_E_CUDA, "stream / event creation failed");
     }
     if (!e && cudaMemset(s->gacc, 0, 8 * B * S * 3) != cudaSuccess) e = fail(NDP_E_CUDA, "cudaMemset failed");
+    if (!e && s->nnstats && cudaMemset(s->nnstats, 0, 16) != cudaSuccess) e = fail(NDP_E_CUDA, "cudaMemset failed");
     if (e) { ndp_solver_destroy(s); return e; }
     *out = s;
     return NDP_OK;
@@ -397,6 +412,15 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
 extern "C" int64_t ndp_solver_params_per_pair(const ndp_solver* s) { return s ? (int64_t)s->cfg.levels * s->P : -1; }
 extern "C" int64_t ndp_solver_launch_count(const ndp_solver* s) { return s ? s->launches : -1; }
 extern "C" int32_t ndp_solver_profiled_pairs(const ndp_solver* s) { return s ? s->prof_pairs : -1; }
+extern "C" int ndp_solver_nn_stats(const ndp_solver* s, int64_t* pair_evals, int64_t* query_blocks) {
+    if (!s || !pair_evals || !query_blocks) return fail(NDP_E_INVALID, "NULL argument");
+    if (!s->nnstats) return fail(NDP_E_INVALID, "the solver was created without profile_every > 0 (or runs the brute-force search)");
+    DeviceGuard guard(s->device);
+    unsigned long long h[2] = {0, 0};
+    CK(cudaMemcpy(h, s->nnstats, 16, cudaMemcpyDeviceToHost));
+    *pair_evals = (int64_t)h[0]; *query_blocks = (int64_t)h[1];
+    return NDP_OK;
+}
 extern "C" int ndp_solver_profile(const ndp_solver* s, double* ms, int64_t* samples) {
     if (!s || !ms || !samples) return fail(NDP_E_INVALID, "NULL argument");
     for (int k = 0; k < 5; ++k) ms[k] = s->prof_ms[k];
@@ -479,7 +503,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         pn.x4 = s->x4; pn.y4 = s->t4; pn.p4_stride = s->S128; pn.xbox = s->xbox; pn.ybox = s->tbox; pn.box_stride = s->nboxes;
         pn.prev_x = s->prev_x; pn.prev_y = s->prev_y; pn.prev_stride = S; pn.inv_x = s->inv_s; pn.inv_y = s->inv_t; pn.inv_stride = S; pn.n = s->S; pn.ncounts = s->ncount;
         pn.m = s->S; pn.mcounts = s->mcount; pn.part = s->nnpart; pn.part_pair_stride = ch.nn.part_pair_stride;
-        pn.qpitch = s->plan.qpitch; pn.state = s->state; pn.npairs = npairs;
+        pn.qpitch = s->plan.qpitch; pn.state = s->state; pn.npairs = npairs; pn.stats = s->nnstats;
         ch.trunc = c.trunc; ch.gx = s->gx; ch.gx_stride = S * 3; ch.gacc = s->gacc; ch.gacc_stride = S * 3;
         ch.d2x = nullptr; ch.idxx = nullptr; ch.nx_stride = 0; ch.d2y = nullptr; ch.idxy = nullptr; ch.ny_stride = 0;
         ch.blocksums = s->blocksums; ch.blocks_pitch = s->plan.blocks; ch.counters = s->counters; ch.loss_out = s->loss;
@@ -506,6 +530,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         ad.n = s->S; ad.counts = s->ncount; ad.grads_out = nullptr; ad.grads_stride = 0; ad.state = s->state;
         ad.fixed_step = 0; ad.lr = c.lr; ad.beta1 = 0.9; ad.beta2 = 0.999; ad.eps = 1e-8; ad.do_adam = 1; ad.npairs = npairs;
         ad.tiles_per_row = s->mlp_mode == 0 ? ndp_bwd_tc_tiles_per_cta(L.hidden, s->S, s->tpc) : 1;
+        ad.pack_fp32 = s->mlp_mode == 0 ? 0 : 1;
 
         // the batch is split into stream groups (contiguous pair ranges, sizes differ by at most one)
         const int ng = npairs < s->nstreams ? npairs : s->nstreams;
@@ -548,15 +573,15 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
                 if (pg) CK(cudaEventRecord(ev[0], q));
                 if (s->mlp_mode == 0) ndp_launch_fwd_tc(f, q); else ndp_launch_fwd(f, q);
                 if (pg) CK(cudaEventRecord(ev[1], q));
-                if (culled) ndp_launch_nn_pruned(pn, q); else ndp_launch_nn(ch.nn, q);
+                if (culled) { pn.fuse = &ch; ndp_launch_nn_pruned(pn, q); } else ndp_launch_nn(ch.nn, q);   // culled: search + Chamfer epilogue in one launch
                 if (pg) CK(cudaEventRecord(ev[2], q));
-                ndp_launch_chamfer_reduce(ch, q);
+                if (!culled) ndp_launch_chamfer_reduce(ch, q);
                 if (pg) CK(cudaEventRecord(ev[3], q));
                 if (s->mlp_mode == 0) ndp_launch_bwd_tc(b, q); else ndp_launch_bwd(b, q);
                 if (pg) CK(cudaEventRecord(ev[4], q));
                 ndp_launch_adam(ad, q);
                 if (pg) CK(cudaEventRecord(ev[5], q));
-                s->launches += (s->mlp_mode == 0) ? 6 : 5;
+                s->launches += ((s->mlp_mode == 0) ? 6 : 5) - (culled ? 1 : 0);
             }
             if ((it + 1) % poll == 0 && it + 1 < c.iters) {
                 if (int e = join()) return e;
@@ -627,18 +652,6 @@ static int solver_counts(ndp_solver* s, int npairs, const int32_t* ns, const int
     CK(cudaMemcpyAsync(s->ntcount, s->h_counts + 3 * s->B, sizeof(int) * npairs, cudaMemcpyHostToDevice, st));
     return NDP_OK;
 }
-
-// The solver's buffers, streams and events belong to the device that was current at creation: make it
-// current for the duration of a call (and restore the caller's), whatever the calling thread had selected.
-struct DeviceGuard {
-    int prev = -1; bool ok = true;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
-        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
-        if (prev == dev) prev = -1;
-    }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
 
 static int solver_register(ndp_solver* s, int32_t npairs, const float* const* src, const int32_t* ns,
                            const float* const* tgt, const int32_t* nt, const int32_t* const* src_perm,

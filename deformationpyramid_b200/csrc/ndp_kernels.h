@@ -75,6 +75,7 @@ struct NdpAdamArgs {
     int do_adam;
     int npairs;
     int pair0 = 0;
+    int pack_fp32 = 1;                                // 0: refresh only the fp16 hi/lo images (the tensor-core kernels read nothing else of the pack)
 };
 void ndp_launch_adam(const NdpAdamArgs& a, cudaStream_t s);
 
@@ -152,6 +153,8 @@ struct NdpPrunedArgs {
     const NdpPairState* state;
     int npairs;
     int pair0 = 0;
+    unsigned long long* stats = nullptr;                              // optional [2]: pair evaluations issued (32 lanes x 32 targets per scanned block), 32-query blocks searched
+    const struct NdpChamferArgs* fuse = nullptr;                      // host pointer, read at launch: when set the kernel also does the whole Chamfer epilogue
 };
 void ndp_launch_nn_pruned(const NdpPrunedArgs& a, cudaStream_t s);
 

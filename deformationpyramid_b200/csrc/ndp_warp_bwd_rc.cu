@@ -45,6 +45,7 @@
 
 #ifndef NDP_EMU
 __device__ unsigned long long ndp_dbg_rc[64];
+__device__ unsigned long long ndp_dbg_rc_sum[2];      // sum of CTA durations (ns), CTAs: since the last read
 #define NDP_TR(i) do { if ((tid & 255) == 0 && blockIdx.x == 0 && blockIdx.y == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ndp_dbg_rc[(i) + 24 * (tid >> 8)] = t_; } } while (0)
 #define NDP_TI(i) do { if (blockIdx.x == 0 && blockIdx.y == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ndp_dbg_rc[i] = t_; } } while (0)
 #else
@@ -103,6 +104,10 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
     const int c = (warp >> 3) & 1, q = warp & 3, ch = (warp >> 2) & 1, f = q * 32 + lane, ct = tid & 255;
     const int RS = NDP_IMG_RS(128), CS = NDP_IMG_CS;
     NDP_TR(0);
+#ifndef NDP_EMU
+    unsigned long long t_cta0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_cta0));
+#endif
 
     if (warp == 0) ndp_tmem_alloc_warp(&S.tmem_slot, 512);
     if (issw && ndp_elect_one()) {
@@ -470,6 +475,19 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
     ndp_tc_fence_before();
     __syncthreads();
     NDP_TR(12);
+#ifndef NDP_EMU
+    if (tid == 0 && blockIdx.x == 0) {   // self-contained duration of this CTA (valid with several launches in flight) + its SM
+        unsigned long long t1_; unsigned sm_;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1_));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_));
+        ndp_dbg_rc[62] = t1_ - t_cta0; ndp_dbg_rc[63] = sm_;
+    }
+    if (tid == 0) {                      // running sum / count of CTA durations over every launch since the last read
+        unsigned long long t1_;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1_));
+        atomicAdd(&ndp_dbg_rc_sum[0], t1_ - t_cta0); atomicAdd(&ndp_dbg_rc_sum[1], 1ull);
+    }
+#endif
     if (warp == 0) ndp_tmem_dealloc(S.tmem_slot, 512);
 }
 
@@ -483,7 +501,14 @@ int ndp_bwd_rc_init() {
 }
 
 #ifndef NDP_EMU
-int ndp_debug_copy_rc(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, ndp_dbg_rc, sizeof(unsigned long long) * 64); }
+int ndp_debug_copy_rc(unsigned long long* out) {
+    int e = (int)cudaMemcpyFromSymbol(out, ndp_dbg_rc, sizeof(unsigned long long) * 64);
+    unsigned long long s2[2] = {0, 0}, z[2] = {0, 0};
+    if (e == 0) e = (int)cudaMemcpyFromSymbol(s2, ndp_dbg_rc_sum, sizeof(s2));
+    if (e == 0) e = (int)cudaMemcpyToSymbol(ndp_dbg_rc_sum, z, sizeof(z));
+    out[60] = s2[0]; out[61] = s2[1];
+    return e;
+}
 #else
 int ndp_debug_copy_rc(unsigned long long* out) { for (int i = 0; i < 64; ++i) out[i] = 0; return 0; }
 #endif

@@ -317,6 +317,10 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc2_kernel
     float* xs = S.xs[g];
 
     NDP_T(0);
+#ifndef NDP_EMU
+    unsigned long long t_cta0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_cta0));
+#endif
     if (warp == 0) ndp_tmem_alloc_warp(&S.tmem_slot, 512);
     if (tid == 0) {
         ndp_mbar_init(&S.bar_w[0], 1); ndp_mbar_init(&S.bar_w[1], 1); ndp_mbar_init(&S.bar_mma[0], 1); ndp_mbar_init(&S.bar_mma[1], 1);
@@ -453,6 +457,18 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc2_kernel
     ndp_tc_fence_before();
     __syncthreads();
     NDP_T(63);
+#ifndef NDP_EMU
+    if (tid == 0 && blockIdx.x == 0) {   // self-contained duration of this CTA (valid with several launches in flight)
+        unsigned long long t1_;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1_));
+        ndp_dbg_fwd[62] = t1_ - t_cta0;
+    }
+    if (tid == 0) {
+        unsigned long long t1_;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1_));
+        atomicAdd(&ndp_dbg_fwd[58], t1_ - t_cta0); atomicAdd(&ndp_dbg_fwd[59], 1ull);
+    }
+#endif
     if (warp == 0) ndp_tmem_dealloc(S.tmem_slot, 512);
 }
 

@@ -177,22 +177,30 @@ class Registration():
         return warped, iters, losses
 
     def register_batches(self, batches, seeds=None, host: bool = True):
-        """Generator over a sequence of batches (each a list of (src, tgt) pairs): yields register_batch's
-        result per batch.  The host-side preparation of batch k + 1 (weight construction in the reference's
-        RNG order, permutations) runs in a worker thread while batch k is being optimised on the GPU -- the
-        native call releases the GIL.  Same results as calling register_batch per batch; `seeds` is a
-        sequence of per-batch seed lists (or None).  The preparation uses torch's global CPU generator
-        (like the reference): do not draw from it in the consuming thread while the generator is active."""
+        """Generator over a sequence (or iterator) of batches, each a list of (src, tgt) pairs: yields register_batch's
+        result per batch.  The host-side work for batch k + 1 -- pulling it from the iterator (data loading), weight
+        construction in the reference's RNG order, permutations -- runs in a worker thread while batch k is being
+        optimised on the GPU (the native call releases the GIL).  Same results as calling register_batch per batch;
+        `seeds` is a sequence / iterator of per-batch seed lists (or None).  The preparation uses torch's global CPU
+        generator (like the reference): do not draw from it in the consuming thread while the generator is active."""
         from concurrent.futures import ThreadPoolExecutor
-        batches = list(batches)
-        if not batches:
-            return
+        it_b = iter(batches)
+        it_s = iter(seeds) if seeds is not None else None
+
+        def prepare_next():
+            try:
+                batch = next(it_b)
+            except StopIteration:
+                return None
+            return self._prepare_batch(batch, next(it_s) if it_s is not None else None, host)
+
         with ThreadPoolExecutor(max_workers=1) as pool:
-            nxt = pool.submit(self._prepare_batch, batches[0], None if seeds is None else seeds[0], host)
-            for k in range(len(batches)):
+            nxt = pool.submit(prepare_next)
+            while True:
                 prepared = nxt.result()
-                if k + 1 < len(batches):
-                    nxt = pool.submit(self._prepare_batch, batches[k + 1], None if seeds is None else seeds[k + 1], host)
+                if prepared is None:
+                    return
+                nxt = pool.submit(prepare_next)
                 yield self._run_prepared(prepared, host)
 
     # ------------------------------------------------------------------------------------------

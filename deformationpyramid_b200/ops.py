@@ -313,6 +313,12 @@ class Solver:
         _lib.check(self.lib, self.lib.ndp_solver_profile(self.handle, ms, ctypes.byref(n)), "ndp_solver_profile")
         return dict(zip(self.KERNELS, [float(v) for v in ms])), int(n.value)
 
+    def nn_stats(self):
+        """(distance evaluations issued by the culled search, 32-query blocks searched) since creation."""
+        a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+        _lib.check(self.lib, self.lib.ndp_solver_nn_stats(self.handle, ctypes.byref(a), ctypes.byref(b)), "ndp_solver_nn_stats")
+        return int(a.value), int(b.value)
+
     @property
     def profiled_pairs(self) -> int:
         """Pairs per sampled launch (the driver runs two half-batches on two streams)."""

@@ -94,23 +94,51 @@ def average_metrics(rows: torch.Tensor, keys: Sequence[str] = METRIC_KEYS) -> Di
     return {k: float(rows[:, 1 + i].mean()) for i, k in enumerate(keys)} if rows.numel() else {}
 
 
+def cloud_checksum(t: torch.Tensor) -> float:
+    """48 bits of the SHA-256 of a cloud's bytes as an exactly representable float64: lets ranks compare warped
+    clouds bit for bit through the metric gather."""
+    import hashlib
+    return float(int.from_bytes(hashlib.sha256(t.detach().cpu().contiguous().numpy().tobytes()).digest()[:6], "big"))
+
+
 def evaluate(registration, n_items: int, get_item: Callable[[int], dict], rank: int = 0, world: int = 1,
-             batch: int = 8, base_seed: int = 0, compute_metrics: bool = True, gather_device=None):
+             batch: int = 8, base_seed: int = 0, compute_metrics: bool = True, gather_device=None,
+             host: bool = False, checksum: bool = False):
     """Sharded, batched version of the loop at eval_nolearned.py:70-143.
 
     get_item(i) -> dict(src_pcd, tgt_pcd[, correspondences, rot, trans, s2t_flow]) (numpy).
     Pair i is registered with torch.manual_seed(base_seed + i) applied before its weights and
-    permutations are drawn, so the result does not depend on world size or batch size.
-    Returns (rows gathered on every rank [n_items, 1 + 12], dict of averages)."""
+    permutations are drawn, so the result does not depend on world size or (for a given execution
+    profile, see ops.execution_profile) on the batch it runs in.  Loading and host-side preparation of
+    batch k + 1 overlap the GPU work of batch k (Registration.register_batches).  host=True: the clouds
+    stay (pinned) host tensors and the host<->device copies happen inside the native call.
+    Returns (rows gathered on every rank [n_items, 1 + 12 (+ 1 checksum of the warped cloud)], averages)."""
     from .model.loss import compute_flow_metrics
     mine = shard_indices(n_items, rank, world)
+    groups = [mine[b0:b0 + batch] for b0 in range(0, len(mine), batch)]
+    loaded = []
+
+    def batches():
+        for idxs in groups:
+            items = [get_item(i) for i in idxs]
+            pairs = []
+            for it in items:
+                s = torch.from_numpy(np.ascontiguousarray(it["src_pcd"], dtype=np.float32))
+                t = torch.from_numpy(np.ascontiguousarray(it["tgt_pcd"], dtype=np.float32))
+                if host and torch.cuda.is_available():
+                    s, t = s.pin_memory(), t.pin_memory()
+                pairs.append((s, t))
+            loaded.append((idxs, items, pairs))
+            yield pairs
+
     rows = []
-    for b0 in range(0, len(mine), batch):
-        idxs = mine[b0:b0 + batch]
-        items = [get_item(i) for i in idxs]
-        pairs = [(torch.from_numpy(np.ascontiguousarray(it["src_pcd"], dtype=np.float32)),
-                  torch.from_numpy(np.ascontiguousarray(it["tgt_pcd"], dtype=np.float32))) for it in items]
-        warped, iters, losses = registration.register_batch(pairs, seeds=[base_seed + i for i in idxs])
+    seeds = ([base_seed + i for i in idxs] for idxs in groups)
+    if hasattr(registration, "register_batches"):
+        results = registration.register_batches(batches(), seeds=seeds, host=host)
+    else:                                   # an object with only the one-batch entry point
+        results = (registration.register_batch(b, seeds=sd, host=host) for b, sd in zip(batches(), seeds))
+    for warped, iters, losses in results:
+        idxs, items, pairs = loaded.pop(0)
         for i, it, w, (src, _), ls in zip(idxs, items, warped, pairs, losses):
             row = [float(i)]
             if compute_metrics and "s2t_flow" in it:
@@ -120,7 +148,10 @@ def evaluate(registration, n_items: int, get_item: Callable[[int], dict], rank: 
                 row += [m[k] for k in METRIC_KEYS]
             else:
                 row += [float(ls[-1])] + [float("nan")] * (len(METRIC_KEYS) - 1)
+            if checksum:
+                row.append(cloud_checksum(w))
             rows.append(row)
-    rows_t = torch.tensor(rows, dtype=torch.float64).reshape(-1, 1 + len(METRIC_KEYS))
+    width = 1 + len(METRIC_KEYS) + (1 if checksum else 0)
+    rows_t = torch.tensor(rows, dtype=torch.float64).reshape(-1, width)
     allrows = gather_metric_rows(rows_t, device=gather_device)
     return allrows, average_metrics(allrows)

@@ -395,13 +395,15 @@ def optimize_pair(cfg: NDPConfig, src_pcd: torch.Tensor, tgt_pcd: torch.Tensor,
                   src_perm: Optional[torch.Tensor] = None, tgt_perm: Optional[torch.Tensor] = None,
                   landmarks: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
                   knn_mode: int = 0, knn_threads: int = 1, iters_cap: Optional[int] = None,
-                  hook=None) -> PairResult:
+                  hook=None, timers: Optional[Dict[str, float]] = None) -> PairResult:
     """Registration.optimize_deformation_pyramid, registration.py:126-262, on CPU.
 
     RNG order matches the reference: weights first (:133-140), then two randperm (:156-157).
     `init`, `src_perm`, `tgt_perm` inject them instead (teacher forcing / reproducible pairs).
     `hook(level, it, state)` is called once per iteration before the early-stop test with the
-    tensors of that iteration (used by the golden generator)."""
+    tensors of that iteration (used by the golden generator).  `timers`: a dict that receives the wall-clock
+    seconds of the reference's timer keys lvl_warp / Chamfer / backprop (registration.py:207-213, 234-238)."""
+    import time as _time
     specs = make_specs(cfg.depth, cfg.width, cfg.k0, cfg.m, cfg.rotation_format,
                        nonrigidity_est=cfg.w_reg > 0, motion=cfg.motion_type)
     if init is None:
@@ -445,9 +447,14 @@ def optimize_pair(cfg: NDPConfig, src_pcd: torch.Tensor, tgt_pcd: torch.Tensor,
                     w_ldmk, nr = layer_forward(spec, P, src_ldmk)
                     loss = torch.mean(torch.sum((w_ldmk - tgt_ldmk) ** 2, dim=-1))
             else:                                                                  # :205-213
+                t0 = _time.perf_counter()
                 s_warped, nr = layer_forward(spec, P, s_sample)
+                t1 = _time.perf_counter()
                 loss = chamfer_truncated(s_warped[None], t_sample[None], trunc=1e9,
                                          mode=knn_mode, threads=knn_threads)
+                if timers is not None:
+                    timers["lvl_warp"] = timers.get("lvl_warp", 0.0) + (t1 - t0)
+                    timers["Chamfer"] = timers.get("Chamfer", 0.0) + (_time.perf_counter() - t1)
             if level > 0 and cfg.w_reg > 0:                                        # :216-220
                 loss = loss + cfg.w_reg * bce(nr, torch.zeros_like(nr))
             last = loss.item()
@@ -457,9 +464,12 @@ def optimize_pair(cfg: NDPConfig, src_pcd: torch.Tensor, tgt_pcd: torch.Tensor,
                                      x_out=s_warped if landmarks is None or cfg.w_cd > 0 else None))
             if stop.should_stop(last):                                             # :225-232
                 break
+            t2 = _time.perf_counter()
             opt.zero_grad()                                                        # :235-237
             loss.backward()
             opt.step()
+            if timers is not None:
+                timers["backprop"] = timers.get("backprop", 0.0) + (_time.perf_counter() - t2)
             done += 1
         for v in P.values():
             v.requires_grad_(False)

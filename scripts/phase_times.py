@@ -15,7 +15,7 @@ lib = _lib.load()
 specs = O.make_specs(3, 128, -8, 1, "axis_angle")
 pairs = [make_pair(p, 8192, 8192) for p in range(B)]
 solver = ops.Solver(max_pairs=B, max_src_points=8192, max_tgt_points=8192, samples=8192, levels=1, k0=-8, depth=3, width=128,
-                    motion="SE3", rotation_format="axis_angle", iters=20, max_break_count=10**9, break_threshold_ratio=0.001, lr=0.01,
+                    motion="SE3", rotation_format="axis_angle", iters=int(sys.argv[5]) if len(sys.argv) > 5 else 20, max_break_count=10**9, break_threshold_ratio=0.001, lr=0.01,
                     streams=streams, tiles_per_bwd_cta=tpc, fwd_rounds=rounds)
 torch.manual_seed(0)
 flats = [torch.cat([O.flatten_params(s, O.init_params(s)) for s in specs]).to(dev) for _ in range(B)]
@@ -27,4 +27,8 @@ for which, name in ((0, 'fwd'), (2, 'bwd_rc (chain 0: [0..12], chain 1: [24..36]
     lib.ndp_debug_phase_times(which, buf)
     t = [int(v) for v in buf]
     t0 = t[0]
-    print(name, ' '.join(f"[{i}]{(v - t0)/1000:.2f}" for i, v in enumerate(t) if v))
+    print(name, ' '.join(f"[{i}]{(v - t0)/1000:.2f}" for i, v in enumerate(t[:62]) if v))
+    print(name.split()[0], f"CTA(0,*) duration of the last launch to finish: {t[62]/1000:.2f} us")
+    a, b = (58, 59) if which == 0 else (60, 61)
+    if t[b]:
+        print(name.split()[0], f"mean CTA duration over all {t[b]} CTAs of the run: {t[a]/t[b]/1000:.2f} us")

@@ -175,6 +175,10 @@ static inline double __shfl_xor_sync(unsigned, double v, int m) {
 static inline int __shfl_xor_sync(unsigned, int v, int m) {
     return (int)ndp_emu::warp_exchange((uint64_t)(unsigned)v, ndp_emu::ctx.lane ^ m);
 }
+static inline float __shfl_sync(unsigned, float v, int src) {
+    uint64_t r = ndp_emu::warp_exchange(__float_as_uint(v), src);
+    return __uint_as_float((unsigned)r);
+}
 static inline int __shfl_sync(unsigned, int v, int src) {
     return (int)ndp_emu::warp_exchange((uint64_t)(unsigned)v, src);
 }

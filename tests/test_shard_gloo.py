@@ -56,6 +56,42 @@ def _worker(rank, world, port, n_items, out_dir):
     dist.destroy_process_group()
 
 
+def _real_worker(rank, world, port, n_items, out_dir):
+    """The REAL Registration (fused driver, register_batches pipeline) over the CPU-emulated build of the kernel sources."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import torch.distributed as dist
+    from deformationpyramid_b200 import _lib
+    from deformationpyramid_b200.config import ndp_config
+    from deformationpyramid_b200.model.registration import Registration
+    from emu_util import emu_lib
+    _lib._LIB = emu_lib()
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    reg = Registration(ndp_config(samples=48, m=1, iters=2, device="cpu"))
+    rows, avg = shard.evaluate(reg, n_items, make_item, rank=rank, world=world, batch=2, base_seed=5, checksum=True)
+    torch.save((rows, avg), os.path.join(out_dir, f"real{world}_{rank}.pt"))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_real_registration_matches_single_process():
+    """SURVEY.md section 4, T4 on the host side: identical per-pair outputs (warped-cloud checksums bit for bit) and
+    identical gathered metrics whether 1 or 2 ranks register the pairs -- with the real Registration object."""
+    n_items = 4
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_real_worker, args=(2, _free_port(), n_items, d), nprocs=2, join=True)
+        _real_worker(0, 1, 0, n_items, d)
+        r0, a0 = torch.load(os.path.join(d, "real2_0.pt"))
+        r1, a1 = torch.load(os.path.join(d, "real2_1.pt"))
+        rs, as_ = torch.load(os.path.join(d, "real1_0.pt"))
+    assert r0.shape == (n_items, 14) and torch.equal(r0, r1)
+    assert torch.equal(r0[:, -1], rs[:, -1])                        # the warped clouds, bit for bit
+    assert torch.equal(torch.nan_to_num(r0), torch.nan_to_num(rs)) and a0.keys() == as_.keys()
+
+
 def test_shard_indices_cover_everything_once():
     for world in (1, 2, 3, 8):
         seen = sorted(i for r in range(world) for i in shard.shard_indices(11, r, world))
