@@ -140,6 +140,14 @@ __device__ __forceinline__ void ndp_mbar_wait(NdpMbar* b, unsigned parity) {
 __device__ __forceinline__ void ndp_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
 
+// Align a pointer into the dynamic shared-memory array WITHOUT a round trip through an integer (which would lose the
+// address space: every access through the result would compile to generic LD / ST instead of LDS / STS).
+#ifdef NDP_EMU
+#define NDP_SMEM_ALIGN(ptr, A) ((unsigned char*)(((uintptr_t)(ptr) + ((A) - 1)) & ~(uintptr_t)((A) - 1)))
+#else
+#define NDP_SMEM_ALIGN(ptr, A) ((ptr) + (((unsigned)(A) - (ndp_smem_u32(ptr) & ((unsigned)(A) - 1u))) & ((unsigned)(A) - 1u)))
+#endif
+
 // Warp-uniform helpers.  tcgen05.mma takes its operands from UNIFORM registers: issued from a branch the
 // compiler cannot prove single-threaded (e.g. `tid == 0`) every MMA is wrapped in a per-thread
 // "waterfall" loop (VOTEU / ELECT / 7 x R2UR / UTCHMMA / BRA, ~100 cycles).  Branching on elect.sync

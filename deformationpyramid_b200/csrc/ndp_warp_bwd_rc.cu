@@ -84,7 +84,9 @@ size_t ndp_bwd_rc_smem_bytes() { return sizeof(BwdRcSmem) + 128; }
 
 __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpBwdArgs a) {
     NDP_DYN_SMEM(smem_raw);
-    BwdRcSmem& S = *(BwdRcSmem*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    // aligned by pointer arithmetic on the shared array itself: a round trip through an integer would lose the address
+    // space and turn every shared-memory access of the kernel into a generic LD / ST
+    BwdRcSmem& S = *(BwdRcSmem*)NDP_SMEM_ALIGN(smem_raw, 128);
 
     const int tid = threadIdx.x, pair = blockIdx.y + a.pair0, tile0 = blockIdx.x * a.tpc;
     const int n = a.counts ? a.counts[pair] : a.n;
@@ -267,8 +269,12 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
             if (lane == 0) ndp_mbar_arrive(&S.bar_ready[c][sk & 1u]);
             sk += 1u;
         };
+        // one warp of the chain polls the barrier, the other seven sleep at a named barrier (a polling warp costs
+        // issue slots and shared-memory bandwidth every ~100 cycles; 16 of them were 19 % of all instructions issued)
         auto wait_mma = [&]() {
-            ndp_mbar_wait(&S.bar_mma[c], mph); mph ^= 1u;
+            if ((warp & 7) == 0) ndp_mbar_wait(&S.bar_mma[c], mph);
+            mph ^= 1u;
+            ndp_group_sync(1 + c, 256);
             ndp_tc_fence_after();
         };
         // h0 = relu(W_in e + b_in) for this thread's feature and its 32 points -> dst image (nets.py:114, 164-177);
@@ -410,7 +416,8 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
                 }
             }
         }
-        ndp_mbar_wait(&S.bar_fin, 0u);      // every product of the CTA has retired
+        if ((warp & 7) == 0) ndp_mbar_wait(&S.bar_fin, 0u);      // every product of the CTA has retired
+        ndp_group_sync(1 + c, 256);
         ndp_tc_fence_after();
         NDP_TR(10);
         // bias gradients: this thread's sums, combined below in a fixed order

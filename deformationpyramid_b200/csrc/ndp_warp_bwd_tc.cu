@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(NDP_TP) ndp_head_grad_kernel(NdpBwdArgs a) {
 
 __global__ void __launch_bounds__(NDP_BWD_TC_THREADS, 1) ndp_warp_bwd_tc_kernel(NdpBwdArgs a) {
     NDP_DYN_SMEM(smem_raw);
-    BwdTcSmem& S = *(BwdTcSmem*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    BwdTcSmem& S = *(BwdTcSmem*)NDP_SMEM_ALIGN(smem_raw, 128);
 
     // A CTA owns a.tpc consecutive tiles of one pair and accumulates their gradients in TMEM / smem:
     // one partial row per CTA (fixed grouping => deterministic), drained once.

@@ -97,7 +97,7 @@ __device__ __forceinline__ void ndp_fwd_point_tail(const NdpFwdArgs& a, const Nd
 
 __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc_kernel(NdpFwdArgs a) {
     NDP_DYN_SMEM(smem_raw);
-    FwdTcSmem& S = *(FwdTcSmem*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    FwdTcSmem& S = *(FwdTcSmem*)NDP_SMEM_ALIGN(smem_raw, 1024);
 
     const int tid = threadIdx.x, pair = blockIdx.y + a.pair0;
     const int g = tid >> 8, gt = tid & (NDP_GROUP - 1);          // tile group, thread within the group
@@ -297,7 +297,7 @@ size_t ndp_fwd_tc2_smem_bytes() { return sizeof(FwdTc2Smem) + 1024; }
 
 __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc2_kernel(NdpFwdArgs a) {
     NDP_DYN_SMEM(smem_raw);
-    FwdTc2Smem& S = *(FwdTc2Smem*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    FwdTc2Smem& S = *(FwdTc2Smem*)NDP_SMEM_ALIGN(smem_raw, 1024);
 
     const int tid = threadIdx.x, pair = blockIdx.y + a.pair0;
     const int g = tid >> 8, gt = tid & (NDP_GROUP - 1);          // tile group, thread within the group
@@ -404,7 +404,9 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc2_kernel
                 if (s == 0 && r == 0 && g == 0 && LH > 1) ndp_stage_bulk(S.W[1], wimg + NDP_SET128, NDP_SET128, &S.bar_w[1]);
                 NDP_T(8 + 4 * s);
             }
-            ndp_mbar_wait(&S.bar_mma[g], mph); mph ^= 1;
+            if (ldw) ndp_mbar_wait(&S.bar_mma[g], mph);      // one warp polls, the other seven sleep at the named barrier
+            mph ^= 1;
+            ndp_group_sync(1 + g, NDP_GROUP);
             ndp_tc_fence_after();
             NDP_T(9 + 4 * s);
             const float* bias = params + (s == 0 ? L.off_b_in : L.off_b[s - 1]);
@@ -444,7 +446,9 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc2_kernel
                               ndp_idesc_f16(128, 16, 0, 0));
             ndp_umma_commit(&S.bar_mma[g]);
         }
-        ndp_mbar_wait(&S.bar_mma[g], mph); mph ^= 1;
+        if (ldw) ndp_mbar_wait(&S.bar_mma[g], mph);      // one warp polls, the other seven sleep at the named barrier
+        mph ^= 1;
+        ndp_group_sync(1 + g, NDP_GROUP);
         ndp_tc_fence_after();
         NDP_T(60);
         ndp_fwd_point_tail(a, L, pair, tile, n, gt, HD, tlane + TM2_ACC, xs, S.hb);

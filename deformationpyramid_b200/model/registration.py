@@ -147,24 +147,45 @@ class Registration():
 
     def _prepare_batch(self, pairs, seeds, host):
         """Host-side part of register_batch: per pair the pyramid's fresh weights (reference RNG order,
-        nets.py:20-30,180-183) and the two sampling permutations (registration.py:156-157)."""
+        nets.py:20-30,180-183) and the two sampling permutations (registration.py:156-157).  With per-pair seeds
+        the pairs are independent random streams (a private torch.Generator seeded like torch.manual_seed would
+        seed the global one: bit-identical draws), so they are prepared by a small thread pool; without seeds the
+        global generator is consumed pair after pair, exactly like a sequential reference run."""
         config = self.config
         if config.w_reg > 0:
             raise NotImplementedError("register_batch covers the Chamfer-only NDP objective")
-        srcs, tgts, flats, sps, tps = [], [], [], [], []
         dev = torch.device("cuda", self.device) if isinstance(self.device, int) else torch.device(self.device)
-        for p, (src, tgt) in enumerate(pairs):
+        n = len(pairs)
+        per_pair = _params_per_pair(config)
+        pin = host and torch.cuda.is_available()
+        flat_all = torch.empty(n, per_pair, dtype=torch.float32, pin_memory=pin)      # one block: no stacking copy later
+
+        def one(p):
+            src, tgt = pairs[p]
+            gen = None
             if seeds is not None:
-                torch.manual_seed(int(seeds[p]))
-            layers_cpu = _init_flat_cpu(config)
-            sp = torch.randperm(src.shape[0])[:config.samples].to(torch.int32)
-            tp = torch.randperm(tgt.shape[0])[:config.samples].to(torch.int32)
+                gen = torch.Generator()
+                gen.manual_seed(int(seeds[p]))
+            _init_flat_cpu(config, generator=gen, out=flat_all[p])
+            sp = torch.randperm(src.shape[0], generator=gen)[:config.samples].to(torch.int32)
+            tp = torch.randperm(tgt.shape[0], generator=gen)[:config.samples].to(torch.int32)
+            return sp, tp
+
+        if seeds is not None and n > 1:
+            import os
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1, n)) as pool:
+                perms = list(pool.map(one, range(n)))
+        else:
+            perms = [one(p) for p in range(n)]
+        srcs, tgts, sps, tps = [], [], [], []
+        for (src, tgt), (sp, tp) in zip(pairs, perms):
             if host:
-                srcs.append(src.contiguous()); tgts.append(tgt.contiguous()); flats.append(layers_cpu)
-                sps.append(sp); tps.append(tp)
+                srcs.append(src.contiguous()); tgts.append(tgt.contiguous()); sps.append(sp); tps.append(tp)
             else:
                 srcs.append(src.to(dev).contiguous()); tgts.append(tgt.to(dev).contiguous())
-                flats.append(layers_cpu.to(dev)); sps.append(sp.to(dev)); tps.append(tp.to(dev))
+                sps.append(sp.to(dev)); tps.append(tp.to(dev))
+        flats = flat_all if host else list(flat_all.to(dev))
         return srcs, tgts, flats, sps, tps
 
     def _run_prepared(self, prepared, host):
@@ -172,7 +193,7 @@ class Registration():
         dev = torch.device("cuda", self.device) if isinstance(self.device, int) else torch.device(self.device)
         self.src_pcd = srcs[0] if not host else srcs[0].to(dev)   # keeps _get_solver's device key valid
         solver = self._get_solver(len(srcs), max(s.shape[0] for s in srcs), max(t.shape[0] for t in tgts))
-        warped, iters, losses = solver.register(srcs, tgts, flats, sps, tps, host=host)
+        warped, iters, losses = solver.register(srcs, tgts, flats, sps, tps, host=host, params_out=False)
         self.last_iters, self.last_losses = iters, losses
         return warped, iters, losses
 
@@ -312,14 +333,7 @@ def _feed_timer(timer, solver, prof0, iterations: int) -> None:
             timer.tictoc(key, total)
 
 
-def _init_flat_cpu(config) -> torch.Tensor:
-    """Fresh weights of a whole pyramid drawn on the CPU in the reference's RNG order, flattened
-    (level 0 first), without building nn.Modules: per level the nn.Linear default initialisation of every
-    sub-module in construction order (weight U(+-1/sqrt(fan_in)) = kaiming_uniform(a=sqrt(5)), then bias
-    U(+-1/sqrt(fan_in)); nets.py:75-101), then Xavier uniform over every weight in parameters() order
-    (nets.py:180-183).  Consumes torch's global CPU generator exactly like
-    `Deformation_Pyramid(...)` does (tests/test_cabi_and_host.py compares the two bit for bit)."""
-    import math
+def _level_linears(config):
     W = config.width
     linears = [(W, 6)] + [(W, W)] * (config.depth - 1)
     if config.motion_type in ("Sim3", "SE3"):
@@ -329,8 +343,24 @@ def _init_flat_cpu(config) -> torch.Tensor:
         if config.motion_type == "Sim3":
             linears.append((1, W))
     linears.append((3, W))
+    return linears
+
+
+def _params_per_pair(config) -> int:
+    return config.m * sum(o * i + o for o, i in _level_linears(config))
+
+
+def _init_flat_cpu(config, generator=None, out=None) -> torch.Tensor:
+    """Fresh weights of a whole pyramid drawn on the CPU in the reference's RNG order, flattened
+    (level 0 first), without building nn.Modules: per level the nn.Linear default initialisation of every
+    sub-module in construction order (weight U(+-1/sqrt(fan_in)) = kaiming_uniform(a=sqrt(5)), then bias
+    U(+-1/sqrt(fan_in)); nets.py:75-101), then Xavier uniform over every weight in parameters() order
+    (nets.py:180-183).  Consumes torch's global CPU generator exactly like `Deformation_Pyramid(...)` does
+    (tests/test_cabi_and_host.py compares the two bit for bit) -- or `generator`, a private stream."""
+    import math
+    linears = _level_linears(config)
     per_level = sum(o * i + o for o, i in linears)
-    flat = torch.empty(config.m * per_level, dtype=torch.float32)
+    flat = out if out is not None else torch.empty(config.m * per_level, dtype=torch.float32)
     off = 0
     for _ in range(config.m):
         views = []
@@ -338,12 +368,12 @@ def _init_flat_cpu(config) -> torch.Tensor:
             b = 1.0 / math.sqrt(i)
             w = flat[off:off + o * i].view(o, i); off += o * i
             bias = flat[off:off + o]; off += o
-            w.uniform_(-b, b)
-            bias.uniform_(-b, b)
+            w.uniform_(-b, b, generator=generator)
+            bias.uniform_(-b, b, generator=generator)
             views.append(w)
         for w in views:
             a = math.sqrt(3.0) * math.sqrt(2.0 / float(w.shape[0] + w.shape[1]))     # xavier_uniform_, gain 1
-            w.uniform_(-a, a)
+            w.uniform_(-a, a, generator=generator)
     return flat
 
 

@@ -248,23 +248,30 @@ class Solver:
     def register(self, src: Sequence[torch.Tensor], tgt: Sequence[torch.Tensor], params: Sequence[torch.Tensor],
                  src_perm: Optional[Sequence[torch.Tensor]] = None, tgt_perm: Optional[Sequence[torch.Tensor]] = None,
                  host: bool = False, src_samples: Optional[Sequence[int]] = None,
-                 tgt_samples: Optional[Sequence[int]] = None):
+                 tgt_samples: Optional[Sequence[int]] = None, params_out: bool = True):
         """src[p] [ns,3], tgt[p] [nt,3], params[p] flat [levels*P] (updated in place), perms int32.
         src_samples / tgt_samples: points optimised per pair (default min(samples, n)); a permutation must hold
         exactly that many indices (its length is checked here, the C ABI receives the counts explicitly).
+        host=True: `params` may also be ONE contiguous (ideally pinned) [npairs, levels*P] tensor, used in place;
+        params_out=False skips the read-back of the optimised weights (the evaluation loop never looks at them).
         host=True: all tensors are (pinned) CPU tensors and the copies run inside the call.
         Returns (warped list, iters [npairs, levels] int32, last loss [npairs, levels])."""
         lib = self.lib
         npairs = len(src)
         cuda = getattr(lib, "_ndp_requires_cuda", False)
-        for group, nm, dt in ((src, "src", torch.float32), (tgt, "tgt", torch.float32), (params, "params", torch.float32),
+        stacked = host and torch.is_tensor(params)
+        if stacked:
+            if params.ndim != 2 or params.shape[0] != npairs or not params.is_contiguous():
+                raise ValueError("a stacked params tensor must be contiguous [npairs, levels * param_count]")
+        plist = list(params) if stacked else params
+        for group, nm, dt in ((src, "src", torch.float32), (tgt, "tgt", torch.float32), (plist, "params", torch.float32),
                               (src_perm or [], "src_perm", torch.int32), (tgt_perm or [], "tgt_perm", torch.int32)):
             for t in group:
                 if t.dtype != dt or not t.is_contiguous():
                     raise ValueError(f"{nm} tensors must be contiguous {dt}")
                 if cuda and (t.is_cuda == host):
                     raise ValueError(f"{nm} must be {'CPU' if host else 'CUDA'} tensors for this entry point")
-        for p in params:
+        for p in plist:
             if p.numel() != self.params_per_pair:
                 raise ValueError("params[p] must hold levels * param_count floats")
         ns = (ctypes.c_int32 * npairs)(*[int(t.shape[0]) for t in src])
@@ -291,12 +298,13 @@ class Solver:
         a_ps, a_pt = self._ptr_array(src_perm, npairs), self._ptr_array(tgt_perm, npairs)
         a_w = self._ptr_array(warped, npairs)
         if host:
-            flat = torch.stack([p.reshape(-1) for p in params]).contiguous()
-            rc = lib.ndp_solver_register_host(self.handle, npairs, a_src, ns, a_tgt, nt, a_ps, a_pt, a_cs, a_ct, _ptr(flat), 1,
-                                              a_w, _ptr(iters), _ptr(loss), stream)
+            flat = params if stacked else torch.stack([p.reshape(-1) for p in params]).contiguous()
+            rc = lib.ndp_solver_register_host(self.handle, npairs, a_src, ns, a_tgt, nt, a_ps, a_pt, a_cs, a_ct, _ptr(flat),
+                                              1 if params_out else 0, a_w, _ptr(iters), _ptr(loss), stream)
             _lib.check(lib, rc, "ndp_solver_register_host")
-            for p, f in zip(params, flat):
-                p.copy_(f.view_as(p))
+            if params_out and not stacked:
+                for p, f in zip(params, flat):
+                    p.copy_(f.view_as(p))
         else:
             a_par = self._ptr_array(params, npairs)
             rc = lib.ndp_solver_register_device(self.handle, npairs, a_src, ns, a_tgt, nt, a_ps, a_pt, a_cs, a_ct, a_par, a_w,
