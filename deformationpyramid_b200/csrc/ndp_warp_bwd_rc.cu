@@ -36,8 +36,11 @@
 // 128 points (the old kernel: two weight sets + three activation sets).  Gradients accumulate in TMEM
 // over all tiles of the CTA (dW_1^T, dW_0^T: 128 columns each, dW_h^T, dW_in: 16 each) and leave once.
 // A 17th warp's elected lane issues every MMA and TMA copy from a static schedule, alternating between
-// the chains; chains and issuer meet only through mbarriers (operands ready: 8 warp arrivals; MMAs
-// retired: tcgen05.commit), never through a CTA-wide barrier inside the tile loop.
+// the chains.  The 16 worker warps are NOT split between the chains: all of them do chain 0's epilogue
+// (16 of its 64 columns each) while chain 1's MMAs run, then chain 1's while chain 0's next MMAs run, so an
+// epilogue takes half as long as with eight warps and the tensor pipe and the FP32 pipes stay busy
+// together.  Workers and issuer meet through mbarriers (operands ready: 16 warp arrivals; MMAs retired:
+// tcgen05.commit; one warp polls, the others sleep at a named barrier).
 // Deltas are carried multiplied by the CTA's power-of-two scale (fp16 range), as in ndp_warp_bwd_tc.cu.
 // No atomics: one partial row per CTA, fixed summation order => bit-reproducible.
 #include "ndp_kernels.h"
@@ -101,9 +104,9 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
     float* part = a.partials + (long long)pair * a.partials_stride + (long long)blockIdx.x * a.partial_pitch;
     const int warp = tid >> 5, lane = tid & 31;
     const bool issw = ndp_warp_uniform(warp) == 16;
-    // chain thread: chain c, TMEM lane quarter q (hardware: warp % 4), feature f = its TMEM lane / image row,
-    // column half ch: points [32 ch, 32 ch + 32) of the chain's 64
-    const int c = (warp >> 3) & 1, q = warp & 3, ch = (warp >> 2) & 1, f = q * 32 + lane, ct = tid & 255;
+    // worker thread: TMEM lane quarter q (hardware: warp % 4), feature f = its TMEM lane / image row, column group cg:
+    // points [16 cg, 16 cg + 16) of EACH chain's 64.  c / ct: the thread's role in the per-tile staging of the records
+    const int c = (warp >> 3) & 1, q = warp & 3, cg = (warp >> 2) & 3, f = q * 32 + lane, ct = tid & 255;
     const int RS = NDP_IMG_RS(128), CS = NDP_IMG_CS;
     NDP_TR(0);
 #ifndef NDP_EMU
@@ -114,8 +117,8 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
     if (warp == 0) ndp_tmem_alloc_warp(&S.tmem_slot, 512);
     if (issw && ndp_elect_one()) {
         ndp_mbar_init(&S.bar_w, 1); ndp_mbar_init(&S.bar_wfree, 1);
-        ndp_mbar_init(&S.bar_ready[0][0], 8); ndp_mbar_init(&S.bar_ready[0][1], 8);
-        ndp_mbar_init(&S.bar_ready[1][0], 8); ndp_mbar_init(&S.bar_ready[1][1], 8);
+        ndp_mbar_init(&S.bar_ready[0][0], 16); ndp_mbar_init(&S.bar_ready[0][1], 16);
+        ndp_mbar_init(&S.bar_ready[1][0], 16); ndp_mbar_init(&S.bar_ready[1][1], 16);
         ndp_mbar_init(&S.bar_mma[0], 1); ndp_mbar_init(&S.bar_mma[1], 1); ndp_mbar_init(&S.bar_fin, 1);
         ndp_stage_bulk(S.WB, wimg, NDP_SET128, &S.bar_w);                      // W_0 for the first F1
     }
@@ -251,42 +254,41 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
 #undef RC_RELOAD_W
       }
     } else {
-        // ================================================================ the two chains
-        unsigned mph = 0u;
-        unsigned char* const X = S.X[c];
-        unsigned char* const Y = S.Y[c];
-        const unsigned tacc = tmem + ((unsigned)(q * 32) << 16) + RC_ACC(c) + 32u * (unsigned)ch;
-        float dbs0 = 0.0f, dbs1 = 0.0f, dbs2 = 0.0f;            // sum over points of delta0 / delta1 / delta2 (this thread's feature, its column half)
-        const float (*ef)[8] = S.ef[c];
+        // ================================================================ the 16 worker warps
+        unsigned mph[2] = {0u, 0u};
+        const int col0 = 16 * cg;
+        const unsigned tlq = tmem + ((unsigned)(q * 32) << 16);
+        float dbs0 = 0.0f, dbs1 = 0.0f, dbs2 = 0.0f;            // sum over points of delta0 / delta1 / delta2 (this thread's feature, its columns, both chains)
 
-        // every chain thread announces "my part of the next batch's operands is in shared memory and I have
-        // finished reading the accumulator": one arrival per warp
-        unsigned sk = 0u;           // signals made so far: they alternate between the chain's two "ready" barriers
-        auto signal_ready = [&]() {
+        // "my part of chain cc's next operands is in shared memory and I have finished reading its accumulator": one
+        // arrival per warp; consecutive signals of a chain alternate between its two barriers (see the issuer)
+        unsigned sk[2] = {0u, 0u};
+        auto signal_ready = [&](int cc) {
             ndp_fence_proxy_async();
             ndp_tc_fence_before();
             __syncwarp();
-            if (lane == 0) ndp_mbar_arrive(&S.bar_ready[c][sk & 1u]);
-            sk += 1u;
+            if (lane == 0) ndp_mbar_arrive(&S.bar_ready[cc][sk[cc] & 1u]);
+            sk[cc] += 1u;
         };
-        // one warp of the chain polls the barrier, the other seven sleep at a named barrier (a polling warp costs
-        // issue slots and shared-memory bandwidth every ~100 cycles; 16 of them were 19 % of all instructions issued)
-        auto wait_mma = [&]() {
-            if ((warp & 7) == 0) ndp_mbar_wait(&S.bar_mma[c], mph);
-            mph ^= 1u;
-            ndp_group_sync(1 + c, 256);
+        // one warp polls the barrier, the other fifteen sleep at a named barrier (a polling warp costs issue slots and
+        // shared-memory bandwidth every ~100 cycles)
+        auto wait_mma = [&](int cc) {
+            if (warp == 0) ndp_mbar_wait(&S.bar_mma[cc], mph[cc]);
+            mph[cc] ^= 1u;
+            ndp_group_sync(1, 512);
             ndp_tc_fence_after();
         };
-        // h0 = relu(W_in e + b_in) for this thread's feature and its 32 points -> dst image (nets.py:114, 164-177);
-        // returns relu' as a bit mask (bit j = point 32 ch + j)
-        auto gen_h0 = [&](unsigned char* dst) -> unsigned {
+        // h0 = relu(W_in e + b_in) for this thread's feature and its 16 points of chain cc -> dst image (nets.py:114,
+        // 164-177); returns relu' as a bit mask (bit j = point col0 + j)
+        auto gen_h0 = [&](unsigned char* dst, int cc) -> unsigned {
             unsigned mask = 0u;
+            const float (*ef)[8] = S.ef[cc];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 2; ++k) {
                 float u[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int p = 32 * ch + 8 * k + j;
+                    const int p = col0 + 8 * k + j;
                     const float4 e0 = *(const float4*)&ef[p][0], e1 = *(const float4*)&ef[p][4];
                     float v = fmaf(w_in[0], e0.x, b_in);
                     v = fmaf(w_in[1], e0.y, v); v = fmaf(w_in[2], e0.z, v); v = fmaf(w_in[3], e0.w, v);
@@ -294,17 +296,17 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
                     mask |= (v > 0.0f ? 1u : 0u) << (8 * k + j);
                     u[j] = fmaxf(v, 0.0f);
                 }
-                ndp_store_chunk2(dst, NDP_IMG64, ndp_img_off(f, 32 * ch + 8 * k, NDP_RS64), u);
+                ndp_store_chunk2(dst, NDP_IMG64, ndp_img_off(f, col0 + 8 * k, NDP_RS64), u);
             }
             return mask;
         };
-        // forward epilogue: dst = relu(acc + bias) re-split into the image; returns relu' as a bit mask
-        auto epi_fwd = [&](unsigned char* dst, float bias) -> unsigned {
-            float v[32];
-            ndp_tmem_ld32(tacc, v);
+        // forward epilogue of chain cc: dst = relu(acc + bias) re-split into the image; returns relu' as a bit mask
+        auto epi_fwd = [&](unsigned char* dst, int cc, float bias) -> unsigned {
+            float v[16];
+            ndp_tmem_ld16(tlq + RC_ACC(cc) + (unsigned)col0, v);
             unsigned mask = 0u;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 2; ++k) {
                 float u[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -312,26 +314,27 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
                     mask |= (x > 0.0f ? 1u : 0u) << (8 * k + j);
                     u[j] = fmaxf(x, 0.0f);
                 }
-                ndp_store_chunk2(dst, NDP_IMG64, ndp_img_off(f, 32 * ch + 8 * k, NDP_RS64), u);
+                ndp_store_chunk2(dst, NDP_IMG64, ndp_img_off(f, col0 + 8 * k, NDP_RS64), u);
             }
             return mask;
         };
-        // backward epilogue: buf <- delta = acc . relu'(h) (mask from the epilogue that produced h); returns the sum over the points
-        auto epi_bwd = [&](unsigned char* buf, unsigned mask) -> float {
-            float v[32];
-            ndp_tmem_ld32(tacc, v);
-            float s = 0.0f;
+        // backward epilogue of chain cc: buf <- delta = acc . relu'(h) (mask from the epilogue that produced h); returns the sum
+        auto epi_bwd = [&](unsigned char* buf, int cc, unsigned mask) -> float {
+            float v[16];
+            ndp_tmem_ld16(tlq + RC_ACC(cc) + (unsigned)col0, v);
+            float sum = 0.0f;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 2; ++k) {
                 float u[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { u[j] = ((mask >> (8 * k + j)) & 1u) ? v[8 * k + j] : 0.0f; s += u[j]; }
-                ndp_store_chunk2(buf, NDP_IMG64, ndp_img_off(f, 32 * ch + 8 * k, NDP_RS64), u);
+                for (int j = 0; j < 8; ++j) { u[j] = ((mask >> (8 * k + j)) & 1u) ? v[8 * k + j] : 0.0f; sum += u[j]; }
+                ndp_store_chunk2(buf, NDP_IMG64, ndp_img_off(f, col0 + 8 * k, NDP_RS64), u);
             }
-            return s;
+            return sum;
         };
-        // this thread's share of the record of ndp_head_grad_kernel for one half tile: ct < 128: 8 head gradients of point
-        // ct / 2; 128 <= ct < 192: the encoding of point ct - 128.  Loaded one tile ahead (global latency off the chain).
+        // this thread's share of the record of ndp_head_grad_kernel for one tile (staging role: chain c = tid / 256,
+        // ct = tid % 256): ct < 128: 8 head gradients of point ct / 2 of half c; 128 <= ct < 192: the encoding of point
+        // ct - 128 of half c.  Loaded one tile ahead (global latency off the critical path).
         float4 r0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), r1 = r0;
         auto load_rec = [&](int t) {
             const float* rec = rec0 + (long long)t * NDP_HGREC;
@@ -347,12 +350,12 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
 
         for (int t = 0; t < ntl; ++t) {
             const int tile = tile0 + t;
-            unsigned char* const A = (t & 1) ? Y : X;       // h0 -> h2 -> delta2 -> h0 -> delta0
-            unsigned char* const B = (t & 1) ? X : Y;       // h1 -> delta1
+            unsigned char* const A[2] = {(t & 1) ? S.Y[0] : S.X[0], (t & 1) ? S.Y[1] : S.X[1]};     // h0 -> h2 -> delta2 -> h0 -> delta0
+            unsigned char* const B[2] = {(t & 1) ? S.X[0] : S.Y[0], (t & 1) ? S.X[1] : S.Y[1]};     // h1 -> delta1
             NDP_TR(2);
-            // head-gradient image and fp32 encoding of this half tile (HG: its readers, B2 of the previous tile, retired
-            // long ago; A = the previous tile's delta1, dead since B0).  The encoding IMAGE is still being read by the
-            // previous tile's Bin products: it is rewritten after the wait for F1 below, whose commit covers them.
+            // head-gradient images and fp32 encodings of both half tiles (HG: its readers, B2 of the previous tile, retired
+            // long ago; A = the previous tile's delta1, dead since B0).  The encoding IMAGES are still being read by the
+            // previous tile's Bin products: they are rewritten after the first wait for F1 below, whose commit covers them.
             if (ct < 128) {
                 float v[8] = {r0.x * dscale, r0.y * dscale, r0.z * dscale, r0.w * dscale, r1.x * dscale, r1.y * dscale, r1.z * dscale, r1.w * dscale};
                 ndp_store_chunk2(S.HG[c], NDP_IMG16H, ndp_img_off(ct >> 1, (ct & 1) * 8, NDP_RS16), v);
@@ -361,40 +364,48 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
                 *(float4*)&S.ef[c][pt][0] = r0;
                 *(float4*)&S.ef[c][pt][4] = make_float4(r1.x, r1.y, 0.0f, 0.0f);
             }
-            ndp_group_sync(1 + c, 256);     // ef complete
-            unsigned m0 = gen_h0(A);
-            signal_ready();                 // -> F1
+            ndp_group_sync(1, 512);         // ef complete
+            unsigned m0[2], m1[2], m2[2];
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) { m0[cc] = gen_h0(A[cc], cc); signal_ready(cc); }       // -> F1
             NDP_TR(3);
-            wait_mma(); NDP_TR(4);
-            if (ct >= 128 && ct < 192) {
-                float e[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, 0.0f, 0.0f};
-                ndp_store_chunk2(S.E[c], NDP_IMG16H, ndp_img_off(ct - 128, 0, NDP_RS16), e);
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                wait_mma(cc);
+                if (cc == 0) {
+                    NDP_TR(4);
+                    if (ct >= 128 && ct < 192) {
+                        float e[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, 0.0f, 0.0f};
+                        ndp_store_chunk2(S.E[c], NDP_IMG16H, ndp_img_off(ct - 128, 0, NDP_RS16), e);
+                    }
+                    if (t + 1 < ntl) load_rec(t + 1);
+                }
+                m1[cc] = epi_fwd(B[cc], cc, b_0);
+                signal_ready(cc);           // -> F2
             }
-            if (t + 1 < ntl) load_rec(t + 1);
-            const unsigned m1 = epi_fwd(B, b_0);
-            signal_ready();                 // -> F2
-            wait_mma(); NDP_TR(5);
-            const unsigned m2 = epi_fwd(A, b_1);
-            signal_ready();                 // -> B2
-            wait_mma(); NDP_TR(6);
-            dbs2 += epi_bwd(A, m2);
-            signal_ready();                 // -> B1
-            wait_mma(); NDP_TR(7);
-            dbs1 += epi_bwd(B, m1);
-            m0 = gen_h0(A);                 // delta2 is dead (B1 retired): h0 again, for dW_0 and relu'(h0)
-            signal_ready();                 // -> B0
-            wait_mma(); NDP_TR(8);
-            dbs0 += epi_bwd(A, m0);
-            signal_ready();                 // -> Bin
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) { wait_mma(cc); if (cc == 0) NDP_TR(5); m2[cc] = epi_fwd(A[cc], cc, b_1); signal_ready(cc); }       // -> B2
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) { wait_mma(cc); if (cc == 0) NDP_TR(6); dbs2 += epi_bwd(A[cc], cc, m2[cc]); signal_ready(cc); }    // -> B1
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                wait_mma(cc); if (cc == 0) NDP_TR(7);
+                dbs1 += epi_bwd(B[cc], cc, m1[cc]);
+                m0[cc] = gen_h0(A[cc], cc);     // delta2 is dead (B1 retired): h0 again, for dW_0 and relu'(h0)
+                signal_ready(cc);           // -> B0
+            }
+#pragma unroll
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) { wait_mma(cc); if (cc == 0) NDP_TR(8); dbs0 += epi_bwd(A[cc], cc, m0[cc]); signal_ready(cc); }    // -> Bin
             NDP_TR(9);
             if (a.gx) {     // optional dL/dx: + the path through the positional encoding (ndp_head_grad_kernel wrote the direct part)
-                ndp_group_sync(1 + c, 256); // delta0 complete
+                ndp_group_sync(1, 512);     // delta0 of both chains complete
                 const int p = ct >> 2, oq = ct & 3;
                 float de[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
                 const float* wi = params + L.off_w_in;
                 for (int o = 32 * oq; o < 32 * oq + 32; ++o) {
                     const unsigned off = ndp_img_off(o, p, NDP_RS64);
-                    const float d = (ndp_f16_to_f32(*(const unsigned short*)(A + off)) + ndp_f16_to_f32(*(const unsigned short*)(A + NDP_IMG64 + off))) * dinv;
+                    const float d = (ndp_f16_to_f32(*(const unsigned short*)(A[c] + off)) + ndp_f16_to_f32(*(const unsigned short*)(A[c] + NDP_IMG64 + off))) * dinv;
 #pragma unroll
                     for (int k = 0; k < 6; ++k) de[k] = fmaf(d, __ldg(wi + o * 6 + k), de[k]);
                 }
@@ -416,17 +427,16 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
                 }
             }
         }
-        if ((warp & 7) == 0) ndp_mbar_wait(&S.bar_fin, 0u);      // every product of the CTA has retired
-        ndp_group_sync(1 + c, 256);
+        if (warp == 0) ndp_mbar_wait(&S.bar_fin, 0u);      // every product of the CTA has retired
+        ndp_group_sync(1, 512);
         ndp_tc_fence_after();
         NDP_TR(10);
         // bias gradients: this thread's sums, combined below in a fixed order
         ndp_tc_fence_before();
-        ndp_group_sync(1 + c, 256);         // everybody's last products have retired: HG is free
-        float* dbred = (float*)S.HG[0];     // [chain][column half][layer][feature] = 6 KB <= 8 KB
-        dbred[((c * 2 + ch) * 3 + 0) * NDP_W + f] = dbs0;
-        dbred[((c * 2 + ch) * 3 + 1) * NDP_W + f] = dbs1;
-        dbred[((c * 2 + ch) * 3 + 2) * NDP_W + f] = dbs2;
+        float* dbred = (float*)S.HG[0];     // [column group][layer][feature] = 6 KB <= 8 KB (HG is free: every product has retired)
+        dbred[(cg * 3 + 0) * NDP_W + f] = dbs0;
+        dbred[(cg * 3 + 1) * NDP_W + f] = dbs1;
+        dbred[(cg * 3 + 2) * NDP_W + f] = dbs2;
     }
     ndp_tc_fence_before();
     __syncthreads();            // every MMA of the CTA has retired (each chain waited for its last commit), dbred complete
@@ -462,13 +472,13 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
             float* dst = part + L.off_w_in + f * 6;
 #pragma unroll
             for (int k = 0; k < 6; ++k) dst[k] = h[k] * dinv;
-        } else if (cq == 2) {   // bias gradients: column halves, then chains, in fixed order
+        } else if (cq == 2) {   // bias gradients: the four column groups in fixed order
             const float* dbred = (const float*)S.HG[0];
             float tot[3];
 #pragma unroll
             for (int l = 0; l < 3; ++l)
-                tot[l] = (dbred[((0 * 2 + 0) * 3 + l) * NDP_W + f] + dbred[((0 * 2 + 1) * 3 + l) * NDP_W + f]) +
-                         (dbred[((1 * 2 + 0) * 3 + l) * NDP_W + f] + dbred[((1 * 2 + 1) * 3 + l) * NDP_W + f]);
+                tot[l] = (dbred[(0 * 3 + l) * NDP_W + f] + dbred[(1 * 3 + l) * NDP_W + f]) +
+                         (dbred[(2 * 3 + l) * NDP_W + f] + dbred[(3 * 3 + l) * NDP_W + f]);
             part[L.off_b_in + f] = tot[0] * dinv;
             part[L.off_b[0] + f] = tot[1] * dinv;
             part[L.off_b[1] + f] = tot[2] * dinv;
