@@ -44,6 +44,7 @@ sys.stdout = os.fdopen(os.dup(2), "w", buffering=1)
 import torch  # noqa: E402
 
 METRIC = "registered point-cloud pairs/sec (8192-pt, 9-level NDP, 500 iters/level)"
+P_LEVEL = 34694          # parameters of one SE3 / axis-angle level
 UNIT = "pairs/s"
 
 
@@ -66,6 +67,8 @@ def parse():
     ap.add_argument("--cpu-modeb-pairs", type=int, default=3, help="pairs the CPU oracle registers in full in mode B")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mode-b", action="store_true")
+    ap.add_argument("--no-config5", action="store_true", help="skip the config-5-shaped leg (30 000-pt clouds, samples=2000, mode B)")
+    ap.add_argument("--config5-batches", type=int, default=4)
     ap.add_argument("--nn-mode", type=int, default=0, help="0: exact culled NN search (default), 1: brute force")
     ap.add_argument("--mlp", default="tensor", choices=["tensor", "fp32"], help="tcgen05 tensor cores (default) or FP32 pipes")
     ap.add_argument("--tpc", type=int, default=None, help="override: tiles per backward CTA")
@@ -375,21 +378,60 @@ def main():
                        gather_device=dev, host=True)
         barrier()
         tb0 = time.perf_counter()
-        shard.evaluate(regb, 2 * B * world, get_item, rank=rank, world=world, batch=B, base_seed=0, compute_metrics=False,
+        shard.evaluate(regb, 4 * B * world, get_item, rank=rank, world=world, batch=B, base_seed=0, compute_metrics=False,
                        gather_device=dev, host=True)
         barrier()
         tb = torch.tensor([ms_b / 1e3, time.perf_counter() - tb0], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(tb, op=dist.ReduceOp.MAX)
-        mode_b = {"value": B * world / float(tb[0]), "e2e": 2 * B * world / float(tb[1]), "unit": UNIT,
+        mode_b = {"value": B * world / float(tb[0]), "e2e": 4 * B * world / float(tb[1]), "unit": UNIT,
                   "adam_steps_per_pair_mean": float(its_b.sum()) / B,
                   "adam_steps_first_pairs": [int(v) for v in its_b.sum(dim=1)[:a.cpu_modeb_pairs]],
                   "note": "same pairs, weights and permutations as mode A; shipped thresholds max_break_count=15, "
-                          "break_threshold_ratio=0.001 (config/NDP.yaml:10-11); e2e over two batches per rank"}
+                          "break_threshold_ratio=0.001 (config/NDP.yaml:10-11); e2e over four batches per rank"}
+
+    # ---- config-5-shaped leg (BASELINE.json configs[4]; eval_nolearned.py:70-143 with config/NDP.yaml as shipped): clouds of
+    #      30 000 points (the cap of _4dmatch.py:30), samples = 2000 (15.6 ragged tiles), 9 levels, <= 500 iterations per level
+    #      with the shipped early-stop thresholds, through shard.evaluate with host buffers; the 4DMatch data is not
+    #      available offline, the clouds are synthetic ------------------------------------------------------------------
+    config5 = None
+    if a.mode == "fixed" and not a.no_config5:
+        NP5, B5 = 30000, B
+        cfg5 = ndp_config(device=local, **prof)                      # NDP.yaml defaults: samples 2000, m 9, iters 500, early stop on
+        reg5 = Registration(cfg5)
+        pairs5 = {}
+
+        def get_item5(i):
+            g = i % (B5 * world)
+            if g not in pairs5:
+                s, t = make_pair(5000 + g, NP5, NP5)
+                pairs5[g] = dict(src_pcd=s.numpy(), tgt_pcd=t.numpy())
+            return pairs5[g]
+
+        for i in shard.shard_indices(B5 * world, rank, world):
+            get_item5(i)
+        shard.evaluate(reg5, B5 * world, get_item5, rank=rank, world=world, batch=B5, base_seed=0, compute_metrics=False,
+                       gather_device=dev, host=True)
+        barrier()
+        t50 = time.perf_counter()
+        nb5 = a.config5_batches
+        shard.evaluate(reg5, nb5 * B5 * world, get_item5, rank=rank, world=world, batch=B5, base_seed=0, compute_metrics=False,
+                       gather_device=dev, host=True)
+        barrier()
+        t5 = torch.tensor([time.perf_counter() - t50], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+        config5 = {"workload": f"synthetic {NP5}-pt clouds, config/NDP.yaml as shipped (samples=2000, m=9, iters<=500, max_break_count=15), "
+                               f"{B5} pairs per batch per GPU, {nb5} batches per rank",
+                   "e2e": {"value": nb5 * B5 * world / float(t5[0]), "unit": UNIT,
+                           "h2d_bytes_per_batch": B5 * (2 * NP5 * 12 + 2 * 2000 * 4 + a.levels * P_LEVEL * 4),
+                           "d2h_bytes_per_batch": B5 * (NP5 * 12 + a.levels * 8)},
+                   "adam_steps_per_pair_mean": float(reg5.last_iters.sum()) / B5,
+                   "api": "shard.evaluate(Registration, host=True)"}
 
     if rank == 0:
         pk, pk_src = peaks()
-        P = 34694
+        P = P_LEVEL
         iters_done = int(its.sum()) // B if its is not None else a.levels * a.iters
         n_s = max(ns1 - ns0, 1)
         shares = {k: (prof1[k] - prof0[k]) / n_s for k in prof1}      # ms per sampled launch (prof_pairs pairs each)
@@ -467,7 +509,7 @@ def main():
                                     "note": "exact NN search is ALU-issue bound, not HBM bound (SURVEY.md 8d): see nn_search_work"},
                "nn_search_work": nn_work,
                "kernel_ms_per_launch": shares, "pairs_per_launch": prof_pairs,
-               "rank_independence": t4, "mode_b": mode_b}
+               "rank_independence": t4, "mode_b": mode_b, "config5": config5}
         if not a.no_cpu_baseline and world == 1:
             from oracle import ndp_oracle as O
             torch.set_num_threads(os.cpu_count() or 1)
