@@ -183,7 +183,7 @@ def execution_profile(npairs: int) -> dict:
     library's latency-oriented defaults below.  Only regroups work; the gradient summation grouping follows
     tiles_per_bwd_cta, so a pair's result is bit-reproducible for a given profile."""
     if npairs >= 24:
-        return dict(tiles_per_bwd_cta=8, fwd_rounds=2, streams=4)
+        return dict(tiles_per_bwd_cta=8, fwd_rounds=4, streams=4)
     return dict(tiles_per_bwd_cta=0, fwd_rounds=0, streams=0)
 
 

@@ -14,9 +14,9 @@ import shutil
 import subprocess
 import sys
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 pairs = int(sys.argv[2]) if len(sys.argv) > 2 else 32
-groups = int(sys.argv[3]) if len(sys.argv) > 3 else 4          # stream groups of the solver (NDP_SOLVER_STREAMS)
+groups = int(sys.argv[3]) if len(sys.argv) > 3 else 4          # stream groups of the solver (ndp_solver_cfg::streams)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 os.makedirs(PROF, exist_ok=True)
@@ -86,7 +86,7 @@ if os.path.exists(ll):
             line = f"{n[:60]:60s} n={len(x):5d} mean={sum(x) / len(x):9.2f} us  share={100 * sum(x) / tot:5.1f}%"
             print(line)
             f.write(line + "\n")
-for name in ("bench_default.json", "bench_reference.json", "bench_pairs8.json", "bench_pairs16.json", "bench_fp32pipes_pairs16.json",
+for name in ("bench_default.json", "bench_reference.json", "bench_pairs8.json", "bench_pairs16.json", "bench_fp32pipes_pairs16.json", "bench_2gpu.json",
              "smoke.log", "pytest_gpu.log", "sanitizer_memcheck.log", "sanitizer_racecheck.log", "sanitizer_synccheck.log", "host.txt", "nvidia-smi.txt"):
     src = os.path.join(OUT, name)
     if os.path.exists(src):
