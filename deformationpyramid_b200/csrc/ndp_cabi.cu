@@ -4,6 +4,7 @@
 #include "ndp_kernels.h"
 #include "ndp_tc.cuh"
 
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -283,7 +284,7 @@ struct ndp_solver {
     int npad = 0, S128 = 0, nboxes = 0, mlp_mode = 0;
     int device = 0;                     // the CUDA device the solver's buffers, streams and events live on
     int tpc = 0, fwd_rounds = 0;        // work grouping of the tensor-core kernels (0 = automatic)
-    unsigned long long* nnstats = nullptr;   // [2] device counters of the culled search (profile_every > 0)
+    unsigned long long* nnstats = nullptr;   // [4] device counters of the culled search (profile_every > 0)
     int last_npairs = 0, last_cur = 0;  // the last register call: pairs, and which sample buffer holds the last warped samples
     long long act_pair = 0;
     double* blocksums = nullptr;
@@ -302,6 +303,8 @@ struct ndp_solver {
     int prof_pairs = 0;                 // pairs per profiled launch
     // the batch is split into two halves that run on two streams, so that one half's small kernels
     // (NN search, Chamfer epilogue, Adam) fill the SM time the other half's tensor-core CTAs leave idle
+    int dbg_nn = 0;                     // NDP_DEBUG_NN, see NdpPrunedArgs::dbg
+    int dbg_skip = 0;                   // NDP_DEBUG_SKIP (read once at creation; measurement aid only, results are garbage): bit 0 forward, 1 NN search, 2 backward, 3 Adam
     int nstreams = 1;                   // stream groups (1..NDP_MAX_STREAMS), env NDP_SOLVER_STREAMS, default 4
     cudaStream_t st_extra[NDP_MAX_STREAMS - 1] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[NDP_MAX_STREAMS - 1] = {};
@@ -387,12 +390,14 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
         DA(orig_s, B * S); DA(orig_t, B * S); DA(inv_s, B * S); DA(inv_t, B * S); DA(prev_x, B * S); DA(prev_y, B * S);
     }
     if (c->record_loss) DA(loss_hist, B * c->levels * (long long)c->iters);
-    if (c->profile_every > 0 && c->nn_mode == 0) DA(nnstats, 2);
+    if (c->profile_every > 0 && c->nn_mode == 0) DA(nnstats, 4);
 #undef DA
     if (!e && cudaMallocHost((void**)&s->h_state, sizeof(NdpPairState) * B) != cudaSuccess) e = fail(NDP_E_NOMEM, "cudaMallocHost failed");
     if (!e && cudaMallocHost((void**)&s->h_counts, sizeof(int) * B * 4) != cudaSuccess) e = fail(NDP_E_NOMEM, "cudaMallocHost failed");
     if (!e && cudaMemset(s->counters, 0, sizeof(int) * B) != cudaSuccess) e = fail(NDP_E_CUDA, "cudaMemset failed");
     if (!e) {
+        if (const char* dv = getenv("NDP_DEBUG_SKIP")) s->dbg_skip = atoi(dv);
+        if (const char* dv = getenv("NDP_DEBUG_NN")) s->dbg_nn = atoi(dv);
         const int want = c->streams > 0 ? c->streams : 4;
         s->nstreams = (int)(B < want ? B : want);
         if (s->nstreams > 1 && cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess)
@@ -403,7 +408,7 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
                 e = fail(NDP_E_CUDA, "stream / event creation failed");
     }
     if (!e && cudaMemset(s->gacc, 0, 8 * B * S * 3) != cudaSuccess) e = fail(NDP_E_CUDA, "cudaMemset failed");
-    if (!e && s->nnstats && cudaMemset(s->nnstats, 0, 16) != cudaSuccess) e = fail(NDP_E_CUDA, "cudaMemset failed");
+    if (!e && s->nnstats && cudaMemset(s->nnstats, 0, 32) != cudaSuccess) e = fail(NDP_E_CUDA, "cudaMemset failed");
     if (e) { ndp_solver_destroy(s); return e; }
     *out = s;
     return NDP_OK;
@@ -412,13 +417,15 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
 extern "C" int64_t ndp_solver_params_per_pair(const ndp_solver* s) { return s ? (int64_t)s->cfg.levels * s->P : -1; }
 extern "C" int64_t ndp_solver_launch_count(const ndp_solver* s) { return s ? s->launches : -1; }
 extern "C" int32_t ndp_solver_profiled_pairs(const ndp_solver* s) { return s ? s->prof_pairs : -1; }
-extern "C" int ndp_solver_nn_stats(const ndp_solver* s, int64_t* pair_evals, int64_t* query_blocks) {
+extern "C" int ndp_solver_nn_stats(const ndp_solver* s, int64_t* pair_evals, int64_t* query_blocks, int64_t* exact_evals, int64_t* max_blocks) {
     if (!s || !pair_evals || !query_blocks) return fail(NDP_E_INVALID, "NULL argument");
     if (!s->nnstats) return fail(NDP_E_INVALID, "the solver was created without profile_every > 0 (or runs the brute-force search)");
     DeviceGuard guard(s->device);
-    unsigned long long h[2] = {0, 0};
-    CK(cudaMemcpy(h, s->nnstats, 16, cudaMemcpyDeviceToHost));
+    unsigned long long h[4] = {0, 0, 0, 0};
+    CK(cudaMemcpy(h, s->nnstats, 32, cudaMemcpyDeviceToHost));
     *pair_evals = (int64_t)h[0]; *query_blocks = (int64_t)h[1];
+    if (exact_evals) *exact_evals = (int64_t)h[2];
+    if (max_blocks) *max_blocks = (int64_t)h[3];
     return NDP_OK;
 }
 extern "C" int ndp_solver_profile(const ndp_solver* s, double* ms, int64_t* samples) {
@@ -503,7 +510,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         pn.x4 = s->x4; pn.y4 = s->t4; pn.p4_stride = s->S128; pn.xbox = s->xbox; pn.ybox = s->tbox; pn.box_stride = s->nboxes;
         pn.prev_x = s->prev_x; pn.prev_y = s->prev_y; pn.prev_stride = S; pn.inv_x = s->inv_s; pn.inv_y = s->inv_t; pn.inv_stride = S; pn.n = s->S; pn.ncounts = s->ncount;
         pn.m = s->S; pn.mcounts = s->mcount; pn.part = s->nnpart; pn.part_pair_stride = ch.nn.part_pair_stride;
-        pn.qpitch = s->plan.qpitch; pn.state = s->state; pn.npairs = npairs; pn.stats = s->nnstats;
+        pn.qpitch = s->plan.qpitch; pn.state = s->state; pn.npairs = npairs; pn.stats = s->nnstats; pn.dbg = s->dbg_nn;
         ch.trunc = c.trunc; ch.gx = s->gx; ch.gx_stride = S * 3; ch.gacc = s->gacc; ch.gacc_stride = S * 3;
         ch.d2x = nullptr; ch.idxx = nullptr; ch.nx_stride = 0; ch.d2y = nullptr; ch.idxy = nullptr; ch.ny_stride = 0;
         ch.blocksums = s->blocksums; ch.blocks_pitch = s->plan.blocks; ch.counters = s->counters; ch.loss_out = s->loss;
@@ -571,15 +578,18 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
                 f.pair0 = pn.pair0 = ch.nn.pair0 = b.pair0 = ad.pair0 = gfirst[g];
                 f.npairs = pn.npairs = ch.nn.npairs = b.npairs = ad.npairs = gcount[g];
                 if (pg) CK(cudaEventRecord(ev[0], q));
+                if (s->dbg_skip & 1) {} else
                 if (s->mlp_mode == 0) ndp_launch_fwd_tc(f, q); else ndp_launch_fwd(f, q);
                 if (pg) CK(cudaEventRecord(ev[1], q));
+                if (s->dbg_skip & 2) {} else
                 if (culled) { pn.fuse = &ch; ndp_launch_nn_pruned(pn, q); } else ndp_launch_nn(ch.nn, q);   // culled: search + Chamfer epilogue in one launch
                 if (pg) CK(cudaEventRecord(ev[2], q));
                 if (!culled) ndp_launch_chamfer_reduce(ch, q);
                 if (pg) CK(cudaEventRecord(ev[3], q));
+                if (s->dbg_skip & 4) {} else
                 if (s->mlp_mode == 0) ndp_launch_bwd_tc(b, q); else ndp_launch_bwd(b, q);
                 if (pg) CK(cudaEventRecord(ev[4], q));
-                ndp_launch_adam(ad, q);
+                if (!(s->dbg_skip & 8)) ndp_launch_adam(ad, q);
                 if (pg) CK(cudaEventRecord(ev[5], q));
                 s->launches += ((s->mlp_mode == 0) ? 6 : 5) - (culled ? 1 : 0);
             }

@@ -15,6 +15,28 @@
 
 #include "ndp_math.cuh"
 
+// ---- packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2): two values per instruction ----------------
+// Each component is the same IEEE round-to-nearest operation as the scalar __fadd_rn / __fmul_rn / __fmaf_rn.
+#ifdef NDP_EMU
+struct NdpF2 { float a, b; };
+static inline NdpF2 ndp_f2_make(float a, float b) { return NdpF2{a, b}; }
+static inline NdpF2 ndp_f2_bcast(float v) { return NdpF2{v, v}; }
+static inline void ndp_f2_get(NdpF2 v, float& a, float& b) { a = v.a; b = v.b; }
+static inline NdpF2 ndp_f2_add(NdpF2 x, NdpF2 y) { return NdpF2{__fadd_rn(x.a, y.a), __fadd_rn(x.b, y.b)}; }
+static inline NdpF2 ndp_f2_sub(NdpF2 x, NdpF2 y) { return NdpF2{__fsub_rn(x.a, y.a), __fsub_rn(x.b, y.b)}; }
+static inline NdpF2 ndp_f2_mul(NdpF2 x, NdpF2 y) { return NdpF2{__fmul_rn(x.a, y.a), __fmul_rn(x.b, y.b)}; }
+static inline NdpF2 ndp_f2_fma(NdpF2 x, NdpF2 y, NdpF2 z) { return NdpF2{__fmaf_rn(x.a, y.a, z.a), __fmaf_rn(x.b, y.b, z.b)}; }
+#else
+typedef unsigned long long NdpF2;
+__device__ __forceinline__ NdpF2 ndp_f2_make(float a, float b) { NdpF2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ NdpF2 ndp_f2_bcast(float v) { return ndp_f2_make(v, v); }
+__device__ __forceinline__ void ndp_f2_get(NdpF2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ NdpF2 ndp_f2_add(NdpF2 x, NdpF2 y) { NdpF2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y)); return r; }
+__device__ __forceinline__ NdpF2 ndp_f2_sub(NdpF2 x, NdpF2 y) { NdpF2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y)); return r; }
+__device__ __forceinline__ NdpF2 ndp_f2_mul(NdpF2 x, NdpF2 y) { NdpF2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y)); return r; }
+__device__ __forceinline__ NdpF2 ndp_f2_fma(NdpF2 x, NdpF2 y, NdpF2 z) { NdpF2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(x), "l"(y), "l"(z)); return r; }
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // Tile constants.  The MLP kernels are specialised for the reference's hidden width 128
 // (config/NDP.yaml:26, shape_transfer.py:43); other widths are rejected at the C-ABI.

@@ -14,6 +14,13 @@
 //     minimum of some lane.  Box distances are evaluated with the same monotone fp32 expression
 //     (componentwise gaps -> fma chain), so in floating point lb(box) <= d(q, t) for every t in the
 //     box and culling never discards a candidate, not even an exact tie.
+//   * inside a block the points are ordered by ORIGINAL sample index, so the first minimum of a scan in block order is
+//     the one the reference's tie rule picks: a block is scanned with a plain "d < best" (distance + position, no index
+//     in the loop) and only its winner is merged into the running (distance, original index) key;
+//   * the scan is bound by the shared-memory pipe, not by the FP32 pipes: every candidate is broadcast to the 32 lanes
+//     and an LDS.128 occupies that pipe for four cycles whether or not the lanes read the same address.  The staged
+//     block therefore holds coordinates only (12 bytes per candidate, negated and pair-interleaved for the packed
+//     FADD2 / FMUL2 / FFMA2), and the index is fetched once per block.
 // Reference semantics: pytorch3d knn_points(K=1) as called at model/loss.py:177-178.
 #include "ndp_kernels.h"
 
@@ -31,6 +38,12 @@ __device__ __forceinline__ float ndp_gap(float alo, float ahi, float blo, float 
 }
 __device__ __forceinline__ float ndp_sq3(float gx, float gy, float gz) {
     return __fmaf_rn(gz, gz, __fmaf_rn(gy, gy, __fmul_rn(gx, gx)));
+}
+// squared distances of one query to a staged candidate pair (nx = (-x0, -x1), ...): each component is the same IEEE
+// operation sequence as ndp_sqdist3 (q - t == q + (-t) exactly), so the results are bit-identical to it
+__device__ __forceinline__ void ndp_sqdist3_pair(NdpF2 qx, NdpF2 qy, NdpF2 qz, NdpF2 nx, NdpF2 ny, NdpF2 nz, float& d0, float& d1) {
+    const NdpF2 dx = ndp_f2_add(qx, nx), dy = ndp_f2_add(qy, ny), dz = ndp_f2_add(qz, nz);
+    ndp_f2_get(ndp_f2_fma(dz, dz, ndp_f2_fma(dy, dy, ndp_f2_mul(dx, dx))), d0, d1);
 }
 
 // ---- cloud bounds (one CTA per (pair, cloud)); deterministic min/max tree -----------------------
@@ -118,8 +131,15 @@ __global__ void __launch_bounds__(256) ndp_apply_order_kernel(NdpSortArgs a) {
     const float INF = __int_as_float(0x7f800000);
     float x = INF, y = INF, z = INF;
     int o = 0x7fffffff;
+    if (i < n) o = (int)(unsigned)(keys[i] & 0xffffffffull);
+    // inside the 32-point block: ascending original index (bitonic network over the warp; padded slots stay last)
+    for (int k = 2; k <= 32; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int other = __shfl_xor_sync(0xffffffffu, o, j);
+            const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+            o = (lower == up) ? (o < other ? o : other) : (o < other ? other : o);
+        }
     if (i < n) {
-        o = (int)(unsigned)(keys[i] & 0xffffffffull);
         x = P[(long long)o * 3]; y = P[(long long)o * 3 + 1]; z = P[(long long)o * 3 + 2];
         out[(long long)i * 3] = x; out[(long long)i * 3 + 1] = y; out[(long long)i * 3 + 2] = z;
         (which ? a.tgt_orig : a.src_orig)[(long long)pair * a.orig_stride + i] = o;
@@ -172,7 +192,8 @@ struct NdpFuseArgs {             // the Chamfer epilogue's arguments (subset of 
 
 template <bool FUSE>
 __global__ void __launch_bounds__(NDP_PN_WARPS * 32, 12) ndp_nn_pruned_kernel(NdpPrunedArgs a, NdpFuseArgs fz) {
-    __shared__ __align__(16) float4 stage[NDP_PN_WARPS][32];
+    __shared__ __align__(16) float stage[NDP_PN_WARPS][16][6];   // per warp: 16 candidate pairs (-x0, -x1, -y0, -y1, -z0, -z1)
+    __shared__ int stage_o[NDP_PN_WARPS][32];                    // their original sample indices
     __shared__ double wsum[NDP_PN_WARPS];
     __shared__ int is_last;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -211,8 +232,9 @@ __global__ void __launch_bounds__(NDP_PN_WARPS * 32, 12) ndp_nn_pruned_kernel(Nd
     for (int s = 16; s > 0; s >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, s));
     const float4 qlo = *(const float4*)qbox, qhi = *(const float4*)(qbox + 4);
     int scanned = 0;
+    const NdpF2 qx2 = ndp_f2_bcast(qq.x), qy2 = ndp_f2_bcast(qq.y), qz2 = ndp_f2_bcast(qq.z);
 
-    for (int base = 0; base < ntblk; base += 32) {
+    for (int base = 0; base < ntblk && !(a.dbg & 1); base += 32) {
         const int blk = base + lane;
         bool need = false;
         if (blk < ntblk) {
@@ -235,22 +257,37 @@ __global__ void __launch_bounds__(NDP_PN_WARPS * 32, 12) ndp_nn_pruned_kernel(Nd
             if (!__any_sync(0xffffffffu, live && lbq <= best)) continue;
             ++scanned;
             const int tj = tb * 32 + lane;
-            stage[w][lane] = (tj < nt) ? T4[tj] : make_float4(INF, INF, INF, __int_as_float(0x7fffffff));
-            __syncwarp();
-#pragma unroll 8
-            for (int j = 0; j < 32; ++j) {
-                const float4 t = stage[w][j];
-                const float d = ndp_sqdist3(qq.x, qq.y, qq.z, t.x, t.y, t.z);
-                const unsigned long long k = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(t.w);
-                bestk = k < bestk ? k : bestk;
+            {   // stage the block: negated, pair-interleaved coordinates (two candidates per packed FP32 instruction)
+                const float4 t = (tj < nt) ? T4[tj] : make_float4(INF, INF, INF, __int_as_float(0x7fffffff));
+                float* sp = &stage[w][lane >> 1][lane & 1];
+                sp[0] = -t.x; sp[2] = -t.y; sp[4] = -t.z;
+                stage_o[w][lane] = __float_as_int(t.w);
             }
-            best = __uint_as_float((unsigned)(bestk >> 32));
+            __syncwarp();
+            // block-local minimum and its position; strict '<' in block order = lowest original index among equal distances
+            float bd = INF;
+            int bp = 0;
+#pragma unroll 8
+            for (int p = 0; p < 16; ++p) {
+                const float4 g = *(const float4*)&stage[w][p][0];
+                const float2 z = *(const float2*)&stage[w][p][4];
+                float d0, d1;
+                ndp_sqdist3_pair(qx2, qy2, qz2, ndp_f2_make(g.x, g.y), ndp_f2_make(g.z, g.w), ndp_f2_make(z.x, z.y), d0, d1);
+                if (d0 < bd) { bd = d0; bp = 2 * p; }
+                if (d1 < bd) { bd = d1; bp = 2 * p + 1; }
+            }
+            if (bd < INF) {     // (candidates at infinite distance never replace the seed; NaN distances never compare below)
+                const unsigned long long k = ((unsigned long long)__float_as_uint(bd) << 32) | (unsigned)stage_o[w][bp];
+                bestk = k < bestk ? k : bestk;
+                best = __uint_as_float((unsigned)(bestk >> 32));
+            }
             __syncwarp();
         }
     }
     if (a.stats && lane == 0) {
         atomicAdd(a.stats, (unsigned long long)scanned * 1024ull);
         atomicAdd(a.stats + 1, 1ull);
+        atomicMax(a.stats + 3, (unsigned long long)scanned);                     // most blocks any warp scanned
     }
     if (live) {
         const int bo = (int)(unsigned)(bestk & 0xffffffffull);
@@ -259,7 +296,7 @@ __global__ void __launch_bounds__(NDP_PN_WARPS * 32, 12) ndp_nn_pruned_kernel(Nd
         if (!(qq.x == qq.x) || !(qq.y == qq.y) || !(qq.z == qq.z)) best = __int_as_float(0x7fc00000);
         a.part[(long long)pair * a.part_pair_stride + (long long)dir * a.qpitch + q] = make_float2(best, __int_as_float(bj));
         prev[q] = bj;
-        if (FUSE) {
+        if (FUSE && !(a.dbg & 2)) {
             // Chamfer epilogue (ndp_chamfer.cu: ndp_chamfer_reduce_kernel), same expressions on the same coordinates
             if (dir == 0) {     // x -> y: point q owns its gradient slot
                 float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;

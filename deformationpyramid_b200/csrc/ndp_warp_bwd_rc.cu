@@ -72,7 +72,7 @@ struct BwdRcSmem {
     unsigned char HG[2][2 * NDP_IMG16H];   // per chain [64 points][16]: scaled mlp_scale * dL/dz; at the very end: bias-gradient scratch
     unsigned char E[2][2 * NDP_IMG16H];    // per chain [64 points][16]: cols 0..5 positional encoding, rest 0
     unsigned char HWT[2 * NDP_IMG16F];     // [128 features][16 head rows]: head weights transposed, rows >= head_dim zero
-    float ef[2][NDP_HP][8];                // per chain: fp32 positional encoding (h0 on the CUDA cores)
+    float ef[2][6][NDP_HP];                // per chain: fp32 positional encoding, one row per component (h0 on the CUDA cores)
     NdpMbar bar_w, bar_wfree, bar_ready[2][2], bar_mma[2], bar_fin;   // ready: [chain][signal parity]
     unsigned tmem_slot, pad[3];
 };
@@ -85,6 +85,7 @@ size_t ndp_bwd_rc_smem_bytes() { return sizeof(BwdRcSmem) + 128; }
 #define RC_DWH 384u                        // dW_h^T [128 i][16 head rows]
 #define RC_DWIN 400u                       // dW_in  [128 o][16] (cols 0..5)
 
+// 544 threads = 17 warps are allocated as 20 (groups of four): 65 536 / 640 = 102 -> 96 registers per thread is the ceiling.
 __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpBwdArgs a) {
     NDP_DYN_SMEM(smem_raw);
     // aligned by pointer arithmetic on the shared array itself: a round trip through an integer would lose the address
@@ -122,7 +123,11 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
         ndp_mbar_init(&S.bar_mma[0], 1); ndp_mbar_init(&S.bar_mma[1], 1); ndp_mbar_init(&S.bar_fin, 1);
         ndp_stage_bulk(S.WB, wimg, NDP_SET128, &S.bar_w);                      // W_0 for the first F1
     }
-    float w_in[6], b_in = 0.0f, b_0 = 0.0f, b_1 = 0.0f;
+    // h0 role of a worker thread (gen_h0 below): 8 consecutive points (group hp8) of TWO features fA, fB = fA + 8.  All lanes
+    // of a warp share hp8 (their encoding loads are one broadcast per warp) and the 8 lanes of a quarter warp hold 8
+    // consecutive features, so the 16-byte image stores of a quarter warp fill all 32 banks.
+    const int hp8 = (tid >> 6) & 7, fA = ((tid & 63) >> 3) * 16 + (tid & 7), fB = fA + 8;
+    float wA[6], wB[6], bA = 0.0f, bB = 0.0f, b_0 = 0.0f, b_1 = 0.0f;
     if (!issw) {
         // transposed head weight image: row i = ct & 127, 8-column chunk ct >> 7 (head rows 8 chunk .. 8 chunk + 7)
         const int i = ct & 127, c8 = ct >> 7;
@@ -137,8 +142,9 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
             if (ct < 64) ndp_store_chunk2(S.E[c], NDP_IMG16H, ndp_img_off(ct, 8, NDP_RS16), z8);
         }
 #pragma unroll
-        for (int k = 0; k < 6; ++k) w_in[k] = __ldg(params + L.off_w_in + f * 6 + k);
-        b_in = __ldg(params + L.off_b_in + f); b_0 = __ldg(params + L.off_b[0] + f); b_1 = __ldg(params + L.off_b[1] + f);
+        for (int k = 0; k < 6; ++k) { wA[k] = __ldg(params + L.off_w_in + fA * 6 + k); wB[k] = __ldg(params + L.off_w_in + fB * 6 + k); }
+        bA = __ldg(params + L.off_b_in + fA); bB = __ldg(params + L.off_b_in + fB);
+        b_0 = __ldg(params + L.off_b[0] + f); b_1 = __ldg(params + L.off_b[1] + f);
     }
     // the CTA's delta scale: an exact power of two that brings the largest head gradient of its tiles
     // into [1, 2) (fp16 operand range, see ndp_tc.cuh); undone when the gradients leave TMEM
@@ -278,27 +284,36 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
             ndp_group_sync(1, 512);
             ndp_tc_fence_after();
         };
-        // h0 = relu(W_in e + b_in) for this thread's feature and its 16 points of chain cc -> dst image (nets.py:114,
-        // 164-177); returns relu' as a bit mask (bit j = point col0 + j)
-        auto gen_h0 = [&](unsigned char* dst, int cc) -> unsigned {
-            unsigned mask = 0u;
-            const float (*ef)[8] = S.ef[cc];
+        // h0 = relu(W_in e + b_in) (nets.py:114, 164-177) for this thread's two features and its 8 points of chain cc -> dst
+        // image.  The encodings are the same for every lane, and a broadcast LDS.128 still costs four cycles of the SM's
+        // shared-memory pipe (the resource this kernel is bound by, next to the MMAs' operand fetch): two features x eight
+        // points per thread need 12 such loads per warp where one feature x sixteen points needed 32.  Two points per
+        // FFMA2, same accumulation order as a scalar chain.  relu' is NOT kept: the backward epilogue that needs it
+        // (delta0) reads it back from the image ("hi > 0"), which ndp_relu_img makes exact.
+        auto gen_h0 = [&](unsigned char* dst, int cc) {
+            NdpF2 aA[4], aB[4];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                float u[8];
+            for (int j = 0; j < 4; ++j) { aA[j] = ndp_f2_bcast(bA); aB[j] = ndp_f2_bcast(bB); }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int p = col0 + 8 * k + j;
-                    const float4 e0 = *(const float4*)&ef[p][0], e1 = *(const float4*)&ef[p][4];
-                    float v = fmaf(w_in[0], e0.x, b_in);
-                    v = fmaf(w_in[1], e0.y, v); v = fmaf(w_in[2], e0.z, v); v = fmaf(w_in[3], e0.w, v);
-                    v = fmaf(w_in[4], e1.x, v); v = fmaf(w_in[5], e1.y, v);
-                    mask |= (v > 0.0f ? 1u : 0u) << (8 * k + j);
-                    u[j] = fmaxf(v, 0.0f);
-                }
-                ndp_store_chunk2(dst, NDP_IMG64, ndp_img_off(f, col0 + 8 * k, NDP_RS64), u);
+            for (int k = 0; k < 6; ++k) {
+                const float4 e0 = *(const float4*)&S.ef[cc][k][8 * hp8], e1 = *(const float4*)&S.ef[cc][k][8 * hp8 + 4];
+                const NdpF2 p[4] = {ndp_f2_make(e0.x, e0.y), ndp_f2_make(e0.z, e0.w), ndp_f2_make(e1.x, e1.y), ndp_f2_make(e1.z, e1.w)};
+                const NdpF2 wa = ndp_f2_bcast(wA[k]), wb = ndp_f2_bcast(wB[k]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { aA[j] = ndp_f2_fma(wa, p[j], aA[j]); aB[j] = ndp_f2_fma(wb, p[j], aB[j]); }
             }
-            return mask;
+            float u[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { ndp_f2_get(aA[j], u[2 * j], u[2 * j + 1]); u[2 * j] = ndp_relu_img(u[2 * j]); u[2 * j + 1] = ndp_relu_img(u[2 * j + 1]); }
+            ndp_store_chunk2(dst, NDP_IMG64, ndp_img_off(fA, 8 * hp8, NDP_RS64), u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { ndp_f2_get(aB[j], u[2 * j], u[2 * j + 1]); u[2 * j] = ndp_relu_img(u[2 * j]); u[2 * j + 1] = ndp_relu_img(u[2 * j + 1]); }
+            ndp_store_chunk2(dst, NDP_IMG64, ndp_img_off(fB, 8 * hp8, NDP_RS64), u);
+        };
+        // relu'(h0) of this thread's epilogue cell (feature f, points col0 .. col0 + 15 of chain cc) from the h0 image
+        auto h0_mask = [&](const unsigned char* img) -> unsigned {
+            return ndp_pos_mask8(*(const uint4*)(img + ndp_img_off(f, col0, NDP_RS64))) |
+                   (ndp_pos_mask8(*(const uint4*)(img + ndp_img_off(f, col0 + 8, NDP_RS64))) << 8);
         };
         // forward epilogue of chain cc: dst = relu(acc + bias) re-split into the image; returns relu' as a bit mask
         auto epi_fwd = [&](unsigned char* dst, int cc, float bias) -> unsigned {
@@ -361,13 +376,14 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
                 ndp_store_chunk2(S.HG[c], NDP_IMG16H, ndp_img_off(ct >> 1, (ct & 1) * 8, NDP_RS16), v);
             } else if (ct < 192) {
                 const int pt = ct - 128;
-                *(float4*)&S.ef[c][pt][0] = r0;
-                *(float4*)&S.ef[c][pt][4] = make_float4(r1.x, r1.y, 0.0f, 0.0f);
+                S.ef[c][0][pt] = r0.x; S.ef[c][1][pt] = r0.y; S.ef[c][2][pt] = r0.z; S.ef[c][3][pt] = r0.w;
+                S.ef[c][4][pt] = r1.x; S.ef[c][5][pt] = r1.y;
             }
             ndp_group_sync(1, 512);         // ef complete
-            unsigned m0[2], m1[2], m2[2];
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) { m0[cc] = gen_h0(A[cc], cc); signal_ready(cc); }       // -> F1
+            NDP_TR(13);
+            unsigned m1[2], m2[2];
+            gen_h0(A[0], 0); NDP_TR(14); signal_ready(0); NDP_TR(15);
+            gen_h0(A[1], 1); signal_ready(1);       // -> F1
             NDP_TR(3);
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
@@ -391,12 +407,12 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
             for (int cc = 0; cc < 2; ++cc) {
                 wait_mma(cc); if (cc == 0) NDP_TR(7);
                 dbs1 += epi_bwd(B[cc], cc, m1[cc]);
-                m0[cc] = gen_h0(A[cc], cc);     // delta2 is dead (B1 retired): h0 again, for dW_0 and relu'(h0)
+                gen_h0(A[cc], cc);              // delta2 is dead (B1 retired): h0 again, for dW_0 and relu'(h0)
                 signal_ready(cc);           // -> B0
             }
 #pragma unroll
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) { wait_mma(cc); if (cc == 0) NDP_TR(8); dbs0 += epi_bwd(A[cc], cc, m0[cc]); signal_ready(cc); }    // -> Bin
+            for (int cc = 0; cc < 2; ++cc) { wait_mma(cc); if (cc == 0) NDP_TR(8); dbs0 += epi_bwd(A[cc], cc, h0_mask(A[cc])); signal_ready(cc); }    // -> Bin
             NDP_TR(9);
             if (a.gx) {     // optional dL/dx: + the path through the positional encoding (ndp_head_grad_kernel wrote the direct part)
                 ndp_group_sync(1, 512);     // delta0 of both chains complete

@@ -3,7 +3,7 @@
 OUT=gpurun_out; mkdir -p $OUT
 P=${4:-32}; IT=${5:-60}
 for S in $1; do for T in $2; do for R in $3; do
-  timeout 300 python bench.py --steps 2 --warmup 1 --pairs $P --iters $IT --no-cpu-baseline --streams $S --tpc $T --fwd-rounds $R > $OUT/sw.json 2> $OUT/sw.err
+  timeout 300 python bench.py --steps 2 --warmup 1 --pairs $P --iters $IT --no-cpu-baseline --no-mode-b --no-config5 --streams $S --tpc $T --fwd-rounds $R > $OUT/sw.json 2> $OUT/sw.err
   python - <<PY
 import json
 try:
