@@ -299,7 +299,7 @@ def main():
     barrier()
     l0 = solver.launch_count
     prof0, ns0 = solver.profile()
-    nn0 = solver.nn_stats() if a.nn_mode == 0 else (0, 0, 0, 0)
+    nn0 = solver.nn_stats() if a.nn_mode == 0 else (0, 0, 0)
     ms_dev, its = 0.0, None
     for _ in range(a.steps):
         ms, its, last = dev_step(solver)
@@ -307,7 +307,7 @@ def main():
     barrier()
     launches = solver.launch_count - l0
     prof1, ns1 = solver.profile()
-    nn1 = solver.nn_stats() if a.nn_mode == 0 else (0, 0, 0, 0)
+    nn1 = solver.nn_stats() if a.nn_mode == 0 else (0, 0, 0)
     prof_pairs = solver.profiled_pairs
     clocks = sampler.stop() if rank == 0 else None
     solver.close()
@@ -479,20 +479,24 @@ def main():
         nn_traffic = [(traffic.get(k) or {}).get("dram_bytes_per_launch") for k in nn_names]
         nn_work = None
         if a.nn_mode == 0 and nn1[1] > nn0[1]:
-            evals, qblocks, exact = nn1[0] - nn0[0], nn1[1] - nn0[1], nn1[2] - nn0[2]
-            ipe = (8.0 * exact + 4.5 * (evals - exact)) / max(evals, 1) if evals > 0 else 8.0   # instructions per evaluation: exact pass 8, minimum-only pass 4.5
+            evals, qblocks = nn1[0] - nn0[0], nn1[1] - nn0[1]
             searches = qblocks / (2.0 * (N // 32))                   # (pair, iteration) searches behind the counters
             per_search_s = t_nn / max(prof_pairs, 1)                 # sampled launch time / pairs per launch
+            ipe = 4.5                                                # instructions per evaluation (csrc/ndp_spatial.cu: packed FP32)
             issue_roof = 148 * 128 * sm_clock * 1e6 / ipe            # lane-instructions per second / instructions per evaluation
+            lds_roof = 148 * sm_clock * 1e6 * 32 / 3.0               # shared-memory pipe: 3 cycles per candidate broadcast to 32 lanes
+            rate = evals / searches / max(per_search_s, 1e-12)
             nn_work = {"candidates_per_query": evals / (qblocks * 32.0), "brute_force_candidates_per_query": N,
-                       "exact_pass_fraction": exact / max(evals, 1), "instructions_per_eval": ipe,
-                       "max_blocks_scanned_by_one_warp": nn1[3], "mean_blocks_scanned_per_warp": (evals - exact) / 1024.0 / max(qblocks, 1),
-                       "pair_evals_issued_per_s": evals / searches / max(per_search_s, 1e-12),
-                       "issue_roof_pair_evals_per_s": issue_roof,
-                       "issue_frac": evals / searches / max(per_search_s, 1e-12) / issue_roof,
-                       "model": "distance evaluations the culled search actually issues (32 x 32 per scanned block and pass) per second "
-                                "of its launch time, against 148 SM x 128 lanes x clock / instructions per evaluation (packed FP32: "
-                                "4.5 in the minimum-only pass, 8 in the exact (distance, index) pass, csrc/ndp_spatial.cu)"}
+                       "instructions_per_eval": ipe, "mean_blocks_scanned_per_warp": evals / 1024.0 / max(qblocks, 1),
+                       "max_blocks_scanned_by_one_warp": nn1[2],
+                       "pair_evals_issued_per_s": rate,
+                       "issue_roof_pair_evals_per_s": issue_roof, "issue_frac": rate / issue_roof,
+                       "smem_pipe_roof_pair_evals_per_s": lds_roof, "smem_pipe_frac": rate / lds_roof,
+                       "model": "distance evaluations the culled search actually issues (32 x 32 per scanned block) per second of its "
+                                "launch time, against (a) 148 SM x 128 lanes x clock / 4.5 instructions per evaluation and (b) the "
+                                "shared-memory pipe that broadcasts the candidates (12 bytes per candidate to each of 32 lanes = 3 "
+                                "cycles); an isolated launch is bound by neither: its slowest warp walks max_blocks blocks one after "
+                                "the other (DESIGN.md)"}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": 1e3 * sec_dev / a.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload(a),

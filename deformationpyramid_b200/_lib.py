@@ -84,7 +84,7 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
     lib.ndp_solver_losses.argtypes = [c_void_p, c_int32, c_void_p, c_void_p]
     lib.ndp_solver_profile.argtypes = [c_void_p, P(c_double), P(c_int64)]
     lib.ndp_solver_profile.restype = ctypes.c_int
-    lib.ndp_solver_nn_stats.argtypes = [c_void_p, P(c_int64), P(c_int64), P(c_int64), P(c_int64)]
+    lib.ndp_solver_nn_stats.argtypes = [c_void_p, P(c_int64), P(c_int64), P(c_int64)]
     lib.ndp_solver_nn_stats.restype = ctypes.c_int
     lib.ndp_solver_profiled_pairs.argtypes = [c_void_p]
     lib.ndp_solver_profiled_pairs.restype = c_int32

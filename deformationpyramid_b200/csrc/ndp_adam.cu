@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) ndp_reduce_adam_kernel(NdpAdamArgs a) {
 void ndp_launch_adam(const NdpAdamArgs& a, cudaStream_t s) {
     if (a.npairs <= 0) return;
     dim3 grid((a.lay.param_count + 255) / 256, a.npairs);
-    NDP_LAUNCH(ndp_reduce_adam_kernel, grid, dim3(256), 0, s, a);
+    NDP_LAUNCH_PRIO(1, ndp_reduce_adam_kernel, grid, dim3(256), 0, s, a);
 }
 
 __global__ void __launch_bounds__(256) ndp_pack_kernel(NdpPackArgs a) {

@@ -5,10 +5,12 @@
 #include "ndp_tc.cuh"
 
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <vector>
 
+int ndp_launch_prio[2] = {0, 0};   // per-launch scheduling priorities: [0] tensor-core kernels, [1] the others (NDP_LAUNCH_PRIO)
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CK(call)                                                                          \
@@ -98,7 +100,7 @@ static NnPlan nn_plan(long long n, long long m) {
     p.chunks = (int)((big + p.chunk_targets - 1) / p.chunk_targets);
     if (p.chunks < 1) p.chunks = 1;
     p.qpitch = (int)pad4(big);
-    p.blocks = (int)((big + 127) / 128);          // per-CTA partial sums: 256 points per CTA of the stand-alone epilogue, 128 of the fused search
+    p.blocks = (int)((big + 31) / 32);          // per-CTA partial sums: 256 points per CTA of the stand-alone epilogue, 128 of the fused search
     if (p.blocks < 1) p.blocks = 1;
     return p;
 }
@@ -398,6 +400,7 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
     if (!e) {
         if (const char* dv = getenv("NDP_DEBUG_SKIP")) s->dbg_skip = atoi(dv);
         if (const char* dv = getenv("NDP_DEBUG_NN")) s->dbg_nn = atoi(dv);
+        if (const char* dv = getenv("NDP_DEBUG_PRIO")) { ndp_launch_prio[0] = atoi(dv); const char* c2 = strchr(dv, ':'); ndp_launch_prio[1] = c2 ? atoi(c2 + 1) : 0; }
         const int want = c->streams > 0 ? c->streams : 4;
         s->nstreams = (int)(B < want ? B : want);
         if (s->nstreams > 1 && cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess)
@@ -417,14 +420,13 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
 extern "C" int64_t ndp_solver_params_per_pair(const ndp_solver* s) { return s ? (int64_t)s->cfg.levels * s->P : -1; }
 extern "C" int64_t ndp_solver_launch_count(const ndp_solver* s) { return s ? s->launches : -1; }
 extern "C" int32_t ndp_solver_profiled_pairs(const ndp_solver* s) { return s ? s->prof_pairs : -1; }
-extern "C" int ndp_solver_nn_stats(const ndp_solver* s, int64_t* pair_evals, int64_t* query_blocks, int64_t* exact_evals, int64_t* max_blocks) {
+extern "C" int ndp_solver_nn_stats(const ndp_solver* s, int64_t* pair_evals, int64_t* query_blocks, int64_t* max_blocks) {
     if (!s || !pair_evals || !query_blocks) return fail(NDP_E_INVALID, "NULL argument");
     if (!s->nnstats) return fail(NDP_E_INVALID, "the solver was created without profile_every > 0 (or runs the brute-force search)");
     DeviceGuard guard(s->device);
     unsigned long long h[4] = {0, 0, 0, 0};
     CK(cudaMemcpy(h, s->nnstats, 32, cudaMemcpyDeviceToHost));
     *pair_evals = (int64_t)h[0]; *query_blocks = (int64_t)h[1];
-    if (exact_evals) *exact_evals = (int64_t)h[2];
     if (max_blocks) *max_blocks = (int64_t)h[3];
     return NDP_OK;
 }

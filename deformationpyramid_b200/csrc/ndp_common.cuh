@@ -6,11 +6,19 @@
 #ifdef NDP_EMU
 #include "cuda_emu.h"
 #define NDP_LAUNCH(kernel, grid, block, smem, stream, ...) ndp_emu::launch(kernel, grid, block, smem, __VA_ARGS__)
+#define NDP_LAUNCH_PRIO(cls, kernel, grid, block, smem, stream, ...) ndp_emu::launch(kernel, grid, block, smem, __VA_ARGS__)
 #define NDP_DYN_SMEM(name) unsigned char* name = ndp_emu::dyn_smem()
 #else
 #include <cuda_runtime.h>
 #define NDP_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #define NDP_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
+// launch with a per-launch scheduling priority (cudaLaunchAttributePriority; lower number = served first when an SM frees up)
+extern int ndp_launch_prio[2];      // [0] tensor-core kernels, [1] everything else; 0 / 0 = plain launches (ndp_cabi.cu)
+#define NDP_LAUNCH_PRIO(cls, kernel, grid, block, smem, strm_, ...) do { \
+        if (ndp_launch_prio[0] == ndp_launch_prio[1]) { kernel<<<grid, block, smem, strm_>>>(__VA_ARGS__); } else { \
+            cudaLaunchConfig_t lc_ = {}; lc_.gridDim = grid; lc_.blockDim = block; lc_.dynamicSmemBytes = smem; lc_.stream = strm_; \
+            cudaLaunchAttribute la_[1]; la_[0].id = cudaLaunchAttributePriority; la_[0].val.priority = ndp_launch_prio[cls]; \
+            lc_.attrs = la_; lc_.numAttrs = 1; cudaLaunchKernelEx(&lc_, kernel, __VA_ARGS__); } } while (0)
 #endif
 
 #include "ndp_math.cuh"

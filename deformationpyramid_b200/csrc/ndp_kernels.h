@@ -153,7 +153,7 @@ struct NdpPrunedArgs {
     const NdpPairState* state;
     int npairs;
     int pair0 = 0;
-    unsigned long long* stats = nullptr;                              // optional [4]: distance evaluations issued (32 lanes x 32 targets per block and pass), 32-query blocks searched, evaluations of the exact pass
+    unsigned long long* stats = nullptr;                              // optional [4]: distance evaluations issued (32 lanes x 32 targets per scanned block), 32-query blocks searched, -, most blocks one warp scanned
     int dbg = 0;                                                      // measurement aid (NDP_DEBUG_NN): 1 no candidate walk, 2 no per-query epilogue, 4 no CTA epilogue
     const struct NdpChamferArgs* fuse = nullptr;                      // host pointer, read at launch: when set the kernel also does the whole Chamfer epilogue
 };

@@ -28,6 +28,15 @@
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 #endif
 
+#ifdef NDP_EMU
+static inline int ndp_atomic_add_release(int* p, int v) { return atomicAdd(p, v); }
+#else
+__device__ __forceinline__ int ndp_atomic_add_release(int* p, int v) {
+    int old;
+    asm volatile("atom.add.release.gpu.global.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+#endif
 __device__ __forceinline__ float ndp_sqdist3(float qx, float qy, float qz, float tx, float ty, float tz) {
     const float dx = __fsub_rn(qx, tx), dy = __fsub_rn(qy, ty), dz = __fsub_rn(qz, tz);
     return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
@@ -179,7 +188,9 @@ int ndp_launch_sort(const NdpSortArgs& a, cudaStream_t s) {
 // With FUSE the kernel also does the whole Chamfer epilogue of ndp_chamfer.cu (truncation, L1 sums, direct
 // and scattered gradient terms, loss + early-stop rule in the last CTA of the pair): one launch less per
 // iteration and no second pass over the (d2, idx) arrays.
+#ifndef NDP_PN_WARPS
 #define NDP_PN_WARPS 4
+#endif
 struct NdpFuseArgs {             // the Chamfer epilogue's arguments (subset of NdpChamferArgs), by value
     float trunc;
     float* gx; long long gx_stride;
@@ -191,7 +202,7 @@ struct NdpFuseArgs {             // the Chamfer epilogue's arguments (subset of 
 };
 
 template <bool FUSE>
-__global__ void __launch_bounds__(NDP_PN_WARPS * 32, 12) ndp_nn_pruned_kernel(NdpPrunedArgs a, NdpFuseArgs fz) {
+__global__ void __launch_bounds__(NDP_PN_WARPS * 32, 48 / NDP_PN_WARPS) ndp_nn_pruned_kernel(NdpPrunedArgs a, NdpFuseArgs fz) {
     __shared__ __align__(16) float stage[NDP_PN_WARPS][16][6];   // per warp: 16 candidate pairs (-x0, -x1, -y0, -y1, -z0, -z1)
     __shared__ int stage_o[NDP_PN_WARPS][32];                    // their original sample indices
     __shared__ double wsum[NDP_PN_WARPS];
@@ -336,9 +347,13 @@ __global__ void __launch_bounds__(NDP_PN_WARPS * 32, 12) ndp_nn_pruned_kernel(Nd
         const int nbx = (n + NDP_PN_WARPS * 32 - 1) / (NDP_PN_WARPS * 32), nby = (m + NDP_PN_WARPS * 32 - 1) / (NDP_PN_WARPS * 32);
         double* bs = fz.blocksums + ((long long)pair * fz.blocks_pitch) * 2;
         if (threadIdx.x == 0) {
-            bs[(long long)blockIdx.x * 2 + dir] = (wsum[0] + wsum[1]) + (wsum[2] + wsum[3]);
-            __threadfence();
-            const int ticket = atomicAdd(fz.counters + pair, 1);
+            double cs = wsum[0];
+#pragma unroll
+            for (int k = 1; k < NDP_PN_WARPS; ++k) cs += wsum[k];
+            bs[(long long)blockIdx.x * 2 + dir] = cs;
+            // publish the block sum with a RELEASE on the ticket instead of __threadfence(): the full fence also invalidates
+            // the SM's L1 (CCTL.IVALL), i.e. the boxes and tiles the other resident CTAs of the search keep re-reading
+            const int ticket = ndp_atomic_add_release(fz.counters + pair, 1);
             is_last = (ticket == nbx + nby - 1);
         }
         __syncthreads();
@@ -382,7 +397,7 @@ void ndp_launch_nn_pruned(const NdpPrunedArgs& a, cudaStream_t s) {
         fz.blocksums = c.blocksums; fz.blocks_pitch = c.blocks_pitch; fz.counters = c.counters; fz.loss_out = c.loss_out;
         fz.state = c.state; fz.loss_hist = c.loss_hist; fz.hist_stride = c.hist_stride; fz.hist_cap = c.hist_cap;
         fz.max_break_count = c.max_break_count; fz.break_ratio = c.break_ratio;
-        NDP_LAUNCH(ndp_nn_pruned_kernel<true>, grid, dim3(NDP_PN_WARPS * 32), 0, s, b, fz);
+        NDP_LAUNCH_PRIO(1, ndp_nn_pruned_kernel<true>, grid, dim3(NDP_PN_WARPS * 32), 0, s, b, fz);
     } else {
         NDP_LAUNCH(ndp_nn_pruned_kernel<false>, grid, dim3(NDP_PN_WARPS * 32), 0, s, b, fz);
     }

@@ -63,9 +63,22 @@ __device__ __forceinline__ float ndp_f16_to_f32(unsigned h) { float lo, hi; ndp_
 // 2-way split of a pair of values into two packed f16x2 words (hi and lo parts)
 __device__ __forceinline__ void ndp_split2_pair(float x0, float x1, unsigned& w1, unsigned& w2) {
     w1 = ndp_pack2_f16(x0, x1);
-    float f0, f1;
+    float f0, f1, r0, r1;
     ndp_unpack2_f16(w1, f0, f1);
-    w2 = ndp_pack2_f16(x0 - f0, x1 - f1);
+    ndp_f2_get(ndp_f2_sub(ndp_f2_make(x0, x1), ndp_f2_make(f0, f1)), r0, r1);     // one FADD2 for both residuals
+    w2 = ndp_pack2_f16(r0, r1);
+}
+// relu(v + b) of a value pair, split into its packed hi / lo f16x2 words; the adds run on the packed FP32 pipe
+// (FADD2: one instruction per pair).  Plain max(x, 0): for kernels that do not read relu' back from the image.
+__device__ __forceinline__ void ndp_bias_relu_split2(float v0, float v1, float b0, float b1, unsigned& w1, unsigned& w2) {
+    float x0, x1;
+    ndp_f2_get(ndp_f2_add(ndp_f2_make(v0, v1), ndp_f2_make(b0, b1)), x0, x1);
+    x0 = fmaxf(x0, 0.0f); x1 = fmaxf(x1, 0.0f);
+    w1 = ndp_pack2_f16(x0, x1);
+    float f0, f1, r0, r1;
+    ndp_unpack2_f16(w1, f0, f1);
+    ndp_f2_get(ndp_f2_sub(ndp_f2_make(x0, x1), ndp_f2_make(f0, f1)), r0, r1);
+    w2 = ndp_pack2_f16(r0, r1);
 }
 // one value -> its two fp16 bit patterns
 __device__ __forceinline__ void ndp_split2(float x, unsigned& h1, unsigned& h2) {

@@ -73,6 +73,7 @@ struct BwdRcSmem {
     unsigned char E[2][2 * NDP_IMG16H];    // per chain [64 points][16]: cols 0..5 positional encoding, rest 0
     unsigned char HWT[2 * NDP_IMG16F];     // [128 features][16 head rows]: head weights transposed, rows >= head_dim zero
     float ef[2][6][NDP_HP];                // per chain: fp32 positional encoding, one row per component (h0 on the CUDA cores)
+    float win[7][NDP_W];                   // input layer: rows 0..5 = W_in[:, k], row 6 = b_in (fp32; registers are too scarce to hold them)
     NdpMbar bar_w, bar_wfree, bar_ready[2][2], bar_mma[2], bar_fin;   // ready: [chain][signal parity]
     unsigned tmem_slot, pad[3];
 };
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
     // of a warp share hp8 (their encoding loads are one broadcast per warp) and the 8 lanes of a quarter warp hold 8
     // consecutive features, so the 16-byte image stores of a quarter warp fill all 32 banks.
     const int hp8 = (tid >> 6) & 7, fA = ((tid & 63) >> 3) * 16 + (tid & 7), fB = fA + 8;
-    float wA[6], wB[6], bA = 0.0f, bB = 0.0f, b_0 = 0.0f, b_1 = 0.0f;
+    float b_0 = 0.0f, b_1 = 0.0f;
     if (!issw) {
         // transposed head weight image: row i = ct & 127, 8-column chunk ct >> 7 (head rows 8 chunk .. 8 chunk + 7)
         const int i = ct & 127, c8 = ct >> 7;
@@ -141,9 +142,10 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
             float z8[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
             if (ct < 64) ndp_store_chunk2(S.E[c], NDP_IMG16H, ndp_img_off(ct, 8, NDP_RS16), z8);
         }
-#pragma unroll
-        for (int k = 0; k < 6; ++k) { wA[k] = __ldg(params + L.off_w_in + fA * 6 + k); wB[k] = __ldg(params + L.off_w_in + fB * 6 + k); }
-        bA = __ldg(params + L.off_b_in + fA); bB = __ldg(params + L.off_b_in + fB);
+        for (int idx = tid; idx < 7 * NDP_W; idx += 512) {
+            const int k = idx >> 7, o = idx & (NDP_W - 1);
+            S.win[k][o] = k < 6 ? __ldg(params + L.off_w_in + o * 6 + k) : __ldg(params + L.off_b_in + o);
+        }
         b_0 = __ldg(params + L.off_b[0] + f); b_1 = __ldg(params + L.off_b[1] + f);
     }
     // the CTA's delta scale: an exact power of two that brings the largest head gradient of its tiles
@@ -293,12 +295,12 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
         auto gen_h0 = [&](unsigned char* dst, int cc) {
             NdpF2 aA[4], aB[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { aA[j] = ndp_f2_bcast(bA); aB[j] = ndp_f2_bcast(bB); }
+            for (int j = 0; j < 4; ++j) { aA[j] = ndp_f2_bcast(S.win[6][fA]); aB[j] = ndp_f2_bcast(S.win[6][fB]); }
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
                 const float4 e0 = *(const float4*)&S.ef[cc][k][8 * hp8], e1 = *(const float4*)&S.ef[cc][k][8 * hp8 + 4];
                 const NdpF2 p[4] = {ndp_f2_make(e0.x, e0.y), ndp_f2_make(e0.z, e0.w), ndp_f2_make(e1.x, e1.y), ndp_f2_make(e1.z, e1.w)};
-                const NdpF2 wa = ndp_f2_bcast(wA[k]), wb = ndp_f2_bcast(wB[k]);
+                const NdpF2 wa = ndp_f2_bcast(S.win[k][fA]), wb = ndp_f2_bcast(S.win[k][fB]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { aA[j] = ndp_f2_fma(wa, p[j], aA[j]); aB[j] = ndp_f2_fma(wb, p[j], aB[j]); }
             }
@@ -324,10 +326,12 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
             for (int k = 0; k < 2; ++k) {
                 float u[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float x = v[8 * k + j] + bias;
-                    mask |= (x > 0.0f ? 1u : 0u) << (8 * k + j);
-                    u[j] = fmaxf(x, 0.0f);
+                for (int j = 0; j < 8; j += 2) {
+                    float x0, x1;
+                    ndp_f2_get(ndp_f2_add(ndp_f2_make(v[8 * k + j], v[8 * k + j + 1]), ndp_f2_bcast(bias)), x0, x1);     // FADD2
+                    mask |= (x0 > 0.0f ? 1u : 0u) << (8 * k + j);
+                    mask |= (x1 > 0.0f ? 1u : 0u) << (8 * k + j + 1);
+                    u[j] = fmaxf(x0, 0.0f); u[j + 1] = fmaxf(x1, 0.0f);
                 }
                 ndp_store_chunk2(dst, NDP_IMG64, ndp_img_off(f, col0 + 8 * k, NDP_RS64), u);
             }
@@ -337,15 +341,19 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
         auto epi_bwd = [&](unsigned char* buf, int cc, unsigned mask) -> float {
             float v[16];
             ndp_tmem_ld16(tlq + RC_ACC(cc) + (unsigned)col0, v);
-            float sum = 0.0f;
+            NdpF2 sum2 = ndp_f2_bcast(0.0f);            // even / odd columns (fixed order)
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 float u[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { u[j] = ((mask >> (8 * k + j)) & 1u) ? v[8 * k + j] : 0.0f; sum += u[j]; }
+                for (int j = 0; j < 8; ++j) u[j] = ((mask >> (8 * k + j)) & 1u) ? v[8 * k + j] : 0.0f;
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) sum2 = ndp_f2_add(sum2, ndp_f2_make(u[j], u[j + 1]));
                 ndp_store_chunk2(buf, NDP_IMG64, ndp_img_off(f, col0 + 8 * k, NDP_RS64), u);
             }
-            return sum;
+            float s0, s1;
+            ndp_f2_get(sum2, s0, s1);
+            return s0 + s1;
         };
         // this thread's share of the record of ndp_head_grad_kernel for one tile (staging role: chain c = tid / 256,
         // ct = tid % 256): ct < 128: 8 head gradients of point ct / 2 of half c; 128 <= ct < 192: the encoding of point
@@ -525,7 +533,7 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
 }
 
 void ndp_launch_bwd_rc_main(const NdpBwdArgs& b, int grid_x, cudaStream_t s) {
-    NDP_LAUNCH(ndp_warp_bwd_rc_kernel, dim3(grid_x, b.npairs), dim3(NDP_RC_THREADS), ndp_bwd_rc_smem_bytes(), s, b);
+    NDP_LAUNCH_PRIO(0, ndp_warp_bwd_rc_kernel, dim3(grid_x, b.npairs), dim3(NDP_RC_THREADS), ndp_bwd_rc_smem_bytes(), s, b);
 }
 
 int ndp_bwd_rc_init() {

@@ -461,7 +461,7 @@ void ndp_launch_bwd_rc_main(const NdpBwdArgs& b, int grid_x, cudaStream_t s);
 void ndp_launch_bwd_tc(const NdpBwdArgs& a, cudaStream_t s) {
     if (a.npairs <= 0 || a.n <= 0) return;
     const int tiles = (a.n + NDP_TP - 1) / NDP_TP;
-    NDP_LAUNCH(ndp_head_grad_kernel, dim3(tiles, a.npairs), dim3(NDP_TP), 0, s, a);
+    NDP_LAUNCH_PRIO(1, ndp_head_grad_kernel, dim3(tiles, a.npairs), dim3(NDP_TP), 0, s, a);
     NdpBwdArgs b = a;
     b.tpc = ndp_bwd_tc_tiles_per_cta(a.lay.hidden, a.n, a.tpc);
     const int gx = (tiles + b.tpc - 1) / b.tpc;

@@ -295,6 +295,7 @@ size_t ndp_fwd_tc2_smem_bytes() { return sizeof(FwdTc2Smem) + 1024; }
 #define TM2_AOP 128u
 #define TM2_LO 64u
 
+template <bool SAVE>       // SAVE: the activations are saved as images (a.act), from which the non-recomputing backward reads relu'
 __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc2_kernel(NdpFwdArgs a) {
     NDP_DYN_SMEM(smem_raw);
     FwdTc2Smem& S = *(FwdTc2Smem*)NDP_SMEM_ALIGN(smem_raw, 1024);
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc2_kernel
     const int warp = tid >> 5, p = gt & (NDP_TP - 1), half = gt >> 7;
     const bool ldw = (ndp_warp_uniform(warp) & 7) == 0;   // the group's issuing warp: one elected lane launches the MMAs
     const int RS = NDP_IMG_RS(128), CS = NDP_IMG_CS, RS16 = NDP_IMG_RS(16);
-    unsigned char* const gact_pair = a.act ? (unsigned char*)a.act + ((long long)pair * a.act_stride) * 4 : nullptr;
+    unsigned char* const gact_pair = (SAVE && a.act) ? (unsigned char*)a.act + ((long long)pair * a.act_stride) * 4 : nullptr;
     float* xs = S.xs[g];
 
     NDP_T(0);
@@ -420,6 +421,13 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc2_kernel
 #pragma unroll
                 for (int s8 = 0; s8 < 4; ++s8) {
                     const float4 b0 = __ldg((const float4*)(bias + col0 + s8 * 8)), b1 = __ldg((const float4*)(bias + col0 + s8 * 8 + 4));
+                    if (!SAVE) {         // nothing reads relu' back from an image (the recomputing backward): plain max, packed adds
+                        ndp_bias_relu_split2(v[s8 * 8 + 0], v[s8 * 8 + 1], b0.x, b0.y, hi[s8 * 4 + 0], lo[s8 * 4 + 0]);
+                        ndp_bias_relu_split2(v[s8 * 8 + 2], v[s8 * 8 + 3], b0.z, b0.w, hi[s8 * 4 + 1], lo[s8 * 4 + 1]);
+                        ndp_bias_relu_split2(v[s8 * 8 + 4], v[s8 * 8 + 5], b1.x, b1.y, hi[s8 * 4 + 2], lo[s8 * 4 + 2]);
+                        ndp_bias_relu_split2(v[s8 * 8 + 6], v[s8 * 8 + 7], b1.z, b1.w, hi[s8 * 4 + 3], lo[s8 * 4 + 3]);
+                        continue;
+                    }
                     ndp_split2_pair(ndp_relu_img(v[s8 * 8 + 0] + b0.x), ndp_relu_img(v[s8 * 8 + 1] + b0.y), hi[s8 * 4 + 0], lo[s8 * 4 + 0]);
                     ndp_split2_pair(ndp_relu_img(v[s8 * 8 + 2] + b0.z), ndp_relu_img(v[s8 * 8 + 3] + b0.w), hi[s8 * 4 + 1], lo[s8 * 4 + 1]);
                     ndp_split2_pair(ndp_relu_img(v[s8 * 8 + 4] + b1.x), ndp_relu_img(v[s8 * 8 + 5] + b1.y), hi[s8 * 4 + 2], lo[s8 * 4 + 2]);
@@ -484,8 +492,10 @@ void ndp_launch_fwd_tc(const NdpFwdArgs& a, cudaStream_t s) {
         if (rounds > 8) rounds = 8;
         NdpFwdArgs b2 = a;
         b2.rounds = rounds;
-        NDP_LAUNCH(ndp_warp_fwd_tc2_kernel, dim3((tiles + 2 * rounds - 1) / (2 * rounds), a.npairs), dim3(NDP_FWD_TC_THREADS),
-                   ndp_fwd_tc2_smem_bytes(), s, b2);
+        if (a.act) NDP_LAUNCH_PRIO(0, ndp_warp_fwd_tc2_kernel<true>, dim3((tiles + 2 * rounds - 1) / (2 * rounds), a.npairs), dim3(NDP_FWD_TC_THREADS),
+                                   ndp_fwd_tc2_smem_bytes(), s, b2);
+        else NDP_LAUNCH_PRIO(0, ndp_warp_fwd_tc2_kernel<false>, dim3((tiles + 2 * rounds - 1) / (2 * rounds), a.npairs), dim3(NDP_FWD_TC_THREADS),
+                             ndp_fwd_tc2_smem_bytes(), s, b2);
         return;
     }
     if (rounds > NDP_FWD_MAX_ROUNDS) rounds = NDP_FWD_MAX_ROUNDS;
@@ -498,7 +508,9 @@ void ndp_launch_fwd_tc(const NdpFwdArgs& a, cudaStream_t s) {
 int ndp_fwd_tc_init() {
     int e = (int)cudaFuncSetAttribute(ndp_warp_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)ndp_fwd_tc_smem_bytes());
-    if (e == 0) e = (int)cudaFuncSetAttribute(ndp_warp_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (e == 0) e = (int)cudaFuncSetAttribute(ndp_warp_fwd_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)ndp_fwd_tc2_smem_bytes());
+    if (e == 0) e = (int)cudaFuncSetAttribute(ndp_warp_fwd_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)ndp_fwd_tc2_smem_bytes());
     return e;
 }

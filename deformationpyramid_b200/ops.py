@@ -322,12 +322,12 @@ class Solver:
         return dict(zip(self.KERNELS, [float(v) for v in ms])), int(n.value)
 
     def nn_stats(self):
-        """(distance evaluations issued by the culled search, 32-query blocks searched, evaluations of the exact
-        (distance, index) pass among them, most blocks one warp scanned in a search) since creation."""
-        a, b, c, d = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
-        _lib.check(self.lib, self.lib.ndp_solver_nn_stats(self.handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d)),
+        """(distance evaluations issued by the culled search, 32-query blocks searched, most blocks one warp
+        scanned in a search) since creation."""
+        a, b, c = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+        _lib.check(self.lib, self.lib.ndp_solver_nn_stats(self.handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)),
                    "ndp_solver_nn_stats")
-        return int(a.value), int(b.value), int(c.value), int(d.value)
+        return int(a.value), int(b.value), int(c.value)
 
     @property
     def profiled_pairs(self) -> int:

@@ -194,13 +194,11 @@ int ndp_solver_profile(const ndp_solver* s, double* ms, int64_t* samples);
  * ndp_solver_profile are the FIRST group's: this many pairs each.                            */
 int32_t ndp_solver_profiled_pairs(const ndp_solver* s);
 /* Work actually done by the culled search since creation (profile_every > 0, nn_mode 0): distance evaluations
- * issued (every scanned 32-target block costs 32 x 32 of them per warp of 32 queries and pass) and 32-query
- * blocks searched; the brute-force equivalent is (queries x targets).  exact_evals (may be NULL): the part of
- * pair_evals spent in the exact pass that keeps (distance, index) keys -- the rest only tracks the block
- * minimum (see csrc/ndp_spatial.cu); max_blocks (may be NULL): the most 32-target blocks any warp of 32
- * queries scanned in one search (the tail that bounds a launch).  Synchronises the device.                   */
-int ndp_solver_nn_stats(const ndp_solver* s, int64_t* pair_evals, int64_t* query_blocks, int64_t* exact_evals,
-                        int64_t* max_blocks);
+ * issued (every scanned 32-target block costs 32 x 32 of them per warp of 32 queries) and 32-query blocks
+ * searched; the brute-force equivalent is (queries x targets).  max_blocks (may be NULL): the most 32-target
+ * blocks any warp of 32 queries scanned in one search (the tail that bounds an isolated launch).
+ * Synchronises the device.                                                                               */
+int ndp_solver_nn_stats(const ndp_solver* s, int64_t* pair_evals, int64_t* query_blocks, int64_t* max_blocks);
 
 #ifdef __cplusplus
 }
