@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ndp", choices=["ndp", "reference"])
-    ap.add_argument("--pairs", type=int, default=32, help="pairs registered concurrently per GPU per step")
+    ap.add_argument("--pairs", type=int, default=64, help="pairs registered concurrently per GPU per step")
     ap.add_argument("--points", type=int, default=8192)
     ap.add_argument("--levels", type=int, default=9)
     ap.add_argument("--iters", type=int, default=500)
@@ -80,7 +80,7 @@ def parse():
 def _profile(a):
     """ndp_solver_cfg execution profile selected from the batch size (identical in both arms' config)."""
     from deformationpyramid_b200.ops import execution_profile
-    prof = execution_profile(a.pairs)
+    prof = execution_profile(a.pairs, a.points)
     for k, v in (("tiles_per_bwd_cta", a.tpc), ("fwd_rounds", a.fwd_rounds), ("streams", a.streams)):
         if v is not None:
             prof[k] = v
@@ -99,7 +99,7 @@ def workload(a):
             "nn_search": "exact culled (Morton blocks + boxes + seeds)" if a.nn_mode == 0 else "brute force",
             "width": 128, "depth": 3, "motion": "SE3", "rotation": "axis_angle",
             "l2": "flushed (256 MiB write) between timed steps: the per-iteration working set of a step (weights, "
-                  "Adam moments, gradient partials, clouds: ~60 MiB at 32 pairs) is smaller than the 126 MiB L2"}
+                  f"Adam moments, gradient partials, clouds: ~{1.9 * a.pairs:.0f} MiB at {a.pairs} pairs) does not exceed the 126 MiB L2"}
 
 
 class ClockSampler:
@@ -397,7 +397,9 @@ def main():
     config5 = None
     if a.mode == "fixed" and not a.no_config5:
         NP5, B5 = 30000, B
-        cfg5 = ndp_config(device=local, **prof)                      # NDP.yaml defaults: samples 2000, m 9, iters 500, early stop on
+        prof5 = {k: v for k, v in (("tiles_per_bwd_cta", a.tpc), ("fwd_rounds", a.fwd_rounds), ("streams", a.streams)) if v is not None}
+        cfg5 = ndp_config(device=local, **prof5)                     # NDP.yaml defaults: samples 2000, m 9, iters 500, early stop on; the
+        # execution profile follows Registration's rule for (pairs, samples) unless overridden on the command line
         reg5 = Registration(cfg5)
         pairs5 = {}
 

@@ -245,8 +245,14 @@ __global__ void __launch_bounds__(NDP_PN_WARPS * 32, 48 / NDP_PN_WARPS) ndp_nn_p
     int scanned = 0;
     const NdpF2 qx2 = ndp_f2_bcast(qq.x), qy2 = ndp_f2_bcast(qq.y), qz2 = ndp_f2_bcast(qq.z);
 
-    for (int base = 0; base < ntblk && !(a.dbg & 1); base += 32) {
-        const int blk = base + lane;
+    // Coarse test of all target blocks first, 32 rounds of 32 blocks at most per batch (lane = block; the loads of the rounds
+    // are independent, two rounds in flight); lane r keeps round r's ballot.  Then the survivors are walked.
+    for (int sbase = 0; sbase < ntblk && !(a.dbg & 1); sbase += 1024) {
+    const int nrounds = (ntblk - sbase + 31) >> 5 < 32 ? (ntblk - sbase + 31) >> 5 : 32;
+    int mreg = 0;
+#pragma unroll 2
+    for (int r = 0; r < nrounds; ++r) {
+        const int blk = sbase + r * 32 + lane;
         bool need = false;
         if (blk < ntblk) {
             const float4 blo = *(const float4*)(tbox + (long long)blk * 8), bhi = *(const float4*)(tbox + (long long)blk * 8 + 4);
@@ -254,7 +260,12 @@ __global__ void __launch_bounds__(NDP_PN_WARPS * 32, 48 / NDP_PN_WARPS) ndp_nn_p
                                       ndp_gap(qlo.z, qhi.z, blo.z, bhi.z));
             need = lbw <= wmax;
         }
-        unsigned mask = __ballot_sync(0xffffffffu, need);
+        const int m = (int)__ballot_sync(0xffffffffu, need);
+        if (lane == r) mreg = m;
+    }
+    for (int r = 0; r < nrounds; ++r) {
+        const int base = sbase + r * 32;
+        unsigned mask = (unsigned)__shfl_sync(0xffffffffu, mreg, r);
         while (mask) {
             const int b = __ffs((int)mask) - 1;
             mask &= mask - 1;
@@ -276,17 +287,19 @@ __global__ void __launch_bounds__(NDP_PN_WARPS * 32, 48 / NDP_PN_WARPS) ndp_nn_p
             }
             __syncwarp();
             // block-local minimum and its position; strict '<' in block order = lowest original index among equal distances
-            float bd = INF;
-            int bp = 0;
-#pragma unroll 8
+            // (two running minima, even / odd candidates: the compare-select chain is the longest dependency of the scan)
+            float bd = INF, bd1 = INF;
+            int bp = 0, bp1 = 1;
+#pragma unroll
             for (int p = 0; p < 16; ++p) {
                 const float4 g = *(const float4*)&stage[w][p][0];
                 const float2 z = *(const float2*)&stage[w][p][4];
                 float d0, d1;
                 ndp_sqdist3_pair(qx2, qy2, qz2, ndp_f2_make(g.x, g.y), ndp_f2_make(g.z, g.w), ndp_f2_make(z.x, z.y), d0, d1);
                 if (d0 < bd) { bd = d0; bp = 2 * p; }
-                if (d1 < bd) { bd = d1; bp = 2 * p + 1; }
+                if (d1 < bd1) { bd1 = d1; bp1 = 2 * p + 1; }
             }
+            if (bd1 < bd || (bd1 == bd && bp1 < bp)) { bd = bd1; bp = bp1; }
             if (bd < INF) {     // (candidates at infinite distance never replace the seed; NaN distances never compare below)
                 const unsigned long long k = ((unsigned long long)__float_as_uint(bd) << 32) | (unsigned)stage_o[w][bp];
                 bestk = k < bestk ? k : bestk;
@@ -295,6 +308,7 @@ __global__ void __launch_bounds__(NDP_PN_WARPS * 32, 48 / NDP_PN_WARPS) ndp_nn_p
             __syncwarp();
         }
     }
+    }   // sbase
     if (a.stats && lane == 0) {
         atomicAdd(a.stats, (unsigned long long)scanned * 1024ull);
         atomicAdd(a.stats + 1, 1ull);

@@ -165,6 +165,8 @@ static inline void ndp_umma_f16(unsigned tmem_d, NdpUmmaDesc da, NdpUmmaDesc db,
             ndp_emu::tmem[lane0 + m][col0 + n] = s;
         }
 }
+static inline void ndp_umma_f16_akeep(unsigned d, NdpUmmaDesc da, NdpUmmaDesc db, unsigned idesc, unsigned acc) { ndp_umma_f16(d, da, db, idesc, acc); }
+static inline void ndp_umma_f16_areuse(unsigned d, NdpUmmaDesc da, NdpUmmaDesc db, unsigned idesc, unsigned acc) { ndp_umma_f16(d, da, db, idesc, acc); }
 static inline void ndp_umma_commit(NdpMbar* b) { __atomic_fetch_add((unsigned*)&b->phase, 1u, __ATOMIC_SEQ_CST); }
 static inline void ndp_tmem_ld32(unsigned taddr, float (&v)[32]) {
     const int col0 = (int)(taddr & 0xffff), lane = (int)(taddr >> 16) + (int)(threadIdx.x & 31);
@@ -233,6 +235,21 @@ __device__ __forceinline__ void ndp_umma_f16(unsigned tmem_d, NdpUmmaDesc da, Nd
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+// the same with the A operand kept in / taken from the tensor core's collector buffer: KEEP on the first of two
+// consecutive MMAs with the SAME A descriptor, REUSE on the second -- the second one does not fetch A from shared memory
+// (SASS UTCHMMA ... .A_KEEP / .A_REUSE)
+__device__ __forceinline__ void ndp_umma_f16_akeep(unsigned tmem_d, NdpUmmaDesc da, NdpUmmaDesc db, unsigned idesc, unsigned acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void ndp_umma_f16_areuse(unsigned tmem_d, NdpUmmaDesc da, NdpUmmaDesc db, unsigned idesc, unsigned acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
 }
 // arrive on the mbarrier once every previously issued MMA of this thread has completed
@@ -342,6 +359,30 @@ void ndp_umma_gemm3(unsigned tmem_d, NdpUmmaDesc a0, unsigned a_img, unsigned a_
             da = ndp_umma_desc_adv(da, a_step);
             db = ndp_umma_desc_adv(db, b_step);
         }
+    }
+}
+
+// The same product issued k-step by k-step so that the two partial products that share the A hi chunk are adjacent:
+// hi x lo (A kept in the collector), hi x hi (A reused: no second fetch of the 4 KB chunk from shared memory), lo x hi.
+// For kernels bound by the shared-memory pipe (the recomputing backward): a third of the A-side operand traffic less.
+#ifdef NDP_EMU
+static inline
+#else
+static __device__ __forceinline__
+#endif
+void ndp_umma_gemm3_ar(unsigned tmem_d, NdpUmmaDesc a0, unsigned a_img, unsigned a_step,
+                       NdpUmmaDesc b0, unsigned b_img, unsigned b_step, int ksteps,
+                       unsigned idesc, bool accumulate) {
+    unsigned acc = accumulate ? 1u : 0u;
+    NdpUmmaDesc da = a0, db = b0;
+#pragma unroll 4
+    for (int ks = 0; ks < ksteps; ++ks) {
+        ndp_umma_f16_akeep(tmem_d, da, ndp_umma_desc_adv(db, b_img), idesc, acc);
+        ndp_umma_f16_areuse(tmem_d, da, db, idesc, 1u);
+        ndp_umma_f16(tmem_d, ndp_umma_desc_adv(da, a_img), db, idesc, 1u);
+        acc = 1u;
+        da = ndp_umma_desc_adv(da, a_step);
+        db = ndp_umma_desc_adv(db, b_step);
     }
 }
 

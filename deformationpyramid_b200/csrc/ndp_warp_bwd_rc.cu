@@ -124,10 +124,10 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
         ndp_mbar_init(&S.bar_mma[0], 1); ndp_mbar_init(&S.bar_mma[1], 1); ndp_mbar_init(&S.bar_fin, 1);
         ndp_stage_bulk(S.WB, wimg, NDP_SET128, &S.bar_w);                      // W_0 for the first F1
     }
-    // h0 role of a worker thread (gen_h0 below): 8 consecutive points (group hp8) of TWO features fA, fB = fA + 8.  All lanes
-    // of a warp share hp8 (their encoding loads are one broadcast per warp) and the 8 lanes of a quarter warp hold 8
-    // consecutive features, so the 16-byte image stores of a quarter warp fill all 32 banks.
-    const int hp8 = (tid >> 6) & 7, fA = ((tid & 63) >> 3) * 16 + (tid & 7), fB = fA + 8;
+    // h0 role of a worker thread (gen_h0 below): 8 consecutive points (group hp8) of TWO features fA, fB = fA + 64.  All lanes
+    // of a warp share hp8 (their encoding loads are one broadcast per warp), a warp's lanes hold 32 consecutive features
+    // (conflict-free loads of the input-layer weights from S.win) and a quarter warp's 16-byte image stores fill all 32 banks.
+    const int hp8 = (tid >> 6) & 7, fA = tid & 63, fB = fA + 64;
     float b_0 = 0.0f, b_1 = 0.0f;
     if (!issw) {
         // transposed head weight image: row i = ct & 127, 8-column chunk ct >> 7 (head rows 8 chunk .. 8 chunk + 7)
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
                 RC_READY(cc);
                 if (first && cc == 0) RC_WAIT_W();
                 NDP_TI(40 + cc * 2);
-                ndp_umma_gemm3(tmem + RC_ACC(cc), dW_k, NDP_IMG128, 2 * CS, ndp_umma_desc(cc ? A1 : A0, NDP_RS64, CS), NDP_IMG64, 2 * NDP_RS64, 8, id_f, false);
+                ndp_umma_gemm3_ar(tmem + RC_ACC(cc), dW_k, NDP_IMG128, 2 * CS, ndp_umma_desc(cc ? A1 : A0, NDP_RS64, CS), NDP_IMG64, 2 * NDP_RS64, 8, id_f, false);
                 ndp_umma_commit(&S.bar_mma[cc]);
                 NDP_TI(41 + cc * 2);
             }
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
                 NDP_TI(45 + cc * 3);
                 if (cc == 0) RC_WAIT_W();
                 NDP_TI(46 + cc * 3);
-                ndp_umma_gemm3(tmem + RC_ACC(cc), dW_k, NDP_IMG128, 2 * CS, ndp_umma_desc(cc ? B1 : B0, NDP_RS64, CS), NDP_IMG64, 2 * NDP_RS64, 8, id_f, false);
+                ndp_umma_gemm3_ar(tmem + RC_ACC(cc), dW_k, NDP_IMG128, 2 * CS, ndp_umma_desc(cc ? B1 : B0, NDP_RS64, CS), NDP_IMG64, 2 * NDP_RS64, 8, id_f, false);
                 ndp_umma_commit(&S.bar_mma[cc]);
                 NDP_TI(47 + cc * 3);
             }
@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
             for (int cc = 0; cc < 2; ++cc) {
                 RC_READY(cc);
                 const bool acc = !(first && cc == 0);
-                ndp_umma_gemm3(tmem + RC_ACC(cc), dHWT, NDP_IMG16F, 0, ndp_umma_desc(S.HG[cc], CS, NDP_RS16), NDP_IMG16H, 0, 1, id_h, false);
-                ndp_umma_gemm3(tmem + RC_DWH, ndp_umma_desc(cc ? A1 : A0, CS, NDP_RS64), NDP_IMG64, 2 * CS,
+                ndp_umma_gemm3_ar(tmem + RC_ACC(cc), dHWT, NDP_IMG16F, 0, ndp_umma_desc(S.HG[cc], CS, NDP_RS16), NDP_IMG16H, 0, 1, id_h, false);
+                ndp_umma_gemm3_ar(tmem + RC_DWH, ndp_umma_desc(cc ? A1 : A0, CS, NDP_RS64), NDP_IMG64, 2 * CS,
                                ndp_umma_desc(S.HG[cc], NDP_RS16, CS), NDP_IMG16H, 2 * NDP_RS16, 4, id_s, acc);
                 ndp_umma_commit(&S.bar_mma[cc]);
             }
@@ -226,10 +226,10 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
                 RC_READY(cc);
                 const bool acc = !(first && cc == 0);
                 NDP_TI(51 + cc * 3);
-                ndp_umma_gemm3(tmem + RC_ACC(cc), dW_mn, NDP_IMG128, 2 * RS, ndp_umma_desc(cc ? A1 : A0, NDP_RS64, CS), NDP_IMG64, 2 * NDP_RS64, 8, id_b, false);
+                ndp_umma_gemm3_ar(tmem + RC_ACC(cc), dW_mn, NDP_IMG128, 2 * RS, ndp_umma_desc(cc ? A1 : A0, NDP_RS64, CS), NDP_IMG64, 2 * NDP_RS64, 8, id_b, false);
                 if (cc == 1) ndp_umma_commit(&S.bar_wfree);       // W_1 is free once both chains' products have retired
                 NDP_TI(52 + cc * 3);
-                ndp_umma_gemm3(tmem + RC_DW1, ndp_umma_desc(cc ? B1 : B0, CS, NDP_RS64), NDP_IMG64, 2 * CS,
+                ndp_umma_gemm3_ar(tmem + RC_DW1, ndp_umma_desc(cc ? B1 : B0, CS, NDP_RS64), NDP_IMG64, 2 * CS,
                                ndp_umma_desc(cc ? A1 : A0, CS, NDP_RS64), NDP_IMG64, 2 * CS, 4, id_w, acc);
                 ndp_umma_commit(&S.bar_mma[cc]);
                 NDP_TI(53 + cc * 3);
@@ -241,10 +241,10 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
                 RC_READY(cc);
                 const bool acc = !(first && cc == 0);
                 NDP_TI(58 + cc * 2);
-                ndp_umma_gemm3(tmem + RC_DW0, ndp_umma_desc(cc ? A1 : A0, CS, NDP_RS64), NDP_IMG64, 2 * CS,
+                ndp_umma_gemm3_ar(tmem + RC_DW0, ndp_umma_desc(cc ? A1 : A0, CS, NDP_RS64), NDP_IMG64, 2 * CS,
                                ndp_umma_desc(cc ? B1 : B0, CS, NDP_RS64), NDP_IMG64, 2 * CS, 4, id_w, acc);
                 if (cc == 0) RC_WAIT_W();
-                ndp_umma_gemm3(tmem + RC_ACC(cc), dW_mn, NDP_IMG128, 2 * RS, ndp_umma_desc(cc ? B1 : B0, NDP_RS64, CS), NDP_IMG64, 2 * NDP_RS64, 8, id_b, false);
+                ndp_umma_gemm3_ar(tmem + RC_ACC(cc), dW_mn, NDP_IMG128, 2 * RS, ndp_umma_desc(cc ? B1 : B0, NDP_RS64, CS), NDP_IMG64, 2 * NDP_RS64, 8, id_b, false);
                 ndp_umma_commit(&S.bar_mma[cc]);
                 NDP_TI(59 + cc * 2);
             }
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
             for (int cc = 0; cc < 2; ++cc) {
                 RC_READY(cc);
                 const bool acc = !(first && cc == 0);
-                ndp_umma_gemm3(tmem + RC_DWIN, ndp_umma_desc(cc ? A1 : A0, CS, NDP_RS64), NDP_IMG64, 2 * CS,
+                ndp_umma_gemm3_ar(tmem + RC_DWIN, ndp_umma_desc(cc ? A1 : A0, CS, NDP_RS64), NDP_IMG64, 2 * CS,
                                ndp_umma_desc(S.E[cc], NDP_RS16, CS), NDP_IMG16H, 2 * NDP_RS16, 4, id_s, acc);
             }
         }

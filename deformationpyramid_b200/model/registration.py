@@ -73,7 +73,7 @@ class Registration():
     # ------------------------------------------------------------------------------------------
     def _get_solver(self, npairs: int, ns: int, nt: int, profile_every: Optional[int] = None) -> ops.Solver:
         c = self.config
-        profile = ops.execution_profile(npairs)
+        profile = ops.execution_profile(npairs, int(c.samples))
         for k in profile:                                     # explicit config keys win over the batch-size rule
             v = _cfg_get(c, k, None)
             if v is not None:

@@ -176,15 +176,25 @@ def adam_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, 
                                       _ptr(pack), _stream(lib, params)), "ndp_adam_step")
 
 
-def execution_profile(npairs: int) -> dict:
+def execution_profile(npairs: int, samples: int = 8192) -> dict:
     """The execution profile (ndp_solver_cfg::tiles_per_bwd_cta / fwd_rounds / streams) that
     Registration.register_batch, shard.evaluate and bench.py select from the number of pairs registered
-    concurrently: the throughput profile (fewer, longer tensor-core CTAs) from 24 pairs per call, the
-    library's latency-oriented defaults below.  Only regroups work; the gradient summation grouping follows
-    tiles_per_bwd_cta, so a pair's result is bit-reproducible for a given profile."""
-    if npairs >= 24:
-        return dict(tiles_per_bwd_cta=8, fwd_rounds=4, streams=4)
-    return dict(tiles_per_bwd_cta=0, fwd_rounds=0, streams=0)
+    concurrently and the number of sampled points: below 24 pairs the library's latency-oriented defaults;
+    from 24 pairs the throughput profile -- four stream groups and as many 128-sample tiles per tensor-core
+    CTA (backward: 1..16, forward: half of that in tile pairs) as still leaves every stream group's launch
+    about 64 CTAs (8 tiles at 32 pairs x 8192 samples, 16 at 64 pairs, 2 at 32 pairs x 2000 samples): longer
+    CTAs amortise the weight loads / gradient drains, the other groups' launches fill the remaining SMs.
+    Only regroups work; the gradient summation grouping follows tiles_per_bwd_cta, so a pair's result is
+    bit-reproducible for a given profile."""
+    if npairs < 24:
+        return dict(tiles_per_bwd_cta=0, fwd_rounds=0, streams=0)
+    streams = 4
+    tiles = (int(samples) + 127) // 128
+    want = (npairs // streams) * tiles // 64
+    tpc = 1
+    while tpc * 2 <= min(want, 16):
+        tpc *= 2
+    return dict(tiles_per_bwd_cta=tpc, fwd_rounds=max(1, tpc // 2), streams=streams)
 
 
 class Solver:

@@ -333,7 +333,7 @@ def check_headline_config_vs_oracle(lib, device, npairs=32, points=8192, levels=
     from deformationpyramid_b200.model.registration import _init_flat_cpu
     cfg = ndp_config(samples=points, m=levels, iters=iters, max_break_count=10 ** 9)
     specs = O.make_specs(cfg.depth, cfg.width, cfg.k0, levels, cfg.rotation_format)
-    prof = ops.execution_profile(npairs)
+    prof = ops.execution_profile(npairs, points)
     solver = ops.Solver(max_pairs=npairs, max_src_points=points, max_tgt_points=points, samples=points, levels=levels,
                         k0=cfg.k0, depth=cfg.depth, width=cfg.width, motion=cfg.motion_type,
                         rotation_format=cfg.rotation_format, iters=iters, max_break_count=10 ** 9,
