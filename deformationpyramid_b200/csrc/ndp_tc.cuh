@@ -87,6 +87,21 @@ __device__ __forceinline__ void ndp_split2(float x, unsigned& h1, unsigned& h2) 
     h1 = w1 & 0xffffu; h2 = w2 & 0xffffu;
 }
 
+// 16-byte shared-memory store / load that cannot degrade to a generic ST / LD when the compiler loses the address space of
+// a pointer (buffers selected at run time): explicit st.shared / ld.shared on the 32-bit shared address
+#ifdef NDP_EMU
+static inline void ndp_sts128(void* p, const uint4& v) { *(uint4*)p = v; }
+static inline uint4 ndp_lds128(const void* p) { return *(const uint4*)p; }
+#else
+__device__ __forceinline__ void ndp_sts128(void* p, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ndp_smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ndp_lds128(const void* p) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ndp_smem_u32(p)) : "memory");
+    return v;
+}
+#endif
 // split 8 consecutive values and store them as one 16-byte chunk in each of the two images
 __device__ __forceinline__ void ndp_store_chunk2(unsigned char* set, unsigned img_bytes, unsigned off, const float (&v)[8]) {
     uint4 p0, p1;
@@ -94,8 +109,8 @@ __device__ __forceinline__ void ndp_store_chunk2(unsigned char* set, unsigned im
     ndp_split2_pair(v[2], v[3], p0.y, p1.y);
     ndp_split2_pair(v[4], v[5], p0.z, p1.z);
     ndp_split2_pair(v[6], v[7], p0.w, p1.w);
-    *(uint4*)(set + off) = p0;
-    *(uint4*)(set + img_bytes + off) = p1;
+    ndp_sts128(set + off, p0);
+    ndp_sts128(set + img_bytes + off, p1);
 }
 // the 8 values of a 16-byte chunk re-assembled from the two images
 __device__ __forceinline__ void ndp_load_chunk2(const unsigned char* set, unsigned img_bytes, unsigned off, float (&v)[8]) {
@@ -382,6 +397,28 @@ void ndp_umma_gemm3_ar(unsigned tmem_d, NdpUmmaDesc a0, unsigned a_img, unsigned
         ndp_umma_f16(tmem_d, ndp_umma_desc_adv(da, a_img), db, idesc, 1u);
         acc = 1u;
         da = ndp_umma_desc_adv(da, a_step);
+        db = ndp_umma_desc_adv(db, b_step);
+    }
+}
+
+// A operand in TMEM with explicit geometry: the hi words of k-step j sit at ta0 + j * ta_step (8 columns = 16 fp16), the lo
+// words ta_img columns further; B from shared memory.  hi x lo, hi x hi, lo x hi per k-step.
+#ifdef NDP_EMU
+static inline
+#else
+static __device__ __forceinline__
+#endif
+void ndp_umma_gemm3_tak(unsigned tmem_d, unsigned ta0, unsigned ta_img, unsigned ta_step, NdpUmmaDesc b0, unsigned b_img,
+                        unsigned b_step, int ksteps, unsigned idesc, bool accumulate) {
+    unsigned acc = accumulate ? 1u : 0u, ta = ta0;
+    NdpUmmaDesc db = b0;
+#pragma unroll 4
+    for (int ks = 0; ks < ksteps; ++ks) {
+        ndp_umma_f16_ta(tmem_d, ta, ndp_umma_desc_adv(db, b_img), idesc, acc);
+        ndp_umma_f16_ta(tmem_d, ta, db, idesc, 1u);
+        ndp_umma_f16_ta(tmem_d, ta + ta_img, db, idesc, 1u);
+        acc = 1u;
+        ta += ta_step;
         db = ndp_umma_desc_adv(db, b_step);
     }
 }

@@ -314,8 +314,8 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
         };
         // relu'(h0) of this thread's epilogue cell (feature f, points col0 .. col0 + 15 of chain cc) from the h0 image
         auto h0_mask = [&](const unsigned char* img) -> unsigned {
-            return ndp_pos_mask8(*(const uint4*)(img + ndp_img_off(f, col0, NDP_RS64))) |
-                   (ndp_pos_mask8(*(const uint4*)(img + ndp_img_off(f, col0 + 8, NDP_RS64))) << 8);
+            return ndp_pos_mask8(ndp_lds128(img + ndp_img_off(f, col0, NDP_RS64))) |
+                   (ndp_pos_mask8(ndp_lds128(img + ndp_img_off(f, col0 + 8, NDP_RS64))) << 8);
         };
         // forward epilogue of chain cc: dst = relu(acc + bias) re-split into the image; returns relu' as a bit mask
         auto epi_fwd = [&](unsigned char* dst, int cc, float bias) -> unsigned {
@@ -373,8 +373,11 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
 
         for (int t = 0; t < ntl; ++t) {
             const int tile = tile0 + t;
-            unsigned char* const A[2] = {(t & 1) ? S.Y[0] : S.X[0], (t & 1) ? S.Y[1] : S.X[1]};     // h0 -> h2 -> delta2 -> h0 -> delta0
-            unsigned char* const B[2] = {(t & 1) ? S.X[0] : S.Y[0], (t & 1) ? S.X[1] : S.Y[1]};     // h1 -> delta1
+            // X and Y are adjacent members: the role swap is an OFFSET on one shared-memory object, so the compiler keeps the
+            // address space (a select between two pointers turns the epilogues' STS / LDS into generic ST / LD)
+            const int swp = (t & 1) * (int)sizeof(S.X);
+            unsigned char* const A[2] = {S.X[0] + swp, S.X[1] + swp};     // h0 -> h2 -> delta2 -> h0 -> delta0
+            unsigned char* const B[2] = {S.Y[0] - swp, S.Y[1] - swp};     // h1 -> delta1
             NDP_TR(2);
             // head-gradient images and fp32 encodings of both half tiles (HG: its readers, B2 of the previous tile, retired
             // long ago; A = the previous tile's delta1, dead since B0).  The encoding IMAGES are still being read by the
@@ -420,7 +423,7 @@ __global__ void __launch_bounds__(NDP_RC_THREADS, 1) ndp_warp_bwd_rc_kernel(NdpB
             }
 #pragma unroll
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) { wait_mma(cc); if (cc == 0) NDP_TR(8); dbs0 += epi_bwd(A[cc], cc, h0_mask(A[cc])); signal_ready(cc); }    // -> Bin
+            for (int cc = 0; cc < 2; ++cc) { wait_mma(cc); if (cc == 0) NDP_TR(8); dbs0 += epi_bwd(A[cc], cc, h0_mask(A[cc]));                 signal_ready(cc); }    // -> Bin
             NDP_TR(9);
             if (a.gx) {     // optional dL/dx: + the path through the positional encoding (ndp_head_grad_kernel wrote the direct part)
                 ndp_group_sync(1, 512);     // delta0 of both chains complete
