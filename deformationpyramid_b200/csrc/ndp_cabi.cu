@@ -366,6 +366,7 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
         delete s;
         return fail(NDP_E_INVALID, "mlp_mode must be 0..2, tiles_per_bwd_cta 0..16, fwd_rounds 0..8, streams 0..8");
     }
+    if (c->nn_mode < 0 || c->nn_mode > 2) { delete s; return fail(NDP_E_INVALID, "nn_mode must be 0 (culled search), 1 (brute force) or 2 (paired samples)"); }
     s->mlp_mode = c->mlp_mode == 0 ? g_mlp_mode : c->mlp_mode - 1;
     s->tpc = c->tiles_per_bwd_cta; s->fwd_rounds = c->fwd_rounds;
     if (cudaGetDevice(&s->device) != cudaSuccess) { delete s; return fail(NDP_E_CUDA, "cudaGetDevice failed"); }
@@ -454,7 +455,10 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
     g.in = s->src_raw; g.in_stride = (long long)s->NS * 3; g.idx = nullptr; g.idx_stride = 0; g.which = 0;
     g.out = s->src_c; g.out_stride = (long long)s->NS * 3; g.n = s->NS; g.counts = s->nscount;
     ndp_launch_gather_center(g, st);
-    const bool culled = c.nn_mode == 0;
+    const bool culled = c.nn_mode == 0, paired = c.nn_mode == 2;
+    if (paired)
+        for (int p = 0; p < npairs; ++p)
+            if (s->h_counts[p] != s->h_counts[s->B + p]) return fail(NDP_E_INVALID, "paired samples (nn_mode 2): src_samples must equal tgt_samples");
     g.idx = have_perm_s ? s->perm_s : nullptr; g.idx_stride = S;
     g.out = culled ? s->sraw : s->smp[0]; g.out_stride = S * 3; g.n = s->S; g.counts = s->ncount;
     ndp_launch_gather_center(g, st);
@@ -520,6 +524,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
         ch.loss_hist = s->loss_hist ? s->loss_hist + (long long)level * c.iters : nullptr;
         ch.hist_stride = (long long)c.levels * c.iters; ch.hist_cap = c.iters;
         ch.max_break_count = c.max_break_count; ch.break_ratio = (double)c.break_threshold_ratio;
+        ch.paired = paired ? 1 : 0;
 
         NdpBwdArgs b;
         b.lay = L; b.params = lvl_params; b.params_stride = pstride; b.pack = s->pack; b.pack_stride = s->packn;
@@ -584,7 +589,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
                 if (s->mlp_mode == 0) ndp_launch_fwd_tc(f, q); else ndp_launch_fwd(f, q);
                 if (pg) CK(cudaEventRecord(ev[1], q));
                 if (s->dbg_skip & 2) {} else
-                if (culled) { pn.fuse = &ch; ndp_launch_nn_pruned(pn, q); } else ndp_launch_nn(ch.nn, q);   // culled: search + Chamfer epilogue in one launch
+                if (culled) { pn.fuse = &ch; ndp_launch_nn_pruned(pn, q); } else if (!paired) ndp_launch_nn(ch.nn, q);   // culled: search + Chamfer epilogue in one launch
                 if (pg) CK(cudaEventRecord(ev[2], q));
                 if (!culled) ndp_launch_chamfer_reduce(ch, q);
                 if (pg) CK(cudaEventRecord(ev[3], q));
@@ -593,7 +598,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
                 if (pg) CK(cudaEventRecord(ev[4], q));
                 if (!(s->dbg_skip & 8)) ndp_launch_adam(ad, q);
                 if (pg) CK(cudaEventRecord(ev[5], q));
-                s->launches += ((s->mlp_mode == 0) ? 6 : 5) - (culled ? 1 : 0);
+                s->launches += ((s->mlp_mode == 0) ? 6 : 5) - ((culled || paired) ? 1 : 0);
             }
             if ((it + 1) % poll == 0 && it + 1 < c.iters) {
                 if (int e = join()) return e;
@@ -743,6 +748,7 @@ extern "C" int ndp_solver_last_nn(ndp_solver* s, int32_t pair, int64_t* idx_x, f
     cudaStream_t st = (cudaStream_t)stream;
     const long long S = s->S;
     const int n = s->h_counts[pair], m = s->h_counts[s->B + pair];
+    if (s->cfg.nn_mode == 2) return fail(NDP_E_INVALID, "paired samples (nn_mode 2): there is no nearest-neighbour search to report");
     const bool culled = s->cfg.nn_mode == 0;
     NdpNnExportArgs e;
     e.part = s->nnpart + (long long)pair * 2LL * s->plan.chunks * s->plan.qpitch;

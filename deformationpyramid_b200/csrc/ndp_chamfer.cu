@@ -141,6 +141,16 @@ __global__ void __launch_bounds__(NDP_CR_THREADS) ndp_chamfer_reduce_kernel(NdpC
     const int i = blockIdx.x * NDP_CR_THREADS + tid;
     double sx = 0.0, sy = 0.0;
 
+    if (a.paired) {
+        if (i < n) {   // landmark term: d/dx_i mean_k |x_k - y_k|^2 = 2 (x_i - y_i) / n   (registration.py:200-203)
+            const float dx = X[(long long)i * 3] - Y[(long long)i * 3], dy = X[(long long)i * 3 + 1] - Y[(long long)i * 3 + 1],
+                        dz = X[(long long)i * 3 + 2] - Y[(long long)i * 3 + 2];
+            const float sc = 2.0f / (float)n;
+            float* gp = a.gx + (long long)pair * a.gx_stride + (long long)i * 3;
+            gp[0] = dx * sc; gp[1] = dy * sc; gp[2] = dz * sc;
+            sx = (double)(dx * dx + dy * dy + dz * dz);
+        }
+    } else {
     if (i < n) {   // direction x -> y : point i owns its gradient slot
         float d; int j;
         ndp_combine(part0, ndp_nn_chunks_for(m, g.chunk_targets), g.qpitch, i, d, j);
@@ -176,6 +186,7 @@ __global__ void __launch_bounds__(NDP_CR_THREADS) ndp_chamfer_reduce_kernel(NdpC
             }
         }
     }
+    }   // !paired
     // block reduction of the two L1 sums (fixed tree => deterministic)
     red[0][tid] = sx; red[1][tid] = sy;
     __syncthreads();
@@ -196,7 +207,7 @@ __global__ void __launch_bounds__(NDP_CR_THREADS) ndp_chamfer_reduce_kernel(NdpC
         __threadfence();
         double tx = 0.0, ty = 0.0;
         for (int b = 0; b < nblocks; ++b) { tx += ((volatile double*)bs)[b * 2]; ty += ((volatile double*)bs)[b * 2 + 1]; }
-        const float loss = (float)tx / (float)n + (float)ty / (float)m;
+        const float loss = a.paired ? (float)tx / (float)n : (float)tx / (float)n + (float)ty / (float)m;
         a.loss_out[pair] = loss;
         a.counters[pair] = 0;
         if (a.state) {

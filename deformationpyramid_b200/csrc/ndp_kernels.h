@@ -116,6 +116,8 @@ struct NdpChamferArgs {
     NdpPairState* state;                              // early-stop update, or null
     float* loss_hist; long long hist_stride; int hist_cap;   // optional loss curve: loss_hist[pair*stride + eval], eval < cap
     int max_break_count; double break_ratio;
+    int paired = 0;                                   // 1: no search -- source sample i is matched to target sample i and the loss is
+                                                      // mean_i |x_i - y_i|^2 (the landmark term of LNDP, model/registration.py:200-203)
 };
 void ndp_launch_chamfer_reduce(const NdpChamferArgs& a, cudaStream_t s);
 

@@ -71,15 +71,18 @@ class Registration():
         raise KeyError()
 
     # ------------------------------------------------------------------------------------------
-    def _get_solver(self, npairs: int, ns: int, nt: int, profile_every: Optional[int] = None) -> ops.Solver:
+    def _get_solver(self, npairs: int, ns: int, nt: int, profile_every: Optional[int] = None,
+                    nn_mode: Optional[int] = None, samples: Optional[int] = None) -> ops.Solver:
         c = self.config
-        profile = ops.execution_profile(npairs, int(c.samples))
+        samples = int(c.samples if samples is None else samples)
+        nn_mode = int(_cfg_get(c, "nn_mode", 0) or 0) if nn_mode is None else int(nn_mode)
+        profile = ops.execution_profile(npairs, samples)
         for k in profile:                                     # explicit config keys win over the batch-size rule
             v = _cfg_get(c, k, None)
             if v is not None:
                 profile[k] = int(v)
         prof_every = int(_cfg_get(c, "profile_every", 0) or 0) if profile_every is None else int(profile_every)
-        key = (c.samples, c.m, c.k0, c.depth, c.width, c.motion_type, c.rotation_format, c.iters,
+        key = (samples, nn_mode, c.m, c.k0, c.depth, c.width, c.motion_type, c.rotation_format, c.iters,
                c.max_break_count, c.break_threshold_ratio, c.lr, str(self.src_pcd.device), tuple(sorted(profile.items())),
                prof_every)
         s = self._solver
@@ -89,11 +92,11 @@ class Registration():
                 s.close()
             cap = lambda v: int(max(v, 1024) * 1.25)
             self._solver = ops.Solver(max_pairs=npairs, max_src_points=cap(ns), max_tgt_points=cap(nt),
-                                      samples=c.samples, levels=c.m, k0=c.k0, depth=c.depth, width=c.width,
+                                      samples=samples, levels=c.m, k0=c.k0, depth=c.depth, width=c.width,
                                       motion=c.motion_type, rotation_format=c.rotation_format, iters=c.iters,
                                       max_break_count=c.max_break_count,
                                       break_threshold_ratio=c.break_threshold_ratio, lr=c.lr, trunc=1e9,
-                                      nn_mode=int(_cfg_get(c, "nn_mode", 0) or 0), profile_every=prof_every,
+                                      nn_mode=nn_mode, profile_every=prof_every,
                                       device=self.src_pcd.device, **profile)
             self._solver_key = key
         return self._solver
@@ -108,6 +111,8 @@ class Registration():
         config = self.config
         if visualize:
             raise NotImplementedError("visualisation (mayavi, utils/vis.py) is outside the scope of this package")
+        if self.landmarks is not None and config.w_reg == 0 and float(_cfg_get(config, "w_cd", 0.0) or 0.0) == 0.0:
+            return self._optimize_landmarks_fused(timer)     # config/LNDP.yaml as shipped: landmark term only
         if self.landmarks is not None or config.w_reg > 0:
             return self._optimize_stepwise(timer)
 
@@ -133,6 +138,46 @@ class Registration():
         self.NDP, self.last_iters, self.last_losses = NDP, iters[0], losses[0]
         iter_cnt = {}
         return warped[0], iter_cnt, timer
+
+    def _optimize_landmarks_fused(self, timer=None):
+        """LNDP with the weights of config/LNDP.yaml (w_cd = 0, w_reg = 0): only the landmark term
+        mean_i |warp(src_ldmk_i) - tgt_ldmk_i|^2 of registration.py:187-203 drives the pyramid.  Runs in the fused
+        driver in paired-sample mode (ndp_solver_cfg::nn_mode = 2): the "samples" are the landmark points, source
+        sample i is matched to target sample i, the early-stop rule is evaluated on the device -- no host sync per
+        iteration.  The solver centres the clouds it is given on their own means; the reference centres the
+        landmarks on the means of the FULL clouds (:150-153, :163-165), so centred clouds with a balancing point
+        (mean exactly as computed = 0 to rounding) are passed, as in shape_transfer._register_leading_samples."""
+        config = self.config
+        NDP = self._build_pyramid()                              # consumes the RNG first (:133-140)
+        self.src_pcd = self.src_pcd.to(self.device)
+        src, tgt = self.src_pcd.contiguous(), self.tgt_pcd.contiguous()
+        if src.dtype != torch.float32 or tgt.dtype != torch.float32:
+            raise ValueError("float32 point clouds expected")
+        torch.randperm(src.shape[0]); torch.randperm(tgt.shape[0])      # :156-157 -- drawn, unused with w_cd = 0
+        dev = src.device
+        src_mean, tgt_mean = src.mean(dim=0, keepdim=True), tgt.to(dev).mean(dim=0, keepdim=True)
+        ls = self.landmarks[0].to(dev).float() - src_mean
+        lt = self.landmarks[1].to(dev).float() - tgt_mean
+        if ls.shape != lt.shape or ls.dim() != 2 or ls.shape[1] != 3:
+            raise ValueError("landmarks must be two [L, 3] arrays of matched points")
+        n_src, nl = src.shape[0], ls.shape[0]
+        body = torch.cat([src - src_mean, ls])
+        src_in = torch.cat([body, -body.sum(dim=0, keepdim=True)]).contiguous()
+        tgt_in = torch.cat([lt, -lt.sum(dim=0, keepdim=True)]).contiguous()
+        sp = torch.arange(n_src, n_src + nl, dtype=torch.int32, device=dev)
+        tp = torch.arange(nl, dtype=torch.int32, device=dev)
+        flat = NDP.flat_parameters()
+        solver = self._get_solver(1, src_in.shape[0], tgt_in.shape[0], profile_every=8 if timer else None,
+                                  nn_mode=2, samples=max(int(config.samples), nl))
+        prof0 = solver.profile() if timer else None
+        if timer: timer.tic("ndp_fused")
+        warped, iters, losses = solver.register([src_in], [tgt_in], [flat], [sp], [tp], src_samples=[nl], tgt_samples=[nl])
+        if timer: timer.toc("ndp_fused")
+        if timer: _feed_timer(timer, solver, prof0, int(iters.sum()))
+        NDP.load_flat_parameters(flat)
+        NDP.gradient_setup(optimized_level=-1)
+        self.NDP, self.last_iters, self.last_losses = NDP, iters[0], losses[0]
+        return warped[0][:n_src] + tgt_mean, {}, timer
 
     # ------------------------------------------------------------------------------------------
     def register_batch(self, pairs: Sequence[Tuple[torch.Tensor, torch.Tensor]], seeds: Optional[Sequence[int]] = None,

@@ -124,7 +124,11 @@ typedef struct ndp_solver_cfg {
     int32_t profile_every;      /* k > 0: bracket the kernels of every k-th iteration with CUDA
                                    events on `stream` (see ndp_solver_profile); 0: off            */
     int32_t nn_mode;            /* 0: exact culled search (Morton blocks + boxes + temporal seeds),
-                                   1: plain brute force; identical results                        */
+                                   1: plain brute force; identical results.
+                                   2: PAIRED samples, no search: source sample i is matched to target
+                                   sample i and the loss is mean_i |x'_i - y_i|^2 -- the landmark objective
+                                   of LNDP with w_cd = 0 (model/registration.py:200-203, config/LNDP.yaml);
+                                   src_samples must equal tgt_samples                             */
     /* ---- execution profile (0 = default everywhere).  These regroup work; none changes the arithmetic
      * of a single product, but tiles_per_bwd_cta sets the summation grouping of the gradients, so results
      * are bit-reproducible for a given value.                                                       */

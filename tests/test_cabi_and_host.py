@@ -160,3 +160,14 @@ def test_install_as_model_aliases():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_execution_profile_rule():
+    """ops.execution_profile(pairs, samples): latency defaults below 24 pairs; from 24 pairs four stream groups and as many
+    128-sample tiles per backward CTA (power of two, 1..16) as leaves ~64 CTAs per stream-group launch."""
+    from deformationpyramid_b200.ops import execution_profile as e
+    assert e(8, 8192) == dict(tiles_per_bwd_cta=0, fwd_rounds=0, streams=0)
+    assert e(32, 8192) == dict(tiles_per_bwd_cta=8, fwd_rounds=4, streams=4)
+    assert e(64, 8192) == dict(tiles_per_bwd_cta=16, fwd_rounds=8, streams=4)
+    assert e(32, 2000) == dict(tiles_per_bwd_cta=2, fwd_rounds=1, streams=4)
+    assert e(512, 8192)["tiles_per_bwd_cta"] == 16 and e(24, 200)["tiles_per_bwd_cta"] == 1

@@ -146,6 +146,38 @@ def test_registration_stepwise_landmarks_and_nonrigidity():
     assert rel(warped2.cpu().numpy(), ref2.warped.numpy()) < 1e-3
 
 
+def test_registration_landmarks_fused_route_matches_oracle():
+    """config/LNDP.yaml as shipped (w_cd = 0, w_reg = 0): the landmark objective of registration.py:187-203 runs in the
+    fused driver (paired samples, early stop on the device) -- warped cloud, Adam steps and last loss per level against
+    the oracle, whose landmark branch is pinned on the unmodified reference (tests/golden/branches.npz)."""
+    from deformationpyramid_b200.model.registration import Registration
+    src, tgt = make_pair(34, 900, 800)
+    g = torch.Generator().manual_seed(5)
+    pick = torch.randperm(900, generator=g)[:150]
+    ldmk_s = src[pick].clone()
+    ldmk_t = ldmk_s * 1.02 + torch.tensor([0.03, -0.02, 0.01]) + 0.002 * torch.randn(150, 3, generator=g)
+    for iters, mbc in ((6, 10 ** 9), (60, 3)):                      # fixed iterations; early stop live
+        cfg = ndp_config(samples=300, m=3, iters=iters, max_break_count=mbc, w_cd=0.0, device=0)
+        torch.manual_seed(11)
+        reg = Registration(cfg)
+        reg.load_pcds(src, tgt, landmarks=(ldmk_s.cuda(), ldmk_t.cuda()))
+        warped, _, _ = reg.register()
+        assert reg._solver.cfg.nn_mode == 2                           # the fused route, not the stepwise one
+        cfgo = O.NDPConfig(iters=iters, samples=300, m=3, w_cd=0.0, max_break_count=mbc)
+        torch.manual_seed(11)
+        ref = O.optimize_pair(cfgo, src, tgt, landmarks=(ldmk_s, ldmk_t))
+        assert warped.shape == (900, 3)
+        if mbc > 10 ** 6:
+            assert [int(v) for v in reg.last_iters] == ref.iters_per_level
+            assert rel(warped.cpu().numpy(), ref.warped.numpy()) < 1e-3
+            for a, b in zip(reg.last_losses.tolist(), ref.loss_per_level):
+                assert abs(a - b) <= 1e-3 * abs(b)
+        else:                                                         # free-running with the stop rule: counts may differ by the
+            for a, b in zip([int(v) for v in reg.last_iters], ref.iters_per_level):   # plateau's last few steps
+                assert abs(a - b) <= 3, (reg.last_iters, ref.iters_per_level)
+            assert rel(warped.cpu().numpy(), ref.warped.numpy()) < 5e-3
+
+
 def test_register_batch_seeded_is_batch_independent():
     from deformationpyramid_b200.model.registration import Registration
     cfg = ndp_config(samples=256, m=2, iters=10, device=0)
