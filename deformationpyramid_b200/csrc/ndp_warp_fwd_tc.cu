@@ -280,6 +280,7 @@ struct FwdTc2Smem {
     unsigned char HW[2 * NDP_HWIMG];       // [16 head rows][128]: head weights, rows >= head_dim 0 (operand B of the heads)
     float xs[2][NDP_TP * 4];
     float hb[16];
+    float bias[3][NDP_W];                  // b_in, b_0, b_1: every thread needs 64 of them per epilogue (broadcast LDS instead of LDG + address arithmetic)
     NdpMbar bar_w[2], bar_mma[2];          // one arrival barrier per resident weight set (the first is needed first)
     int pipe_lock;                         // the group that holds it issues its MMA batch alone (see ndp_pipe_acquire)
     unsigned tmem_slot, pad[2];
@@ -332,6 +333,10 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc2_kernel
         NDP_T(2);
     }
     if (tid < 16) S.hb[tid] = (tid < HD) ? __ldg(params + L.head_b[tid]) : 0.0f;
+    if (tid < 3 * NDP_W) {
+        const int l = tid >> 7, o = tid & (NDP_W - 1);
+        S.bias[l][o] = (l == 0) ? __ldg(params + L.off_b_in + o) : (l - 1 < LH ? __ldg(params + L.off_b[l - 1] + o) : 0.0f);
+    }
     if (tid < 256) {            // input-layer weight image: row o = tid / 2, 8-column chunk tid & 1
         const int o = tid >> 1, c8 = tid & 1;
         float v[8];
@@ -410,7 +415,7 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc2_kernel
             ndp_group_sync(1 + g, NDP_GROUP);
             ndp_tc_fence_after();
             NDP_T(9 + 4 * s);
-            const float* bias = params + (s == 0 ? L.off_b_in : L.off_b[s - 1]);
+            const float* bias = S.bias[s];
             unsigned char* gimg = gact ? gact + (long long)s * NDP_SET128 : nullptr;
 #pragma unroll 1
             for (int c32 = 0; c32 < 2; ++c32) {
@@ -420,7 +425,7 @@ __global__ void __launch_bounds__(NDP_FWD_TC_THREADS, 1) ndp_warp_fwd_tc2_kernel
                 ndp_tmem_ld32(tlane + TM2_ACC + col0, v);
 #pragma unroll
                 for (int s8 = 0; s8 < 4; ++s8) {
-                    const float4 b0 = __ldg((const float4*)(bias + col0 + s8 * 8)), b1 = __ldg((const float4*)(bias + col0 + s8 * 8 + 4));
+                    const float4 b0 = *(const float4*)(bias + col0 + s8 * 8), b1 = *(const float4*)(bias + col0 + s8 * 8 + 4);
                     if (!SAVE) {         // nothing reads relu' back from an image (the recomputing backward): plain max, packed adds
                         ndp_bias_relu_split2(v[s8 * 8 + 0], v[s8 * 8 + 1], b0.x, b0.y, hi[s8 * 4 + 0], lo[s8 * 4 + 0]);
                         ndp_bias_relu_split2(v[s8 * 8 + 2], v[s8 * 8 + 3], b0.z, b0.w, hi[s8 * 4 + 1], lo[s8 * 4 + 1]);

@@ -341,3 +341,29 @@ def test_registration_timer_keys_of_the_fused_route():
         t = timer.timers[key]
         assert t.calls == 120 and 0.0 < t.total_time < timer.timers["registration"].total_time, (key, t.calls, t.total_time)
     assert all(isinstance(s, str) for s in timer.get_strings())
+
+
+def test_solver_nn_stats_and_paired_mode_checks():
+    """ndp_solver_nn_stats (work counters of the culled search) and the argument checks of the paired-sample mode."""
+    from deformationpyramid_b200 import ops
+    specs = O.make_specs(3, 128, -8, 1, "axis_angle")
+    src, tgt = make_pair(3, 1000, 900)
+    torch.manual_seed(0)
+    flat = torch.cat([O.flatten_params(s, O.init_params(s)) for s in specs]).to(DEV)
+    common = dict(max_pairs=1, max_src_points=1000, max_tgt_points=900, samples=512, levels=1, k0=-8, depth=3, width=128,
+                  motion="SE3", rotation_format="axis_angle", iters=4, max_break_count=10 ** 9, break_threshold_ratio=0.001,
+                  lr=0.01)
+    solver = ops.Solver(profile_every=1, **common)
+    solver.register([src.to(DEV)], [tgt.to(DEV)], [flat.clone()])
+    evals, qblocks, max_blocks = solver.nn_stats()
+    assert qblocks == 4 * 2 * 16                       # 4 searches x 2 directions x 512 / 32 query blocks
+    assert evals % 1024 == 0 and 0 < evals <= qblocks * 16 * 1024 and 1 <= max_blocks <= 16
+    assert evals / 1024 / qblocks <= max_blocks        # mean blocks per warp <= the slowest warp's
+    solver.close()
+    paired = ops.Solver(nn_mode=2, **common)
+    with pytest.raises((ValueError, RuntimeError)):    # paired samples need equal counts (900-point target < 1000-point source: 512 vs 512 ok,
+        paired.register([src.to(DEV)], [tgt.to(DEV)], [flat.clone()], src_samples=[300], tgt_samples=[200])
+    paired.register([src.to(DEV)], [tgt.to(DEV)], [flat.clone()], src_samples=[200], tgt_samples=[200])
+    with pytest.raises((ValueError, RuntimeError)):
+        paired.last_nn(0)                               # there is no search to report
+    paired.close()
