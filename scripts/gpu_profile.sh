@@ -14,6 +14,9 @@ for Q in 8 16; do
 done
 timeout 900 python bench.py --mlp fp32 --steps 1 --warmup 3 --pairs 16 --no-cpu-baseline --no-mode-b > $OUT/bench_fp32pipes_pairs16.json 2> $OUT/bench_fp32pipes.err; echo "fp32-pipe bench exit $?"
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python __graft_entry__.py --smoke > $OUT/sanitizer_memcheck.log 2>&1; echo "memcheck exit $?"; tail -2 $OUT/sanitizer_memcheck.log
+for T in racecheck synccheck; do
+  timeout 900 compute-sanitizer --tool $T --error-exitcode 7 python __graft_entry__.py --smoke > $OUT/sanitizer_$T.log 2>&1; echo "$T exit $?"; tail -2 $OUT/sanitizer_$T.log
+done
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 1 --warmup 1 --pairs $P --iters 6 --no-cpu-baseline --no-mode-b > $OUT/ncu_launches.log 2>&1; echo "ncu launches exit $?"
 for K in ndp_warp_bwd_rc_kernel ndp_warp_fwd_tc2_kernel ndp_nn_pruned_kernel ndp_reduce_adam_kernel ndp_head_grad_kernel; do
