@@ -219,7 +219,7 @@ class Registration():
         if seeds is not None and n > 1:
             import os
             from concurrent.futures import ThreadPoolExecutor
-            with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1, n)) as pool:
+            with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1, n)) as pool:
                 perms = list(pool.map(one, range(n)))
         else:
             perms = [one(p) for p in range(n)]
@@ -395,30 +395,50 @@ def _params_per_pair(config) -> int:
     return config.m * sum(o * i + o for o, i in _level_linears(config))
 
 
-def _init_flat_cpu(config, generator=None, out=None) -> torch.Tensor:
-    """Fresh weights of a whole pyramid drawn on the CPU in the reference's RNG order, flattened
-    (level 0 first), without building nn.Modules: per level the nn.Linear default initialisation of every
-    sub-module in construction order (weight U(+-1/sqrt(fan_in)) = kaiming_uniform(a=sqrt(5)), then bias
-    U(+-1/sqrt(fan_in)); nets.py:75-101), then Xavier uniform over every weight in parameters() order
-    (nets.py:180-183).  Consumes torch's global CPU generator exactly like `Deformation_Pyramid(...)` does
-    (tests/test_cabi_and_host.py compares the two bit for bit) -- or `generator`, a private stream."""
+_INIT_PLANS = {}
+
+
+def _init_plan(config):
+    """Per configuration: where every final parameter of a level sits in the level's sequence of random draws, and
+    its range.  The reference draws, per level, nn.Linear's default initialisation of every sub-module in construction
+    order (weight U(+-1/sqrt(fan_in)) = kaiming_uniform(a=sqrt(5)), then bias U(+-1/sqrt(fan_in)); nets.py:75-101) and
+    then Xavier uniform over every weight in parameters() order (nets.py:180-183): the weights are drawn twice, only the
+    second draw survives."""
     import math
     linears = _level_linears(config)
-    per_level = sum(o * i + o for o, i in linears)
-    flat = out if out is not None else torch.empty(config.m * per_level, dtype=torch.float32)
-    off = 0
-    for _ in range(config.m):
-        views = []
+    key = tuple(linears)
+    plan = _INIT_PLANS.get(key)
+    if plan is None:
+        per_level = sum(o * i + o for o, i in linears)
+        first, pos = [], 0
         for o, i in linears:
-            b = 1.0 / math.sqrt(i)
-            w = flat[off:off + o * i].view(o, i); off += o * i
-            bias = flat[off:off + o]; off += o
-            w.uniform_(-b, b, generator=generator)
-            bias.uniform_(-b, b, generator=generator)
-            views.append(w)
-        for w in views:
-            a = math.sqrt(3.0) * math.sqrt(2.0 / float(w.shape[0] + w.shape[1]))     # xavier_uniform_, gain 1
-            w.uniform_(-a, a, generator=generator)
+            first.append((pos, pos + o * i))              # (first weight draw, bias draw)
+            pos += o * i + o
+        idx = torch.empty(per_level, dtype=torch.long)
+        a = torch.empty(per_level, dtype=torch.float32)
+        p = 0
+        for (o, i), (_, bpos) in zip(linears, first):
+            idx[p:p + o * i] = torch.arange(pos, pos + o * i); pos += o * i                  # the Xavier draw
+            a[p:p + o * i] = math.sqrt(3.0) * math.sqrt(2.0 / float(o + i)); p += o * i      # xavier_uniform_, gain 1
+            idx[p:p + o] = torch.arange(bpos, bpos + o)
+            a[p:p + o] = 1.0 / math.sqrt(i); p += o
+        plan = _INIT_PLANS[key] = (per_level, pos, idx, 2.0 * a, -a)
+    return plan
+
+
+def _init_flat_cpu(config, generator=None, out=None) -> torch.Tensor:
+    """Fresh weights of a whole pyramid drawn on the CPU in the reference's RNG order, flattened (level 0 first),
+    without building nn.Modules.  ONE uniform_(0, 1) call draws the whole sequence (torch's CPU generator hands out one
+    32-bit word per float32 sample whatever the tensor, so the stream is the reference's), then the surviving draws are
+    gathered and mapped to their ranges with the same fused `x * (to - from) + from` torch's uniform_ evaluates: values
+    and final generator state are bit-identical to `Deformation_Pyramid(...)` (tests/test_cabi_and_host.py compares the
+    two bit for bit).  Three long kernels instead of 135 short ones per pair: the per-pair preparation threads of
+    register_batch no longer queue behind the interpreter lock.  Consumes torch's global CPU generator -- or
+    `generator`, a private stream."""
+    per_level, seq_len, idx, scale, lo = _init_plan(config)
+    flat = out if out is not None else torch.empty(config.m * per_level, dtype=torch.float32)
+    u = torch.empty(config.m, seq_len, dtype=torch.float32).uniform_(0.0, 1.0, generator=generator)
+    torch.addcmul(lo, torch.index_select(u, 1, idx), scale, out=flat.view(config.m, per_level))
     return flat
 
 
