@@ -208,9 +208,12 @@ def test_solver_nn_indices_bit_exact_full_size(lib):
 
 
 def test_headline_config_vs_oracle(lib):
-    """32 pairs x 8192 samples x 9 levels under the bench profile: pairs 0 and 31 (first / last stream group) vs the oracle."""
+    """bench.py's default step -- 64 pairs x 8192 samples x 9 levels under the execution profile it selects (16 tiles per
+    backward CTA, 8 forward rounds, 4 stream groups): pairs 0 and 63 (first / last stream group) vs the oracle; and the
+    32-pair profile (8 tiles per backward CTA)."""
     from parity_cases import check_headline_config_vs_oracle
-    check_headline_config_vs_oracle(lib, DEV)
+    check_headline_config_vs_oracle(lib, DEV, npairs=64, check=(0, 63))
+    check_headline_config_vs_oracle(lib, DEV, npairs=32, check=(31,))
 
 
 def test_solver_repeatable_with_early_stop(lib):
