@@ -294,6 +294,12 @@ struct ndp_solver {
     NdpPairState* state = nullptr;
     // host (pinned)
     NdpPairState* h_state = nullptr;
+    // early-stop polling that does not drain the pipeline: a snapshot of the pair states is copied on its own stream behind
+    // events of the stream groups and looked at one poll interval later (the device-side stop is authoritative: kernels of
+    // stopped pairs return at once, the host merely stops launching)
+    NdpPairState* h_poll = nullptr;
+    cudaStream_t st_poll = nullptr;
+    cudaEvent_t ev_poll_g[NDP_MAX_STREAMS] = {}, ev_poll_done = nullptr;
     int* h_counts = nullptr;
     long long launches = 0;
     std::vector<void*> allocs;
@@ -343,6 +349,11 @@ extern "C" void ndp_solver_destroy(ndp_solver* s) {
         if (s->st_extra[i]) cudaStreamDestroy(s->st_extra[i]);
     }
     if (s->h_state) cudaFreeHost(s->h_state);
+    if (s->h_poll) cudaFreeHost(s->h_poll);
+    if (s->st_poll) cudaStreamDestroy(s->st_poll);
+    if (s->ev_poll_done) cudaEventDestroy(s->ev_poll_done);
+    for (int i = 0; i < NDP_MAX_STREAMS; ++i)
+        if (s->ev_poll_g[i]) cudaEventDestroy(s->ev_poll_g[i]);
     if (s->h_counts) cudaFreeHost(s->h_counts);
     delete s;
 }
@@ -396,6 +407,12 @@ extern "C" int ndp_solver_create(const ndp_solver_cfg* c, ndp_solver** out) {
     if (c->profile_every > 0 && c->nn_mode == 0) DA(nnstats, 4);
 #undef DA
     if (!e && cudaMallocHost((void**)&s->h_state, sizeof(NdpPairState) * B) != cudaSuccess) e = fail(NDP_E_NOMEM, "cudaMallocHost failed");
+    if (!e && cudaMallocHost((void**)&s->h_poll, sizeof(NdpPairState) * B) != cudaSuccess) e = fail(NDP_E_NOMEM, "cudaMallocHost failed");
+    if (!e && (cudaStreamCreateWithFlags(&s->st_poll, cudaStreamNonBlocking) != cudaSuccess ||
+               cudaEventCreateWithFlags(&s->ev_poll_done, cudaEventDisableTiming) != cudaSuccess))
+        e = fail(NDP_E_CUDA, "cannot create the polling stream");
+    for (int i = 0; !e && i < NDP_MAX_STREAMS; ++i)
+        if (cudaEventCreateWithFlags(&s->ev_poll_g[i], cudaEventDisableTiming) != cudaSuccess) e = fail(NDP_E_CUDA, "cudaEventCreate failed");
     if (!e && cudaMallocHost((void**)&s->h_counts, sizeof(int) * B * 4) != cudaSuccess) e = fail(NDP_E_NOMEM, "cudaMallocHost failed");
     if (!e && cudaMemset(s->counters, 0, sizeof(int) * B) != cudaSuccess) e = fail(NDP_E_CUDA, "cudaMemset failed");
     if (!e) {
@@ -567,6 +584,7 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
             }
             return NDP_OK;
         };
+        bool poll_pending = false;
         for (int it = 0; it < c.iters; ++it) {
             const bool prof = c.profile_every > 0 && (it % c.profile_every) == c.profile_every / 2;
             cudaEvent_t* ev = nullptr;
@@ -601,15 +619,22 @@ static int solver_run(ndp_solver* s, int npairs, bool have_perm_s, bool have_per
                 s->launches += ((s->mlp_mode == 0) ? 6 : 5) - ((culled || paired) ? 1 : 0);
             }
             if ((it + 1) % poll == 0 && it + 1 < c.iters) {
-                if (int e = join()) return e;
-                CK(cudaMemcpyAsync(s->h_state, s->state, sizeof(NdpPairState) * npairs, cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                if (int e = prof_flush(s)) return e;
-                bool all = true;
-                for (int p = 0; p < npairs; ++p) all = all && s->h_state[p].stopped;
-                if (all) break;
+                if (poll_pending) {         // the snapshot taken one interval ago (complete by now in all but pathological cases)
+                    CK(cudaEventSynchronize(s->ev_poll_done));
+                    bool all = true;
+                    for (int p = 0; p < npairs; ++p) all = all && s->h_poll[p].stopped;
+                    if (all) break;
+                }
+                for (int g = 0; g < ng; ++g) {
+                    CK(cudaEventRecord(s->ev_poll_g[g], gs[g]));
+                    CK(cudaStreamWaitEvent(s->st_poll, s->ev_poll_g[g], 0));
+                }
+                CK(cudaMemcpyAsync(s->h_poll, s->state, sizeof(NdpPairState) * npairs, cudaMemcpyDeviceToHost, s->st_poll));
+                CK(cudaEventRecord(s->ev_poll_done, s->st_poll));
+                poll_pending = true;
             }
         }
+        if (poll_pending) CK(cudaStreamSynchronize(s->st_poll));
         if (int e = join()) return e;
         CK(cudaMemcpyAsync(s->h_state, s->state, sizeof(NdpPairState) * npairs, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));

@@ -214,6 +214,7 @@ static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new double(0.0)
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new double(0.0); return cudaSuccess; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = 0) {
     struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); *e = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; return cudaSuccess;
 }
