@@ -312,6 +312,24 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     solver.close()
 
+    # ---- the same kernels with the GPU to themselves: ONE stream group (every launch covers all B pairs and is the only
+    #      work on the device), 24 iterations per level, every 4th iteration bracketed with CUDA events.  Not part of the
+    #      timed region: these launch times are what a kernel costs when it does not share the SMs with three other
+    #      groups' kernels (the in-step figures above include that sharing).
+    solo = None
+    if rank == 0 and a.mode == "fixed":
+        c1 = make_cfg("fixed")
+        prof_solo = dict(prof); prof_solo["streams"] = 1
+        sv1 = ops.Solver(max_pairs=B, max_src_points=N, max_tgt_points=N, samples=N, levels=a.levels, k0=c1.k0, depth=c1.depth,
+                         width=c1.width, motion=c1.motion_type, rotation_format=c1.rotation_format, iters=min(a.iters, 24),
+                         max_break_count=10 ** 9, break_threshold_ratio=c1.break_threshold_ratio, lr=c1.lr, profile_every=4,
+                         nn_mode=a.nn_mode, mlp_mode=a.mlp, **prof_solo)
+        sv1.register(d_src, d_tgt, [f.clone() for f in flats0], sps, tps)
+        p1, n1 = sv1.profile()
+        solo = {k: v / max(n1, 1) for k, v in p1.items()}
+        solo["pairs_per_launch"] = sv1.profiled_pairs
+        sv1.close()
+
     # ---- end-to-end arm: the reference-facing API with host buffers, through the sharded evaluation loop ----------
     reg = Registration(cfg)
     all_pairs = {}                                        # global item index -> numpy clouds (this rank's only)
@@ -467,6 +485,13 @@ def main():
                     "launch_ms_note": "sampled inside the step with the other stream groups' kernels interleaved on the same SMs; "
                                       "isolated = the ncu launch (profiles/kernel_traffic.json), same pairs per launch",
                     "isolated_launch_ms": iso_ms, "isolated_frac": (bwd_flops / (iso_ms * 1e-3) / 1e12 / tensor_peak) if iso_ms else None,
+                    # the same launch covering ALL pairs of the step on a single stream (nothing else on the device), measured
+                    # live with CUDA events in this run, outside the timed region
+                    "solo": ({"pairs_per_launch": solo["pairs_per_launch"], "launch_ms": solo["warp_bwd"],
+                              "achieved": solo["pairs_per_launch"] * N * 135680 / (solo["warp_bwd"] * 1e-3) / 1e12,
+                              "frac": solo["pairs_per_launch"] * N * 135680 / (solo["warp_bwd"] * 1e-3) / 1e12 / tensor_peak,
+                              "kernel_ms_per_launch": {k: v for k, v in solo.items() if k != "pairs_per_launch"}}
+                             if solo else None),
                     # the launches of the stream groups overlap, so per-launch durations overstate the cost: the same
                     # ratio for the whole step = algorithmic MLP flops (forward 0.56 + backward 1.11 GFLOP per pair and
                     # iteration at N = 8192) of everything the step registered / the step's device time
