@@ -147,7 +147,10 @@ def check_trajectory_teacher_forced(lib, golden_dir, device):
     s_sample = dev((src - src.mean(0, keepdim=True))[sp[:512]], device)
     t_sample = dev((tgt - tgt.mean(0, keepdim=True))[tp[:512]], device)
     cfg = ops.make_layer_cfg(3, 128, -8, 1, "axis_angle", False, "SE3")
-    for it in G["keep_its"]:
+    keep = list(G["keep_its"])
+    if device == "cpu":                                     # the CPU emulation (one OS thread per CUDA thread): first, an early and the last state
+        keep = [keep[0], keep[2], keep[-1]]
+    for it in keep:
         k = f"it{int(it)}"
         params = dev(torch.from_numpy(G[f"{k}_params_before"]), device)
         pack = ops.pack_params(cfg, params, lib=lib)
@@ -252,10 +255,12 @@ def check_fp32_pipe_mode(lib, device, golden_dir):
     """mlp mode 1 (everything on the FP32 pipes) against the same golden vectors / oracle."""
     ops.set_mlp_mode(1, lib=lib)
     try:
+        small = device == "cpu"
         check_layers_against_golden(lib, golden_dir, device)
-        check_trajectory_teacher_forced(lib, golden_dir, device)
-        check_solver_against_oracle(lib, device, host=False if device != "cpu" else True, npairs=1, n=300, m=260,
-                                    samples=200, levels=2, iters=4, early_stop=False)
+        if not small:
+            check_trajectory_teacher_forced(lib, golden_dir, device)          # the CPU emulation runs one OS thread per CUDA thread: keep its case short
+        check_solver_against_oracle(lib, device, host=small, npairs=1, n=200 if small else 300, m=180 if small else 260,
+                                    samples=130 if small else 200, levels=2, iters=2 if small else 4, early_stop=False)
     finally:
         ops.set_mlp_mode(0, lib=lib)
 

@@ -65,40 +65,40 @@ def test_trajectory(lib, golden_dir):
 
 
 def test_config2_as_written_teacher_forced_sampled(lib, golden_dir):
-    """Three of the 200 steps in the emulation (all 200 + the free-running solver on the GPU: tests/test_gpu_parity.py)."""
+    """Two of the 200 steps in the emulation (all 200 + the free-running solver on the GPU: tests/test_gpu_parity.py)."""
     from parity_cases import check_config2_teacher_forced
-    check_config2_teacher_forced(lib, "cpu", golden_dir, stride=90, free_run=False)
+    check_config2_teacher_forced(lib, "cpu", golden_dir, stride=120, free_run=False)
 
 
 def test_solver_small(lib):
-    check_solver_against_oracle(lib, device="cpu", host=True, npairs=2, n=300, m=260, samples=200, levels=2,
-                                iters=5, early_stop=False)
+    check_solver_against_oracle(lib, device="cpu", host=True, npairs=2, n=200, m=180, samples=130, levels=2,
+                                iters=3, early_stop=False)
 
 
 def test_solver_early_stop_and_ragged(lib):
     # samples > cloud size for pair 1 -> ragged counts; aggressive early stop -> ragged termination
     check_solver_against_oracle(lib, device="cpu", host=True, npairs=2, n=150, m=140, samples=160, levels=2,
-                                iters=12, early_stop=True, ratio=0.05, max_break=2)
+                                iters=6, early_stop=True, ratio=0.05, max_break=2)
 
 
 def test_solver_brute_force_mode(lib):
-    check_solver_against_oracle(lib, device="cpu", host=True, npairs=1, n=300, m=260, samples=200, levels=2,
-                                iters=4, early_stop=False, nn_mode=1)
+    check_solver_against_oracle(lib, device="cpu", host=True, npairs=1, n=200, m=180, samples=130, levels=2,
+                                iters=3, early_stop=False, nn_mode=1)
 
 
 def test_culled_search_equals_brute_force(lib):
-    check_culled_search_equals_brute_force(lib, "cpu", n=330, m=300, samples=280, levels=2, iters=3)
+    check_culled_search_equals_brute_force(lib, "cpu", n=230, m=200, samples=180, levels=2, iters=2)
 
 
 def test_solver_nn_indices_bit_exact(lib):
     from parity_cases import check_solver_last_nn
-    check_solver_last_nn(lib, "cpu", n=300, m=280, samples=256, levels=1, iters=3, dup=20)
-    check_solver_last_nn(lib, "cpu", n=200, m=210, samples=192, levels=1, iters=2, lattice=True, dup=0)
-    check_solver_last_nn(lib, "cpu", n=150, m=140, samples=128, levels=1, iters=2, nn_mode=1, dup=10)
+    check_solver_last_nn(lib, "cpu", n=220, m=200, samples=192, levels=1, iters=2, dup=20)
+    check_solver_last_nn(lib, "cpu", n=140, m=150, samples=128, levels=1, iters=2, lattice=True, dup=0)
+    check_solver_last_nn(lib, "cpu", n=110, m=100, samples=96, levels=1, iters=1, nn_mode=1, dup=10)
 
 
 def test_solver_repeatable_with_early_stop(lib):
-    check_solver_repeatable(lib, "cpu", levels=2, iters=6)      # the GPU suite runs the full-size variant
+    check_solver_repeatable(lib, "cpu", n=180, m=170, samples=128, levels=2, iters=4)      # the GPU suite runs the full-size variant
 
 
 def test_fp32_pipe_mode(lib, golden_dir):

@@ -55,14 +55,14 @@ def _write_4dmatch(root, split, seqs, n, seed0):
             k += 1
 
 
-CFG = dict(iters=3, lr=0.01, max_break_count=15, break_threshold_ratio=0.001, w_reg=0.0, samples=128, m=2, k0=-8,
+CFG = dict(iters=2, lr=0.01, max_break_count=15, break_threshold_ratio=0.001, w_reg=0.0, samples=96, m=2, k0=-8,
            depth=3, width=128, motion_type="SE3", rotation_format="axis_angle")
 
 
 def test_eval_nolearned_runs_unmodified_against_the_mirror(tmp_path):
     data = tmp_path / "data"
-    _write_4dmatch(str(data), "4DMatch-F", 2, 150, 300)
-    _write_4dmatch(str(data), "4DLoMatch-F", 1, 140, 400)
+    _write_4dmatch(str(data), "4DMatch-F", 1, 140, 300)
+    _write_4dmatch(str(data), "4DLoMatch-F", 1, 130, 400)
     cfg = tmp_path / "cfg.yaml"
     cfg.write_text("gpu_mode: False\ndeformation_model: NDP\nuse_ldmk: False\nuse_depth: False\n"
                    + "".join(f"{k}: {v}\n" for k, v in CFG.items())
